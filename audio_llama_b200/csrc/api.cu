@@ -1,0 +1,604 @@
+// C ABI (include/audiollm_b200.h): argument checks, tensor-map construction, the encoder plan, constant tables.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "../../include/audiollm_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace al {
+
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ----------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+  EncodeTiledFn enc = get_encode();
+  AL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  AL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p is not 16-byte aligned", base);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      AL_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map stride %llu (dim %d) is not a multiple of 16 bytes",
+                 (unsigned long long)strides_bytes[i], i);
+      gstr[i - 1] = strides_bytes[i];
+    }
+  }
+  const CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(out, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu,%llu)", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0));
+  return 0;
+}
+
+// A operand / output: [batch][rows][cols], cols contiguous; strides in elements.
+static int tmap_rows3d(CUtensorMap* m, const void* base, int elem_bytes, uint64_t cols, uint64_t rows, uint64_t batch,
+                       uint64_t row_stride, uint64_t batch_stride, uint32_t box_cols, uint32_t box_rows) {
+  const uint64_t dims[3] = {cols, rows, batch};
+  const uint64_t str[3] = {(uint64_t)elem_bytes, row_stride * elem_bytes, batch_stride * elem_bytes};
+  const uint32_t box[3] = {box_cols, box_rows, 1};
+  return make_tmap(m, base, elem_bytes, 3, dims, str, box, true);
+}
+// W operand: [N][K] bf16.
+static int tmap_weight(CUtensorMap* m, const void* W, uint64_t N, uint64_t K) {
+  const uint64_t dims[2] = {K, N};
+  const uint64_t str[2] = {2, K * 2};
+  const uint32_t box[2] = {64, 256};
+  return make_tmap(m, W, 2, 2, dims, str, box, true);
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ----------------------------------------------------------------------------- mel tables
+static std::vector<double> linspace(double a, double b, int n) {
+  std::vector<double> v(n);
+  const double step = (b - a) / (n - 1);
+  for (int i = 0; i < n; ++i) v[i] = i * step + a;
+  v[n - 1] = b;
+  return v;
+}
+// mode 0: transformers.audio_utils.mel_filter_bank(201, n_mels, 0, 8000, 16000, norm="slaney", mel_scale="slaney")
+//         (audio_utils.py:263-333, 356-375, 527-546). mode 1: torchaudio melscale_fbanks(201, 0, 8000, n_mels,
+//         16000, norm=None, mel_scale="htk").
+// torch.linspace(start, end, steps) in float32 (ATen RangeFactories: symmetric evaluation from both ends).
+static std::vector<float> linspace_f32(float a, float b, int n) {
+  std::vector<float> v(n);
+  const float step = (b - a) / (float)(n - 1);
+  const int half = n / 2;
+  for (int i = 0; i < n; ++i) v[i] = i < half ? a + step * (float)i : b - step * (float)(n - i - 1);
+  return v;
+}
+static void build_filterbank(int n_mels, int mode, std::vector<double>& fb /*[201][n_mels]*/) {
+  const int nf = 201;
+  fb.assign((size_t)nf * n_mels, 0.0);
+  if (mode == 0) {
+    std::vector<double> hz(n_mels + 2);
+    const double logstep = 27.0 / log(6.4);
+    auto h2m = [&](double f) { return f >= 1000.0 ? 15.0 + log(f / 1000.0) * logstep : 3.0 * f / 200.0; };
+    auto m2h = [&](double m) { return m >= 15.0 ? 1000.0 * exp((log(6.4) / 27.0) * (m - 15.0)) : 200.0 * m / 3.0; };
+    std::vector<double> mel = linspace(h2m(0.0), h2m(8000.0), n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i) hz[i] = m2h(mel[i]);
+    std::vector<double> freqs = linspace(0.0, 8000.0, nf);
+    for (int k = 0; k < nf; ++k)
+      for (int m = 0; m < n_mels; ++m) {
+        const double down = (freqs[k] - hz[m]) / (hz[m + 1] - hz[m]);
+        const double up = (hz[m + 2] - freqs[k]) / (hz[m + 2] - hz[m + 1]);
+        fb[(size_t)k * n_mels + m] = fmax(0.0, fmin(down, up)) * (2.0 / (hz[m + 2] - hz[m]));
+      }
+  } else {
+    // torchaudio works in float32 tensors with python-float (double) end points; its weights are the parity
+    // target for M2, so the same float32 arithmetic is restated here.
+    const double mmin = 2595.0 * log10(1.0 + 0.0 / 700.0), mmax = 2595.0 * log10(1.0 + 8000.0 / 700.0);
+    std::vector<float> freqs = linspace_f32(0.f, 8000.f, nf);
+    std::vector<float> mel = linspace_f32((float)mmin, (float)mmax, n_mels + 2);
+    std::vector<float> hz(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i) hz[i] = 700.0f * (powf(10.0f, mel[i] / 2595.0f) - 1.0f);
+    for (int k = 0; k < nf; ++k)
+      for (int m = 0; m < n_mels; ++m) {
+        const float down = (-1.0f * (hz[m] - freqs[k])) / (hz[m + 1] - hz[m]);
+        const float up = (hz[m + 2] - freqs[k]) / (hz[m + 2] - hz[m + 1]);
+        fb[(size_t)k * n_mels + m] = (double)fmaxf(0.f, fminf(down, up));
+      }
+  }
+}
+
+struct MelDeviceTables {
+  MelTables t;
+};
+static std::mutex g_mel_mu;
+static std::map<int, MelDeviceTables> g_mel_tables;   // key = mode * 1024 + n_mels (one device per process)
+static std::map<int, std::vector<double>> g_mel_override;   // host-supplied banks (al_mel_set_filterbank_host)
+
+static int get_mel_tables(int n_mels, int mode, MelTables* out) {
+  std::lock_guard<std::mutex> lk(g_mel_mu);
+  const int key = mode * 1024 + n_mels;
+  auto it = g_mel_tables.find(key);
+  if (it != g_mel_tables.end()) {
+    *out = it->second.t;
+    return 0;
+  }
+  const double PI = 3.14159265358979323846;
+  std::vector<float> window(400);
+  for (int i = 0; i < 400; ++i) window[i] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / 400.0));   // torch.hann_window(400)
+  std::vector<float2> tw200(200), tw400(101);
+  for (int k = 0; k < 200; ++k) tw200[k] = make_float2((float)cos(2.0 * PI * k / 200.0), (float)-sin(2.0 * PI * k / 200.0));
+  for (int k = 0; k < 101; ++k) tw400[k] = make_float2((float)cos(2.0 * PI * k / 400.0), (float)-sin(2.0 * PI * k / 400.0));
+  std::vector<double> fb;
+  auto ov = g_mel_override.find(key);
+  if (ov != g_mel_override.end()) fb = ov->second;
+  else build_filterbank(n_mels, mode, fb);
+  std::vector<int> col_start(n_mels + 1, 0), nz_freq;
+  std::vector<float> nz_w;
+  for (int m = 0; m < n_mels; ++m) {
+    col_start[m] = (int)nz_w.size();
+    for (int k = 0; k < 201; ++k) {
+      const float w = (float)fb[(size_t)k * n_mels + m];
+      if (w != 0.f) {
+        nz_freq.push_back(k);
+        nz_w.push_back(w);
+      }
+    }
+  }
+  col_start[n_mels] = (int)nz_w.size();
+  if (nz_w.empty()) {   // keep cudaMalloc sizes non-zero
+    nz_freq.push_back(0);
+    nz_w.push_back(0.f);
+  }
+  MelDeviceTables d;
+  void *pw, *p2, *p4, *pc, *pf, *pz;
+  AL_CHECK_CUDA(cudaMalloc(&pw, 400 * 4));
+  AL_CHECK_CUDA(cudaMalloc(&p2, 200 * 8));
+  AL_CHECK_CUDA(cudaMalloc(&p4, 101 * 8));
+  AL_CHECK_CUDA(cudaMalloc(&pc, (n_mels + 1) * 4));
+  AL_CHECK_CUDA(cudaMalloc(&pf, nz_freq.size() * 4));
+  AL_CHECK_CUDA(cudaMalloc(&pz, nz_w.size() * 4));
+  AL_CHECK_CUDA(cudaMemcpy(pw, window.data(), 400 * 4, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(p2, tw200.data(), 200 * 8, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(p4, tw400.data(), 101 * 8, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(pc, col_start.data(), (n_mels + 1) * 4, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(pf, nz_freq.data(), nz_freq.size() * 4, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(pz, nz_w.data(), nz_w.size() * 4, cudaMemcpyHostToDevice));
+  d.t.window = (const float*)pw;
+  d.t.tw200 = (const float2*)p2;
+  d.t.tw400 = (const float2*)p4;
+  d.t.col_start = (const int*)pc;
+  d.t.nz_freq = (const int*)pf;
+  d.t.nz_w = (const float*)pz;
+  d.t.n_mels = n_mels;
+  g_mel_tables[key] = d;
+  *out = d.t;
+  return 0;
+}
+
+}  // namespace al
+
+using namespace al;
+
+// ============================================================================= encoder plan
+struct LayerW {
+  const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+  const void *wqkv, *wo, *w1, *w2;
+  CUtensorMap tm_wqkv, tm_wo, tm_w1, tm_w2;
+  bool set = false;
+};
+
+struct al_encoder {
+  int d, L, H, ffn, n_mels, c_pad, max_batch;
+  static constexpr int T_MEL = 3000, T = 1500;
+  // workspace
+  uint8_t* ws;
+  size_t ws_bytes;
+  void* melT;   // bf16 [Bm][3002][c_pad]
+  void* h1;     // bf16 [Bm][3002][d]
+  float* x;     // f32  [Bm*1500][d]
+  void* xn;     // bf16 [Bm*1500][d]
+  void* attn;   // bf16 [Bm*1500][d]
+  void* qkv;    // bf16 [Bm*1500][3d]
+  void* hff;    // bf16 [Bm*1500][ffn]
+  // stem
+  const void *conv1_w = nullptr, *conv2_w = nullptr;
+  const float *conv1_b = nullptr, *conv2_b = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
+  CUtensorMap tm_conv1_w, tm_conv2_w;
+  std::vector<LayerW> layers;
+  // activation maps (depend on B only through the flat row count)
+  int maps_B = -1;
+  CUtensorMap tm_melT_A, tm_h1_O, tm_h1_A, tm_x_O3, tm_xn_A, tm_qkv_O, tm_qkv_att, tm_attn_A, tm_x_red, tm_hff_O, tm_hff_A;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void encoder_carve(al_encoder* e, bool assign) {
+  size_t off = 0;
+  const size_t Bm = e->max_batch;
+  auto take = [&](size_t bytes) {
+    void* p = assign ? e->ws + off : nullptr;
+    off = align_up(off + bytes, 1024);
+    return p;
+  };
+  e->melT = take(Bm * 3002 * e->c_pad * 2);
+  e->h1 = take(Bm * 3002 * (size_t)e->d * 2);
+  e->x = (float*)take(Bm * 1500 * (size_t)e->d * 4);
+  e->xn = take(Bm * 1500 * (size_t)e->d * 2);
+  e->attn = take(Bm * 1500 * (size_t)e->d * 2);
+  e->qkv = take(Bm * 1500 * (size_t)e->d * 3 * 2);
+  e->hff = take(Bm * 1500 * (size_t)e->ffn * 2);
+  e->ws_bytes = off;
+}
+
+extern "C" {
+
+int al_version(void) { return 100; }
+const char* al_last_error(void) { return g_err; }
+long long al_launch_count(void) { return g_launches; }
+
+// ----------------------------------------------------------------------------- mel
+int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels, int mode,
+                   float* out, unsigned int* clip_max_ws, al_stream_t stream) {
+  AL_REQUIRE(n_clips >= 0 && n_mels > 0 && n_mels <= 256, "al_mel_forward: bad n_clips=%d / n_mels=%d", n_clips, n_mels);
+  AL_REQUIRE(mode == 0 || mode == 1, "al_mel_forward: mode must be 0 (whisper) or 1 (train), got %d", mode);
+  AL_REQUIRE(n_samples != nullptr || wave_stride >= 480000,
+             "al_mel_forward: without n_samples every clip must hold 480000 samples (wave_stride=%lld)", wave_stride);
+  AL_REQUIRE(mode == 1 || clip_max_ws != nullptr, "al_mel_forward: mode 0 needs clip_max_ws");
+  if (n_clips == 0) return 0;
+  MelTables tb;
+  int rc = get_mel_tables(n_mels, mode, &tb);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_mel(wave, n_samples, n_clips, wave_stride, tb, mode, out, clip_max_ws, st);
+  if (rc) return rc;
+  g_launches += 1;
+  if (mode == 0) {
+    rc = launch_mel_finalize(out, clip_max_ws, n_clips, n_mels, st);
+    if (rc) return rc;
+    g_launches += 1;
+  }
+  return 0;
+}
+
+int al_mel_filterbank_host(int n_mels, int mode, double* out_host) {
+  AL_REQUIRE(n_mels > 0 && out_host != nullptr && (mode == 0 || mode == 1), "al_mel_filterbank_host: bad arguments");
+  std::vector<double> fb;
+  {
+    std::lock_guard<std::mutex> lk(g_mel_mu);
+    auto ov = g_mel_override.find(mode * 1024 + n_mels);
+    if (ov != g_mel_override.end()) fb = ov->second;
+  }
+  if (fb.empty()) build_filterbank(n_mels, mode, fb);
+  memcpy(out_host, fb.data(), fb.size() * sizeof(double));
+  return 0;
+}
+
+int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host) {
+  AL_REQUIRE(n_mels > 0 && n_mels <= 256 && fb_host != nullptr && (mode == 0 || mode == 1),
+             "al_mel_set_filterbank_host: bad arguments");
+  std::lock_guard<std::mutex> lk(g_mel_mu);
+  const int key = mode * 1024 + n_mels;
+  AL_REQUIRE(g_mel_tables.find(key) == g_mel_tables.end(),
+             "al_mel_set_filterbank_host: the (n_mels=%d, mode=%d) tables are already on the device", n_mels, mode);
+  g_mel_override[key].assign(fb_host, fb_host + (size_t)201 * n_mels);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- building blocks
+int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride, int m_per_batch, int batch,
+                 const void* W, int N, int K, const float* bias, void* out, long long o_row_stride,
+                 long long o_batch_stride, int flags, const float* aux, int aux_ld, al_stream_t stream) {
+  AL_REQUIRE(m_per_batch > 0 && batch > 0 && N > 0 && K > 0, "al_gemm_bf16: bad shape m=%d batch=%d N=%d K=%d",
+             m_per_batch, batch, N, K);
+  AL_REQUIRE(K % 8 == 0, "al_gemm_bf16: K=%d must be a multiple of 8", K);
+  AL_REQUIRE(((flags & AL_EPI_ROWAUX) != 0) == (aux != nullptr), "al_gemm_bf16: AL_EPI_ROWAUX and aux must come together");
+  AL_REQUIRE(!(flags & AL_EPI_REDUCE_ADD) || (flags & AL_EPI_OUT_F32), "al_gemm_bf16: REDUCE_ADD needs OUT_F32");
+  CUtensorMap ta, tb, to;
+  int rc = tmap_rows3d(&ta, A, 2, K, m_per_batch, batch, a_row_stride, a_batch_stride, 64, 128);
+  if (rc) return rc;
+  rc = tmap_weight(&tb, W, N, K);
+  if (rc) return rc;
+  const int oe = (flags & AL_EPI_OUT_F32) ? 4 : 2;
+  rc = tmap_rows3d(&to, out, oe, N, m_per_batch, batch, o_row_stride, o_batch_stride, gemm_out_box_cols(flags), 128);
+  if (rc) return rc;
+  GemmParams p{};
+  p.m_per_batch = m_per_batch;
+  p.batch = batch;
+  p.N = N;
+  p.K = K;
+  p.bias = bias;
+  p.aux = aux;
+  p.aux_ld = aux_ld;
+  rc = launch_gemm(ta, tb, to, p, flags, num_sms(), (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int al_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int d, float eps,
+                 int out_dtype, long long out_ld, int rows_per_group, long long out_group_stride,
+                 long long out_row_offset, al_stream_t stream) {
+  int rc = launch_layernorm(x, gamma, beta, out, rows, d, eps, out_dtype, out_ld, rows_per_group, out_group_stride,
+                            out_row_offset, (cudaStream_t)stream);
+  if (rc == 0 && rows > 0) g_launches += 1;
+  return rc;
+}
+
+int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t stream) {
+  AL_REQUIRE(B > 0 && T > 0 && H > 0, "al_attention: bad shape B=%d T=%d H=%d", B, T, H);
+  CUtensorMap tm;
+  const uint64_t d3 = (uint64_t)3 * H * 64;
+  int rc = tmap_rows3d(&tm, qkv, 2, d3, T, B, d3, d3 * T, 64, 128);
+  if (rc) return rc;
+  rc = launch_attention(tm, out, B, T, H, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream) {
+  AL_REQUIRE(c_pad >= n_mels, "al_pack_mel: c_pad=%d < n_mels=%d", c_pad, n_mels);
+  int rc = launch_pack_mel(mel, out_bf16, B, n_mels, T, c_pad, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int al_f32_to_bf16(const float* x, void* out_bf16, long long n, al_stream_t stream) {
+  int rc = launch_f32_to_bf16(x, out_bf16, n, (cudaStream_t)stream);
+  if (rc == 0 && n > 0) g_launches += 1;
+  return rc;
+}
+
+// ----------------------------------------------------------------------------- encoder
+size_t al_encoder_workspace_bytes(int d_model, int n_layers, int n_heads, int ffn_dim, int n_mels, int max_batch) {
+  (void)n_layers;
+  (void)n_heads;
+  al_encoder e{};
+  e.d = d_model;
+  e.ffn = ffn_dim;
+  e.n_mels = n_mels;
+  e.c_pad = (n_mels + 63) / 64 * 64;
+  e.max_batch = max_batch;
+  encoder_carve(&e, false);
+  return e.ws_bytes;
+}
+
+int al_encoder_create(al_encoder** out, int d_model, int n_layers, int n_heads, int ffn_dim, int n_mels,
+                      int max_batch, void* workspace, size_t workspace_bytes) {
+  AL_REQUIRE(out != nullptr, "al_encoder_create: out is NULL");
+  AL_REQUIRE(d_model > 0 && n_heads > 0 && d_model == n_heads * 64,
+             "al_encoder_create: d_model=%d must be n_heads=%d x 64 (Whisper head_dim)", d_model, n_heads);
+  AL_REQUIRE(d_model % 8 == 0 && ffn_dim % 8 == 0 && n_layers >= 0 && max_batch > 0 && n_mels > 0,
+             "al_encoder_create: bad shape");
+  AL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "al_encoder_create: workspace must be 1024-byte aligned");
+  al_encoder* e = new al_encoder();
+  e->d = d_model;
+  e->L = n_layers;
+  e->H = n_heads;
+  e->ffn = ffn_dim;
+  e->n_mels = n_mels;
+  e->c_pad = (n_mels + 63) / 64 * 64;
+  e->max_batch = max_batch;
+  e->ws = (uint8_t*)workspace;
+  encoder_carve(e, true);
+  if (e->ws_bytes > workspace_bytes) {
+    set_error("al_encoder_create: workspace of %zu bytes is smaller than the %zu needed", workspace_bytes, e->ws_bytes);
+    delete e;
+    return -1;
+  }
+  e->layers.resize(n_layers);
+  // conv1 output buffer: rows 0 and 3001 of every clip are conv2's zero padding and are never written again
+  cudaError_t ce = cudaMemset(e->h1, 0, (size_t)max_batch * 3002 * d_model * 2);
+  if (ce != cudaSuccess) {
+    set_error("al_encoder_create: cudaMemset failed: %s", cudaGetErrorString(ce));
+    delete e;
+    return -2;
+  }
+  *out = e;
+  return 0;
+}
+
+int al_encoder_set_stem(al_encoder* e, const void* conv1_w, const float* conv1_b, const void* conv2_w,
+                        const float* conv2_b, const float* pos, const float* lnf_g, const float* lnf_b) {
+  AL_REQUIRE(e && conv1_w && conv1_b && conv2_w && conv2_b && pos && lnf_g && lnf_b, "al_encoder_set_stem: NULL argument");
+  e->conv1_w = conv1_w; e->conv1_b = conv1_b; e->conv2_w = conv2_w; e->conv2_b = conv2_b;
+  e->pos = pos; e->lnf_g = lnf_g; e->lnf_b = lnf_b;
+  int rc = tmap_weight(&e->tm_conv1_w, conv1_w, e->d, 3 * e->c_pad);
+  if (rc) return rc;
+  return tmap_weight(&e->tm_conv2_w, conv2_w, e->d, 3 * e->d);
+}
+
+int al_encoder_set_layer(al_encoder* e, int layer, const float* ln1_g, const float* ln1_b, const void* wqkv,
+                         const float* bqkv, const void* wo, const float* bo, const float* ln2_g, const float* ln2_b,
+                         const void* w1, const float* b1, const void* w2, const float* b2) {
+  AL_REQUIRE(e && layer >= 0 && layer < e->L, "al_encoder_set_layer: layer %d out of range", layer);
+  AL_REQUIRE(ln1_g && ln1_b && wqkv && bqkv && wo && bo && ln2_g && ln2_b && w1 && b1 && w2 && b2,
+             "al_encoder_set_layer: NULL argument");
+  LayerW& w = e->layers[layer];
+  w.ln1_g = ln1_g; w.ln1_b = ln1_b; w.wqkv = wqkv; w.bqkv = bqkv; w.wo = wo; w.bo = bo;
+  w.ln2_g = ln2_g; w.ln2_b = ln2_b; w.w1 = w1; w.b1 = b1; w.w2 = w2; w.b2 = b2;
+  int rc;
+  if ((rc = tmap_weight(&w.tm_wqkv, wqkv, 3 * e->d, e->d))) return rc;
+  if ((rc = tmap_weight(&w.tm_wo, wo, e->d, e->d))) return rc;
+  if ((rc = tmap_weight(&w.tm_w1, w1, e->ffn, e->d))) return rc;
+  if ((rc = tmap_weight(&w.tm_w2, w2, e->d, e->ffn))) return rc;
+  w.set = true;
+  return 0;
+}
+
+static int encoder_maps(al_encoder* e, int B) {
+  if (e->maps_B == B) return 0;
+  const uint64_t d = e->d, c = e->c_pad, f = e->ffn, rows = (uint64_t)B * 1500;
+  int rc;
+  // conv1: im2col row t = melT rows t..t+2 (3*c_pad contiguous), row stride c_pad, clip stride 3002*c_pad
+  if ((rc = tmap_rows3d(&e->tm_melT_A, e->melT, 2, 3 * c, 3000, B, c, 3002 * c, 64, 128))) return rc;
+  // conv1 output -> h1 rows 1..3000 of each clip
+  if ((rc = tmap_rows3d(&e->tm_h1_O, (uint8_t*)e->h1 + d * 2, 2, d, 3000, B, d, 3002 * d, 64, 128))) return rc;
+  // conv2 (stride 2): im2col row t2 = h1 rows 2*t2..2*t2+2, row stride 2*d
+  if ((rc = tmap_rows3d(&e->tm_h1_A, e->h1, 2, 3 * d, 1500, B, 2 * d, 3002 * d, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_x_O3, e->x, 4, d, 1500, B, d, 1500 * d, 32, 128))) return rc;
+  // flat [B*1500] activations
+  if ((rc = tmap_rows3d(&e->tm_xn_A, e->xn, 2, d, rows, 1, d, rows * d, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_qkv_O, e->qkv, 2, 3 * d, rows, 1, 3 * d, rows * 3 * d, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_qkv_att, e->qkv, 2, 3 * d, 1500, B, 3 * d, 1500 * 3 * d, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_attn_A, e->attn, 2, d, rows, 1, d, rows * d, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_x_red, e->x, 4, d, rows, 1, d, rows * d, 32, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_hff_O, e->hff, 2, f, rows, 1, f, rows * f, 64, 128))) return rc;
+  if ((rc = tmap_rows3d(&e->tm_hff_A, e->hff, 2, f, rows, 1, f, rows * f, 64, 128))) return rc;
+  e->maps_B = B;
+  return 0;
+}
+
+int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
+                       al_stream_t stream) {
+  AL_REQUIRE(e && mel && out, "al_encoder_forward: NULL argument");
+  AL_REQUIRE(B > 0 && B <= e->max_batch, "al_encoder_forward: B=%d outside 1..max_batch=%d", B, e->max_batch);
+  AL_REQUIRE(e->conv1_w != nullptr, "al_encoder_forward: stem weights not set");
+  const int L = (n_layers_run < 0 || n_layers_run > e->L) ? e->L : n_layers_run;
+  for (int l = 0; l < L; ++l) AL_REQUIRE(e->layers[l].set, "al_encoder_forward: layer %d weights not set", l);
+  int rc = encoder_maps(e, B);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nsm = num_sms();
+  const int d = e->d, rows = B * 1500;
+#define RUN(expr)            \
+  do {                       \
+    rc = (expr);             \
+    if (rc) return rc;       \
+    g_launches += 1;         \
+  } while (0)
+  RUN(launch_pack_mel(mel, e->melT, B, e->n_mels, 3000, e->c_pad, st));
+  {  // conv1 + GELU (modeling_whisper.py:619)
+    GemmParams p{};
+    p.m_per_batch = 3000; p.batch = B; p.N = d; p.K = 3 * e->c_pad; p.bias = e->conv1_b;
+    RUN(launch_gemm(e->tm_melT_A, e->tm_conv1_w, e->tm_h1_O, p, EPI_GELU, nsm, st));
+  }
+  {  // conv2 (stride 2) + GELU + position table (:620-625) -> fp32 residual stream
+    GemmParams p{};
+    p.m_per_batch = 1500; p.batch = B; p.N = d; p.K = 3 * d; p.bias = e->conv2_b; p.aux = e->pos; p.aux_ld = d;
+    RUN(launch_gemm(e->tm_h1_A, e->tm_conv2_w, e->tm_x_O3, p, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX, nsm, st));
+  }
+  for (int l = 0; l < L; ++l) {
+    const LayerW& w = e->layers[l];
+    RUN(launch_layernorm(e->x, w.ln1_g, w.ln1_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
+    {
+      GemmParams p{};
+      p.m_per_batch = rows; p.batch = 1; p.N = 3 * d; p.K = d; p.bias = w.bqkv;
+      RUN(launch_gemm(e->tm_xn_A, w.tm_wqkv, e->tm_qkv_O, p, 0, nsm, st));
+    }
+    RUN(launch_attention(e->tm_qkv_att, e->attn, B, 1500, e->H, st));
+    {
+      GemmParams p{};
+      p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = d; p.bias = w.bo;
+      RUN(launch_gemm(e->tm_attn_A, w.tm_wo, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
+    }
+    RUN(launch_layernorm(e->x, w.ln2_g, w.ln2_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
+    {
+      GemmParams p{};
+      p.m_per_batch = rows; p.batch = 1; p.N = e->ffn; p.K = d; p.bias = w.b1;
+      RUN(launch_gemm(e->tm_xn_A, w.tm_w1, e->tm_hff_O, p, EPI_GELU, nsm, st));
+    }
+    {
+      GemmParams p{};
+      p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = e->ffn; p.bias = w.b2;
+      RUN(launch_gemm(e->tm_hff_A, w.tm_w2, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
+    }
+  }
+  RUN(launch_layernorm(e->x, e->lnf_g, e->lnf_b, out, rows, d, 1e-5f, out_dtype, d, rows, 0, 0, st));
+#undef RUN
+  return 0;
+}
+
+float* al_encoder_hidden(al_encoder* e) { return e ? e->x : nullptr; }
+
+int al_encoder_destroy(al_encoder* e) {
+  delete e;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- projector
+int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_out, const void* W1, const float* b1,
+                         const void* W2, const float* b2, const float* gamma, const float* beta, void* h_ws,
+                         float* y_ws, void* out, int out_dtype, long long out_ld, int rows_per_group,
+                         long long out_group_stride, long long out_row_offset, al_stream_t stream) {
+  AL_REQUIRE(x && W1 && b1 && W2 && b2 && gamma && beta && h_ws && y_ws && out, "al_projector_forward: NULL argument");
+  int rc = al_gemm_bf16(x, d_in, (long long)rows * d_in, rows, 1, W1, hidden, d_in, b1, h_ws, hidden,
+                        (long long)rows * hidden, AL_EPI_GELU, nullptr, 0, stream);
+  if (rc) return rc;
+  rc = al_gemm_bf16(h_ws, hidden, (long long)rows * hidden, rows, 1, W2, d_out, hidden, b2, y_ws, d_out,
+                    (long long)rows * d_out, AL_EPI_OUT_F32, nullptr, 0, stream);
+  if (rc) return rc;
+  return al_layernorm(y_ws, gamma, beta, out, rows, d_out, 1e-5f, out_dtype, out_ld, rows_per_group, out_group_stride,
+                      out_row_offset, stream);
+}
+
+// ----------------------------------------------------------------------------- splice
+int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
+              const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
+              const void* audio_rows, void* out, float* mask_out, long long* labels_out, al_stream_t stream) {
+  AL_REQUIRE(table && input_ids && out, "al_splice: NULL argument");
+  AL_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "al_splice: elem_bytes must be 2 or 4");
+  AL_REQUIRE(B >= 0 && t_txt >= 0 && n_audio >= 0, "al_splice: negative size");
+  AL_REQUIRE(start_id >= 0 && end_id >= 0, "al_splice: negative delimiter id");
+  int rc = launch_splice(table, elem_bytes, d, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id, end_id,
+                         audio_rows, out, mask_out, labels_out, (cudaStream_t)stream);
+  if (rc == 0 && B > 0) g_launches += 1;
+  return rc;
+}
+
+int al_splice_ragged(const void* table, int elem_bytes, int d, const long long* input_ids,
+                     const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
+                     const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
+                     const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
+                     long long* labels_out, int* span_start_out, al_stream_t stream) {
+  AL_REQUIRE(table && input_ids && out && span_rows && span_src_row && n_spans && audio_rows,
+             "al_splice_ragged: NULL argument");
+  AL_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "al_splice_ragged: elem_bytes must be 2 or 4");
+  int rc = launch_splice_ragged(table, elem_bytes, d, input_ids, attn_mask, labels, B, t_txt, S_out, span_rows,
+                                span_src_row, n_spans, max_spans, audio_rows, start_id, end_id, out, mask_out,
+                                labels_out, span_start_out, (cudaStream_t)stream);
+  if (rc == 0 && B > 0) g_launches += 1;
+  return rc;
+}
+
+}  // extern "C"

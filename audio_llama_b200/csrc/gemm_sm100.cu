@@ -1,0 +1,267 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: out = epilogue(A @ W^T + bias).
+//
+//   A   : [batch][m_per_batch][K] bf16, K contiguous, arbitrary (16 B aligned) row / batch strides —
+//         the strides are what turn Whisper's conv stem into a plain GEMM (rows overlap: conv1 row stride is
+//         Cin, row length 3*Cin; conv2 row stride is 2*d, row length 3*d), see api.cu.
+//   W   : [N][K] bf16 (nn.Linear weight layout), K contiguous.
+//   out : [batch][m_per_batch][N] bf16 or fp32.
+//
+// Roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> swizzled smem -> TMA store /
+// TMA reduce-add). Operands are staged by TMA into 128B-swizzled K-major tiles; the fp32 accumulator lives
+// in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// M / N / K tails need no code: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
+//
+// Replaces, on the reference's path: every nn.Linear / Conv1d of HF WhisperEncoder
+// (modeling_whisper.py:279-282, 310, 404-406, 567-568, 619-620) and of AudioProjector
+// (/root/reference/src/models/projector.py:11-16).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace al {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int STG_BYTES = 16384;   // one epilogue staging buffer: 128 rows x 128 B
+
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * STG_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+}
+
+template <int BN, int STAGES, int FLAGS>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+  constexpr bool OUT_F32 = (FLAGS & EPI_OUT_F32) != 0;
+  constexpr bool DO_GELU = (FLAGS & EPI_GELU) != 0;
+  constexpr bool REDUCE = (FLAGS & EPI_REDUCE_ADD) != 0;
+  constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 B per row)
+  constexpr int NCHUNK = BN / CH;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sStg = sB + STAGES * B_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + 2 * STG_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int nt = t % p.tiles_n;
+        const int mt = t / p.tiles_n;
+        const int m0 = (mt % p.tiles_m_per_batch) * BM;
+        const int b = mt / p.tiles_m_per_batch;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+          tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0, b);
+          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    int s = 0, as = 0;
+    uint32_t ph = 0, aph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)   // +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          umma_commit(&empty[s]);
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;          // row inside the 128-row tile
+    const int etid = threadIdx.x - 128;
+    int as = 0;
+    uint32_t aph = 0;
+    uint32_t chunk_counter = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int nt = t % p.tiles_n;
+      const int mt = t / p.tiles_n;
+      const int m0 = (mt % p.tiles_m_per_batch) * BM;
+      const int b = mt / p.tiles_m_per_batch;
+      const int n0 = nt * BN;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NCHUNK; ++c, ++chunk_counter) {
+        float v[CH];
+        {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * CH, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if constexpr (CH == 64) {
+            tmem_ld_32x32(t_row + c * CH + 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
+          }
+        }
+        const int col0 = n0 + c * CH;
+        if (p.bias != nullptr) {
+          if (col0 + CH <= p.N) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] += __ldg(p.bias + min(col0 + j, p.N - 1));
+          }
+        }
+        if constexpr (DO_GELU) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if constexpr (ROWAUX) {
+          const int arow = min(m0 + row, p.m_per_batch - 1);
+          const float* ap = p.aux + static_cast<size_t>(arow) * p.aux_ld;
+          if (col0 + CH <= p.N) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 av = __ldg(reinterpret_cast<const float4*>(ap + col0 + j));
+              v[j] += av.x; v[j + 1] += av.y; v[j + 2] += av.z; v[j + 3] += av.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] += __ldg(ap + min(col0 + j, p.N - 1));
+          }
+        }
+        // stage into 128B-swizzled smem (row = 128 B; 16 B unit u of row r lives at u ^ (r & 7))
+        uint8_t* stg = sStg + (chunk_counter & 1) * STG_BYTES;
+        if (etid == 0) tma_wait_group_read<1>();   // the store that used this buffer two chunks ago has drained
+        named_bar_sync(1, 128);
+        uint8_t* rowp = stg + row * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint4 q;
+          if constexpr (OUT_F32) {
+            q.x = __float_as_uint(v[4 * u]); q.y = __float_as_uint(v[4 * u + 1]);
+            q.z = __float_as_uint(v[4 * u + 2]); q.w = __float_as_uint(v[4 * u + 3]);
+          } else {
+            q.x = pack_bf16(v[8 * u], v[8 * u + 1]); q.y = pack_bf16(v[8 * u + 2], v[8 * u + 3]);
+            q.z = pack_bf16(v[8 * u + 4], v[8 * u + 5]); q.w = pack_bf16(v[8 * u + 6], v[8 * u + 7]);
+          }
+          *reinterpret_cast<uint4*>(rowp + ((u ^ (row & 7)) << 4)) = q;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (etid == 0) {
+          if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stg, col0, m0, b);
+          else tma_store_3d(&tmO, stg, col0, m0, b);
+          tma_commit_group();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (etid == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+// ----------------------------------------------------------------------------- host launch
+template <int BN, int STAGES, int FLAGS>
+static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
+                      int num_sms, cudaStream_t stream) {
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<BN, STAGES, FLAGS>;
+  if (!attr_set) {
+    AL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, 256, smem, stream>>>(tmA, tmB, tmO, p);
+  AL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int gemm_tile_n(int flags) { (void)flags; return 256; }
+int gemm_out_box_cols(int flags) { return (flags & EPI_OUT_F32) ? 32 : 64; }
+
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
+                int num_sms, cudaStream_t stream) {
+  p.tiles_m_per_batch = (p.m_per_batch + BM - 1) / BM;
+  p.tiles_n = (p.N + 255) / 256;
+  switch (flags) {
+    case 0: return launch_one<256, 4, 0>(tmA, tmB, tmO, p, num_sms, stream);
+    case EPI_GELU: return launch_one<256, 4, EPI_GELU>(tmA, tmB, tmO, p, num_sms, stream);
+    case EPI_OUT_F32: return launch_one<256, 4, EPI_OUT_F32>(tmA, tmB, tmO, p, num_sms, stream);
+    case EPI_OUT_F32 | EPI_REDUCE_ADD:
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, p, num_sms, stream);
+    case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, p, num_sms, stream);
+    default:
+      set_error("launch_gemm: unsupported epilogue flags %d", flags);
+      return -1;
+  }
+}
+
+}  // namespace al

@@ -1,0 +1,72 @@
+// Internal launch interface between api.cu (the C ABI) and the kernel translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace al {
+
+// ------------------------------------------------------------------ GEMM (gemm_sm100.cu)
+enum GemmEpilogue : int {
+  EPI_GELU = 1,         // exact-erf GELU after the bias
+  EPI_OUT_F32 = 2,      // fp32 output (default bf16)
+  EPI_REDUCE_ADD = 4,   // out += result (TMA reduce-add; residual connection on the fp32 stream)
+  EPI_ROWAUX = 8,       // + aux[row_in_batch][col] (fp32; Whisper's position table)
+};
+
+struct GemmParams {
+  int m_per_batch;
+  int batch;
+  int N;
+  int K;
+  int tiles_m_per_batch;   // filled by launch_gemm
+  int tiles_n;             // filled by launch_gemm
+  const float* bias;       // [N] or nullptr
+  const float* aux;        // [m_per_batch][aux_ld] or nullptr
+  int aux_ld;
+};
+
+int gemm_out_box_cols(int flags);   // inner box extent of the output tensor map (32 fp32 / 64 bf16)
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
+                int num_sms, cudaStream_t stream);
+
+// ------------------------------------------------------------------ attention (attention_sm100.cu)
+// qkv: [B][T][3*H*64] bf16 (q pre-scaled), out: [B][T][H*64] bf16. tm_qkv: 3-D map, box {64,128,1}, SW128.
+int launch_attention(const CUtensorMap& tm_qkv, void* out, int B, int T, int H, cudaStream_t stream);
+
+// ------------------------------------------------------------------ row kernels (rowwise.cu)
+// LayerNorm over the last dim of fp32 rows. out_dtype 0 = bf16, 1 = fp32. Output row of input row r is
+// (r / rows_per_group) * out_group_stride + out_row_offset + (r % rows_per_group)   (in rows of out_ld elements),
+// which is how the projector's LayerNorm writes straight into inputs_embeds.
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int d, float eps,
+                     int out_dtype, long long out_ld, int rows_per_group, long long out_group_stride,
+                     long long out_row_offset, cudaStream_t stream);
+// mel [B][n_mels][T] fp32 -> time-major bf16 [B][T+2][c_pad], rows 0 and T+1 and channels >= n_mels zero.
+int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c_pad, cudaStream_t stream);
+// Splice gather (S1/S2): see include/audiollm_b200.h al_splice.
+int launch_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
+                  const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
+                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, cudaStream_t stream);
+int launch_splice_ragged(const void* table, int elem_bytes, int d, const long long* input_ids,
+                         const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
+                         const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
+                         const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
+                         long long* labels_out, int* span_start_out, cudaStream_t stream);
+int launch_f32_to_bf16(const float* x, void* out, long long n, cudaStream_t stream);
+
+// ------------------------------------------------------------------ mel (mel.cu)
+struct MelTables {
+  const float* window;     // [400]
+  const float2* tw200;     // [200] exp(-2 pi i k / 200)
+  const float2* tw400;     // [101] exp(-2 pi i k / 400)
+  const int* col_start;    // [n_mels + 1] CSC offsets into nz_*
+  const int* nz_freq;      // [nnz]
+  const float* nz_w;       // [nnz]
+  int n_mels;
+};
+// mode 0: whisper (log10, per-clip max written to clip_max for finalize); mode 1: ln(x + 1e-9).
+int launch_mel(const float* wave, const int* n_samples, int B, long long wave_stride, const MelTables& tb, int mode,
+               float* out, unsigned int* clip_max_bits, cudaStream_t stream);
+int launch_mel_finalize(float* out, const unsigned int* clip_max_bits, int B, int n_mels, cudaStream_t stream);
+
+}  // namespace al

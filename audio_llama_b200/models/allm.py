@@ -1,0 +1,165 @@
+"""AudioLLM — the reference's model-module API (/root/reference/src/models/allm.py:8-348) with the
+audio-conditioning path running on hand-written sm_100a kernels:
+
+  _process_audio_features  -> al_encoder_forward      (frozen Whisper encoder, E1/E2)
+  projector                -> al_projector_forward    (P1)
+  _combine_text_and_audio_embeddings / _extend_attention_mask / label extension -> al_splice (S1/S2)
+
+Same constructor, attributes (.llama, .whisper_encoder, .projector, .lora_layers, .hooks, .tokenizer,
+.audio_start_token/.audio_end_token), method names, argument meaning and error behaviour. The LLaMA forward /
+generate tail stays stock HF (out of scope). Differences, on purpose: none of the reference's print() calls
+(allm.py:18,83,88-89,121-122,137,172,217), and the dead conv1/2/3 subsampler (allm.py:39-43) is not built.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import base as _base
+from .lora import apply_lora_to_llama, lora_forward_hook
+from .projector import AudioProjector
+
+
+class AudioLLM(nn.Module):
+    def __init__(self, llama_path, whisper_path, lora_rank=64):
+        super().__init__()
+        # looked up through the module so tests can patch `models.base.load_base_models` like the reference's do
+        self.llama, self.whisper_encoder = _base.load_base_models(llama_path, whisper_path)
+
+        whisper_dim = self.whisper_encoder.model.config.d_model
+        llama_dim = self.llama.model.config.hidden_size
+        self.projector = AudioProjector(whisper_dim, llama_dim)
+
+        self.lora_layers = apply_lora_to_llama(self.llama.model, rank=lora_rank)
+        self.hooks = []
+        for name, module in self.llama.model.named_modules():
+            if name in self.lora_layers:
+                hook = module.register_forward_hook(
+                    lambda mod, inp, out, n=name: lora_forward_hook(mod, inp, out, self.lora_layers[n]))
+                self.hooks.append(hook)
+
+        self.audio_start_token = "<audio>"
+        self.audio_end_token = "</audio>"
+        self.tokenizer = None
+
+    # ------------------------------------------------------------------ forward (allm.py:47-106)
+    def forward(self, input_ids=None, attention_mask=None, audio_features=None, labels=None, **kwargs):
+        device = input_ids.device
+        if next(self.llama.model.parameters()).device != device:
+            self.llama.model = self.llama.model.to(device)
+
+        if audio_features is not None:
+            combined_embeddings, combined_attention_mask, adjusted_labels = self._conditioned_inputs(
+                input_ids, attention_mask, audio_features, labels)
+        else:
+            combined_embeddings = self.llama.model.model.embed_tokens(input_ids)
+            combined_attention_mask = attention_mask
+            adjusted_labels = labels
+
+        return self.llama.model(inputs_embeds=combined_embeddings, attention_mask=combined_attention_mask,
+                                labels=adjusted_labels, **kwargs)
+
+    def _delimiter_ids(self):
+        audio_start_id = self.tokenizer.convert_tokens_to_ids(self.audio_start_token)
+        audio_end_id = self.tokenizer.convert_tokens_to_ids(self.audio_end_token)
+        vocab_size = self.llama.model.model.embed_tokens.weight.shape[0]
+        if audio_start_id >= vocab_size or audio_end_id >= vocab_size:
+            raise ValueError(f"Token IDs {audio_start_id}, {audio_end_id} are outside vocabulary size {vocab_size}")
+        return audio_start_id, audio_end_id
+
+    def _conditioned_inputs(self, input_ids, attention_mask, audio_features, labels):
+        """Encoder -> projector -> one splice launch producing embeds, fp32 mask and labels together."""
+        start_id, end_id = self._delimiter_ids()
+        table = self.llama.model.model.embed_tokens.weight
+        processed_audio = self._process_audio_features(audio_features)
+        projected_audio = self.projector(processed_audio)                       # autograd-tracked (trainable)
+        B, A, _ = projected_audio.shape
+        emb, mask, lab = ops.splice(table.detach(), input_ids, attention_mask, labels, A, start_id, end_id,
+                                    audio_rows=None)
+        # audio rows go in through autograd so the projector still receives gradients
+        combined = torch.cat([emb[:, :1], projected_audio.to(emb.dtype), emb[:, A + 1:]], dim=1) \
+            if projected_audio.requires_grad else self._place(emb, projected_audio, A)
+        return combined, mask, lab
+
+    @staticmethod
+    def _place(emb, projected_audio, A):
+        emb[:, 1:1 + A] = projected_audio.to(emb.dtype)
+        return emb
+
+    # ------------------------------------------------------------------ allm.py:109-174
+    def _combine_text_and_audio_embeddings(self, text_embeddings, audio_features, input_ids):
+        if audio_features is None:
+            return text_embeddings
+        start_id, end_id = self._delimiter_ids()
+        processed_audio = self._process_audio_features(audio_features)
+        projected_audio = self.projector(processed_audio)
+        table = self.llama.model.model.embed_tokens.weight
+        A = projected_audio.shape[1]
+        emb, _, _ = ops.splice(table.detach(), input_ids, None, None, A, start_id, end_id, audio_rows=None,
+                               want_mask=False, want_labels=False)
+        if projected_audio.requires_grad:
+            return torch.cat([emb[:, :1], projected_audio.to(emb.dtype), emb[:, A + 1:]], dim=1)
+        return self._place(emb, projected_audio, A)
+
+    # ------------------------------------------------------------------ allm.py:176-196
+    def _extend_attention_mask(self, attention_mask, audio_seq_len, has_special_tokens=True):
+        batch_size, text_seq_len = attention_mask.shape
+        total_audio_len = audio_seq_len + 2 if has_special_tokens else audio_seq_len
+        audio_attention = torch.ones(batch_size, total_audio_len, device=attention_mask.device)
+        return torch.cat([audio_attention, attention_mask], dim=1)
+
+    # ------------------------------------------------------------------ allm.py:198-221
+    def _process_audio_features(self, audio_features):
+        device = audio_features.device
+        if next(self.whisper_encoder.model.parameters()).device != device:
+            self.whisper_encoder.model = self.whisper_encoder.model.to(device)
+        audio_features = audio_features.squeeze(1)
+        with torch.no_grad():
+            whisper_output = self.whisper_encoder.model(audio_features)
+            return whisper_output.last_hidden_state
+
+    def get_trainable_params(self):
+        """Return only trainable parameters (projector + LoRA) — allm.py:244-249."""
+        params = list(self.projector.parameters())
+        for lora in self.lora_layers.values():
+            params.extend(list(lora.parameters()))
+        return params
+
+    def to(self, device):
+        self.llama.to(device)
+        self.whisper_encoder.to(device)
+        self.projector = self.projector.to(device)
+        for layer_name in self.lora_layers:
+            self.lora_layers[layer_name] = self.lora_layers[layer_name].to(device)
+        return super().to(device)
+
+    # ------------------------------------------------------------------ allm.py:263-348
+    def generate(self, input_ids=None, attention_mask=None, audio_features=None, max_new_tokens=256,
+                 temperature=0.7, top_p=0.9, do_sample=True, **kwargs):
+        self.eval()
+        text_len = input_ids.shape[1]
+        with torch.no_grad():
+            if audio_features is not None:
+                combined_embeddings, combined_attention_mask, _ = self._conditioned_inputs(
+                    input_ids, attention_mask, audio_features, None)
+                audio_seq_len = combined_embeddings.shape[1] - text_len
+            else:
+                combined_embeddings = self.llama.model.model.embed_tokens(input_ids)
+                combined_attention_mask = attention_mask
+        tok = self.tokenizer
+        generation_config = {
+            "max_new_tokens": max_new_tokens, "temperature": temperature, "top_p": top_p, "do_sample": do_sample,
+            "pad_token_id": tok.pad_token_id if tok is not None else None,
+            "bos_token_id": tok.bos_token_id if tok is not None else None,
+            "eos_token_id": tok.eos_token_id if tok is not None else None,
+        }
+        generation_config.update(kwargs)
+        with torch.no_grad():
+            outputs = self.llama.model.generate(inputs_embeds=combined_embeddings,
+                                                attention_mask=combined_attention_mask, **generation_config)
+        input_length = text_len + (audio_seq_len if audio_features is not None else 0)
+        generated_tokens = outputs[0, input_length:]
+        if tok is not None:
+            return tok.decode(generated_tokens, skip_special_tokens=True)
+        return generated_tokens

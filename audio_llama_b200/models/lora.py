@@ -1,0 +1,50 @@
+"""LoRA — same names and semantics as the reference (/root/reference/src/models/lora.py:6-43):
+`LoRALayer(in_dim, out_dim, rank=8, alpha=16)` with `lora_A [rank, in]` (zeros), `lora_B [out, rank]`
+(N(0, 0.01)), `scaling = alpha / rank`; `apply_lora_to_llama` matches q/k/v/gate/up/down by substring;
+`lora_forward_hook` returns `output + lora(x)`.
+
+What changes is the arithmetic order: the reference materialises the dense [out, in] delta `B @ A` on every
+call and runs a second full-size GEMM (lora.py:20-21). Here the update is the rank-r side path
+`(x @ A^T) @ B^T * scaling` — 2*M*r*(in+out) FLOPs instead of 2*out*in*r + 2*M*in*out — identical in exact
+arithmetic, within fp32 round-off in practice (tests/test_lora.py pins it to the reference's own output).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+
+class LoRALayer(nn.Module):
+    def __init__(self, in_dim, out_dim, rank=8, alpha=16):
+        super().__init__()
+        self.lora_A = nn.Parameter(torch.zeros(rank, in_dim))
+        self.lora_B = nn.Parameter(torch.randn(out_dim, rank) * 0.01)
+        self.rank = rank
+        self.alpha = alpha
+        self.scaling = alpha / rank
+        nn.init.zeros_(self.lora_A)
+        nn.init.normal_(self.lora_B, std=0.01)
+
+    def forward(self, x):
+        # rank-r side path; never forms the [out, in] matrix
+        a = self.lora_A.to(x.dtype)
+        b = self.lora_B.to(x.dtype)
+        return ((x @ a.T) @ b.T) * self.scaling
+
+
+def apply_lora_to_llama(llama_model, rank=8, alpha=16, target_modules=None):
+    """Returns {qualified module name: LoRALayer} for every nn.Linear whose name contains a target
+    (lora.py:23-39)."""
+    if target_modules is None:
+        target_modules = ['q_proj', 'k_proj', 'v_proj', 'gate_proj', 'up_proj', 'down_proj']
+    lora_layers = {}
+    for name, module in llama_model.named_modules():
+        if isinstance(module, nn.Linear):
+            if any(target_name in name for target_name in target_modules):
+                lora_layers[name] = LoRALayer(module.in_features, module.out_features, rank, alpha)
+    return lora_layers
+
+
+def lora_forward_hook(module, input, output, lora_layer):
+    """Add LoRA output to the original linear layer output (lora.py:41-43)."""
+    return output + lora_layer(input[0])

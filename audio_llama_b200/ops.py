@@ -1,0 +1,195 @@
+"""Torch-tensor wrappers over the C ABI. PyTorch is plumbing here (device memory, streams); every
+function launches hand-written sm_100a kernels from libaudiollm_sm100.so and raises if that fails."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+EPI_GELU, EPI_OUT_F32, EPI_REDUCE_ADD, EPI_ROWAUX = 1, 2, 4, 8
+MEL_WHISPER, MEL_TRAIN = 0, 1
+N_FRAMES = 3000
+
+
+def _req(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def mel_forward(wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None, n_mels: int = 128,
+                mode: int = MEL_WHISPER, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """wave [B, n] float32 (n >= 480000 unless n_samples is given) -> [B, n_mels, 3000] float32."""
+    _req(wave, torch.float32, "wave")
+    B, n = wave.shape
+    if n_samples is None and n < 480000:
+        n_samples = torch.full((B,), n, dtype=torch.int32, device=wave.device)
+    if n_samples is not None:
+        _req(n_samples, torch.int32, "n_samples")
+    if out is None:
+        out = torch.empty(B, n_mels, N_FRAMES, dtype=torch.float32, device=wave.device)
+    ws = torch.empty(max(B, 1), dtype=torch.int32, device=wave.device)
+    if mode == MEL_TRAIN:
+        _ensure_train_bank(n_mels)
+    check(lib().al_mel_forward(ptr(wave), ptr(n_samples), B, n, n_mels, mode, ptr(out), ptr(ws), stream_ptr()),
+          "al_mel_forward")
+    return out
+
+
+_train_bank_installed = set()
+
+
+def htk_filterbank_torch(n_mels: int) -> torch.Tensor:
+    """The HTK bank exactly as torchaudio.functional.melscale_fbanks(201, 0, 8000, n_mels, 16000, norm=None,
+    mel_scale="htk") builds it (float32 torch ops; TA functional.py:518-580) — what
+    /root/reference/src/dataset.py:125-131 ends up using. Returns float32 [201, n_mels]."""
+    import math
+    all_freqs = torch.linspace(0, 8000, 201)
+    m_min = 2595.0 * math.log10(1.0 + 0.0 / 700.0)
+    m_max = 2595.0 * math.log10(1.0 + 8000.0 / 700.0)
+    m_pts = torch.linspace(m_min, m_max, n_mels + 2)
+    f_pts = 700.0 * (10 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.max(torch.zeros(1), torch.min(down, up))
+
+
+def _ensure_train_bank(n_mels: int):
+    if n_mels in _train_bank_installed:
+        return
+    fb = htk_filterbank_torch(n_mels).double().contiguous().numpy()
+    check(lib().al_mel_set_filterbank_host(n_mels, MEL_TRAIN, fb.ctypes.data), "al_mel_set_filterbank_host")
+    _train_bank_installed.add(n_mels)
+
+
+def mel_filterbank(n_mels: int, mode: int = MEL_WHISPER):
+    if mode == MEL_TRAIN:
+        _ensure_train_bank(n_mels)
+    import numpy as np
+    fb = np.empty((201, n_mels), dtype=np.float64)
+    check(lib().al_mel_filterbank_host(n_mels, mode, fb.ctypes.data), "al_mel_filterbank_host")
+    return fb
+
+
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0,
+              out: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """epilogue(a @ w.T + bias): a [M, K] or [batch, M, K] bf16, w [N, K] bf16. With EPI_REDUCE_ADD `out` (fp32)
+    is accumulated into."""
+    _req(a, torch.bfloat16, "a")
+    _req(w, torch.bfloat16, "w")
+    a3 = a if a.dim() == 3 else a.unsqueeze(0)
+    batch, M, K = a3.shape
+    N = w.shape[0]
+    odt = torch.float32 if flags & EPI_OUT_F32 else torch.bfloat16
+    if out is None:
+        if flags & EPI_REDUCE_ADD:
+            raise ValueError("EPI_REDUCE_ADD needs an existing `out`")
+        out = torch.empty(*a.shape[:-1], N, dtype=odt, device=a.device)
+    _req(out, odt, "out")
+    if bias is not None:
+        _req(bias, torch.float32, "bias")
+    if aux is not None:
+        _req(aux, torch.float32, "aux")
+    check(lib().al_gemm_bf16(ptr(a), K, M * K, M, batch, ptr(w), N, K, ptr(bias), ptr(out), N, M * N, flags,
+                             ptr(aux), aux.shape[-1] if aux is not None else 0, stream_ptr()), "al_gemm_bf16")
+    return out
+
+
+def gemm_bf16_strided(a_base: torch.Tensor, a_row_stride: int, a_batch_stride: int, m_per_batch: int, batch: int,
+                      w: torch.Tensor, bias, out_base: torch.Tensor, o_row_stride: int, o_batch_stride: int,
+                      flags: int = 0, aux=None):
+    """Raw-stride form (overlapping rows allowed): what the conv stem uses."""
+    N, K = w.shape
+    check(lib().al_gemm_bf16(ptr(a_base), a_row_stride, a_batch_stride, m_per_batch, batch, ptr(w), N, K, ptr(bias),
+                             ptr(out_base), o_row_stride, o_batch_stride, flags, ptr(aux),
+                             aux.shape[-1] if aux is not None else 0, stream_ptr()), "al_gemm_bf16")
+    return out_base
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out_dtype=torch.bfloat16, out: Optional[torch.Tensor] = None, rows_per_group: Optional[int] = None,
+              out_group_stride: int = 0, out_row_offset: int = 0) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    d = x.shape[-1]
+    rows = x.numel() // d
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        rows_per_group, out_group_stride, out_row_offset = max(rows, 1), 0, 0
+    elif rows_per_group is None:
+        rows_per_group, out_group_stride, out_row_offset = max(rows, 1), 0, 0
+    check(lib().al_layernorm(ptr(x), ptr(_req(gamma, torch.float32, "gamma")), ptr(_req(beta, torch.float32, "beta")),
+                             ptr(out), rows, d, eps, 1 if out.dtype == torch.float32 else 0, out.shape[-1],
+                             rows_per_group, out_group_stride, out_row_offset, stream_ptr()), "al_layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, n_heads: int) -> torch.Tensor:
+    """qkv [B, T, 3*H*64] bf16 (q pre-scaled) -> [B, T, H*64] bf16."""
+    _req(qkv, torch.bfloat16, "qkv")
+    B, T, d3 = qkv.shape
+    if d3 != 3 * n_heads * 64:
+        raise ValueError("attention kernel is head_dim 64 only")
+    out = torch.empty(B, T, n_heads * 64, dtype=torch.bfloat16, device=qkv.device)
+    check(lib().al_attention(ptr(qkv), ptr(out), B, T, n_heads, stream_ptr()), "al_attention")
+    return out
+
+
+def pack_mel(mel: torch.Tensor, c_pad: int) -> torch.Tensor:
+    _req(mel, torch.float32, "mel")
+    B, n_mels, T = mel.shape
+    out = torch.empty(B, T + 2, c_pad, dtype=torch.bfloat16, device=mel.device)
+    check(lib().al_pack_mel(ptr(mel), ptr(out), B, n_mels, T, c_pad, stream_ptr()), "al_pack_mel")
+    return out
+
+
+def f32_to_bf16(x: torch.Tensor) -> torch.Tensor:
+    _req(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().al_f32_to_bf16(ptr(x), ptr(out), x.numel(), stream_ptr()), "al_f32_to_bf16")
+    return out
+
+
+def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
+           labels: Optional[torch.Tensor], n_audio: int, start_id: int, end_id: int,
+           audio_rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           want_mask: bool = True, want_labels: bool = True):
+    """S1/S2. Returns (inputs_embeds [B, n_audio+2+T, d], mask float32 | None, labels int64 | None).
+    With audio_rows=None rows 1..n_audio of `out` are left for the projector to fill in place."""
+    if not table.is_cuda or not table.is_contiguous():
+        raise ValueError("table must be a contiguous CUDA tensor")
+    if table.dtype not in (torch.bfloat16, torch.float32, torch.float16):
+        raise TypeError("embedding table must be bf16 / fp16 / fp32")
+    _req(input_ids, torch.int64, "input_ids")
+    vocab, d = table.shape
+    if start_id >= vocab or end_id >= vocab:
+        # same check and message as the reference (allm.py:140-141)
+        raise ValueError(f"Token IDs {start_id}, {end_id} are outside vocabulary size {vocab}")
+    B, T = input_ids.shape
+    S = n_audio + 2 + T
+    if out is None:
+        out = torch.empty(B, S, d, dtype=table.dtype, device=table.device)
+    if audio_rows is not None:
+        if audio_rows.dtype != table.dtype or not audio_rows.is_contiguous():
+            raise TypeError("audio_rows must be contiguous and of the table's dtype")
+    if attention_mask is not None:
+        _req(attention_mask, torch.int64, "attention_mask")
+    if labels is not None:
+        _req(labels, torch.int64, "labels")
+    mask_out = torch.empty(B, S, dtype=torch.float32, device=table.device) if want_mask else None
+    labels_out = torch.empty(B, S, dtype=torch.int64, device=table.device) if (want_labels and labels is not None) else None
+    check(lib().al_splice(ptr(table), table.element_size(), d, ptr(input_ids), ptr(attention_mask), ptr(labels), B, T,
+                          n_audio, start_id, end_id, ptr(audio_rows), ptr(out), ptr(mask_out), ptr(labels_out),
+                          stream_ptr()), "al_splice")
+    return out, mask_out, labels_out
+
+
+def launch_count() -> int:
+    return int(lib().al_launch_count())

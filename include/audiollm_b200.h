@@ -1,0 +1,136 @@
+/* audiollm_b200 — C ABI of the B200 (sm_100a) audio-conditioning path.
+ *
+ * The reference (cdreetz/audio-llama) has no FFI: its seam is the Python module API under
+ * /root/reference/src/models plus HuggingFace calls. Each entry point below names the reference
+ * interface it replaces; the Python host side (audio_llama_b200/) binds them with ctypes and keeps the
+ * reference's module / method names (INTEGRATION.md shows the binding).
+ *
+ * Conventions: every pointer is a DEVICE pointer unless the name ends in _host; every function is
+ * asynchronous on `stream` (a cudaStream_t), returns 0 on success, -1 on an argument error, -2 on a CUDA
+ * error (al_last_error() has the text), never throws and never allocates on the hot path (workspaces are
+ * passed in; the only library-owned device memory is the constant tables built on first use per process:
+ * FFT twiddles, Hann window, mel filter bank). Caller guarantees dtype, contiguity and 16-byte alignment.
+ * bf16 = raw __nv_bfloat16 bits (torch.bfloat16).
+ */
+#ifndef AUDIOLLM_B200_H
+#define AUDIOLLM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* al_stream_t; /* cudaStream_t */
+
+int al_version(void);
+const char* al_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long al_launch_count(void);
+
+/* ---- M1 / M2: log-mel features --------------------------------------------------------------------
+ * Replaces WhisperFeatureExtractor.__call__ -> _torch_extract_fbank_features
+ * (transformers/models/whisper/feature_extraction_whisper.py:135-164, 296-303) as called by
+ * process_audio, /root/reference/src/inference.py:100-105 (mode 0), and the MelSpectrogram + log of
+ * AudioLLMDataset._process_audio, /root/reference/src/dataset.py:125-133 (mode 1).
+ *   wave       [n_clips][wave_stride] float32 mono 16 kHz
+ *   n_samples  [n_clips] int32 valid samples per clip (NULL = wave_stride); clips are zero-padded /
+ *              truncated to 480 000 samples exactly as the reference does
+ *   out        [n_clips][n_mels][3000] float32
+ *   clip_max_ws[n_clips] uint32 scratch (mode 0)
+ */
+int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels,
+                   int mode, float* out, unsigned int* clip_max_ws, al_stream_t stream);
+/* Host-side copy of the filter bank the kernel uses, [201][n_mels] float64 row-major (for parity tests
+ * against transformers.audio_utils.mel_filter_bank / torchaudio melscale_fbanks). */
+int al_mel_filterbank_host(int n_mels, int mode, double* out_host);
+/* Install a caller-built bank [201][n_mels] float64 for (n_mels, mode) before its first use. The host side uses
+ * this for mode 1: torchaudio builds the HTK bank with float32 torch ops whose last-ulp behaviour moves the very
+ * narrow low filters by ~1e-3 relative, so the bank is rebuilt with the same torch ops and handed in. */
+int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host);
+
+/* ---- building blocks ------------------------------------------------------------------------------ */
+/* epilogue flags for al_gemm_bf16* */
+#define AL_EPI_GELU 1
+#define AL_EPI_OUT_F32 2
+#define AL_EPI_REDUCE_ADD 4
+#define AL_EPI_ROWAUX 8
+
+/* out = epilogue(A @ W^T + bias).  A [batch][m_per_batch][K] bf16 with row / batch strides in ELEMENTS
+ * (rows may overlap — the conv stem uses that), W [N][K] bf16 (nn.Linear layout), bias [N] f32 or NULL,
+ * out [batch][m_per_batch][N] bf16 (or f32 with AL_EPI_OUT_F32), aux [m_per_batch][aux_ld] f32.
+ * Replaces nn.Linear / nn.Conv1d forward (cuBLAS / cuDNN in the reference's stack). */
+int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride, int m_per_batch, int batch,
+                 const void* W, int N, int K, const float* bias, void* out, long long o_row_stride,
+                 long long o_batch_stride, int flags, const float* aux, int aux_ld, al_stream_t stream);
+
+/* LayerNorm(x[rows][d] f32) -> out (out_dtype 0 bf16 / 1 f32). Output row of input row r:
+ * (r / rows_per_group) * out_group_stride + out_row_offset + r % rows_per_group, rows of out_ld elements. */
+int al_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int d, float eps,
+                 int out_dtype, long long out_ld, int rows_per_group, long long out_group_stride,
+                 long long out_row_offset, al_stream_t stream);
+
+/* softmax(Q K^T) V, no mask, head_dim 64, q pre-scaled. qkv [B][T][3*H*64] bf16 -> out [B][T][H*64] bf16.
+ * Replaces WhisperAttention's attention_interface call (modeling_whisper.py:339-349). */
+int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t stream);
+
+int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream);
+int al_f32_to_bf16(const float* x, void* out_bf16, long long n, al_stream_t stream);
+
+/* ---- E1/E2: frozen Whisper encoder forward --------------------------------------------------------
+ * Replaces AudioLLM._process_audio_features (/root/reference/src/models/allm.py:198-221) ->
+ * WhisperEncoder.forward (transformers/models/whisper/modeling_whisper.py:593-647).
+ * Weights are bf16 matrices packed by the host (audio_llama_b200/encoder.py): conv weights as
+ * [d][3*c_in] with column kk*c_in+ci, wqkv = [q*hd^-0.5 ; k ; v] ([3d][d]), biases / LayerNorm / position
+ * table in f32. The plan keeps pointers only; the caller owns weights and workspace. */
+typedef struct al_encoder al_encoder;
+size_t al_encoder_workspace_bytes(int d_model, int n_layers, int n_heads, int ffn_dim, int n_mels, int max_batch);
+int al_encoder_create(al_encoder** out, int d_model, int n_layers, int n_heads, int ffn_dim, int n_mels,
+                      int max_batch, void* workspace, size_t workspace_bytes);
+int al_encoder_set_stem(al_encoder* e, const void* conv1_w, const float* conv1_b, const void* conv2_w,
+                        const float* conv2_b, const float* pos, const float* lnf_g, const float* lnf_b);
+int al_encoder_set_layer(al_encoder* e, int layer, const float* ln1_g, const float* ln1_b, const void* wqkv,
+                         const float* bqkv, const void* wo, const float* bo, const float* ln2_g,
+                         const float* ln2_b, const void* w1, const float* b1, const void* w2, const float* b2);
+/* mel [B][n_mels][3000] f32 -> out [B][1500][d] (out_dtype 0 bf16 / 1 f32). n_layers_run < 0 = all. */
+int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
+                       al_stream_t stream);
+/* fp32 residual stream [max_batch*1500][d] inside the workspace (tests read intermediate states). */
+float* al_encoder_hidden(al_encoder* e);
+int al_encoder_destroy(al_encoder* e);
+
+/* ---- P1: AudioProjector forward -------------------------------------------------------------------
+ * Replaces AudioProjector.forward (/root/reference/src/models/projector.py:18-19):
+ * LN(W2 gelu(W1 x + b1) + b2). x [rows][d_in] bf16; W1 [hidden][d_in], W2 [d_out][hidden] bf16; h_ws
+ * [rows][hidden] bf16 and y_ws [rows][d_out] f32 scratch. The LayerNorm stores with al_layernorm's row
+ * mapping, i.e. straight into inputs_embeds[b, 1 + t] when out = inputs_embeds,
+ * rows_per_group = 1500, out_group_stride = S, out_row_offset = 1. */
+int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_out, const void* W1, const float* b1,
+                         const void* W2, const float* b2, const float* gamma, const float* beta, void* h_ws,
+                         float* y_ws, void* out, int out_dtype, long long out_ld, int rows_per_group,
+                         long long out_group_stride, long long out_row_offset, al_stream_t stream);
+
+/* ---- S1 / S2: splice ------------------------------------------------------------------------------
+ * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask
+ * (allm.py:176-196) and the label extension (allm.py:81-89). Row map per sample (bit-exact contract):
+ * 0 <- table[start_id]; 1..n_audio <- audio rows; n_audio+1 <- table[end_id]; n_audio+2+j <- table[ids[j]].
+ *   table [vocab][d] (elem_bytes 2 or 4), input_ids / attn_mask / labels [B][t_txt] int64 (mask, labels may
+ *   be NULL), audio_rows [B][n_audio][d] or NULL when the projector already wrote them in place,
+ *   out [B][n_audio+2+t_txt][d]; mask_out float32, labels_out int64 (either may be NULL).
+ * The delimiter-id bounds check (ValueError, allm.py:140-141) is the host wrapper's job. */
+int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
+              const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
+              const void* audio_rows, void* out, float* mask_out, long long* labels_out, al_stream_t stream);
+/* Ragged extension (config 5; not in the reference): see audio_llama_b200/splice.py. span_start_out
+ * [B][max_spans] int32 receives the device-computed exclusive prefix sums. */
+int al_splice_ragged(const void* table, int elem_bytes, int d, const long long* input_ids,
+                     const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
+                     const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
+                     const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
+                     long long* labels_out, int* span_start_out, al_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOLLM_B200_H */
