@@ -38,6 +38,8 @@ SIGNATURES = {
     "al_encoder_set_layer": (i32, [vp, i32] + [vp] * 12),
     "al_encoder_forward": (i32, [vp, vp, i32, vp, i32, i32, vp]),
     "al_encoder_hidden": (vp, [vp]),
+    "al_encoder_set_profiling": (i32, [vp, i32]),
+    "al_encoder_profile_read": (i32, [vp, vp, vp]),
     "al_encoder_destroy": (i32, [vp]),
     "al_projector_forward": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i64, i32, i64, i64, vp]),
     "al_splice": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp]),

@@ -247,6 +247,11 @@ struct al_encoder {
   const float *conv1_b = nullptr, *conv2_b = nullptr, *pos = nullptr, *lnf_g = nullptr, *lnf_b = nullptr;
   CUtensorMap tm_conv1_w, tm_conv2_w;
   std::vector<LayerW> layers;
+  // optional live profiling: CUDA events around every launch of a forward, on the launch stream
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;          // pairs, appended per launch
+  std::vector<int> ev_kind;
+  size_t ev_used = 0;
   // activation maps (depend on B only through the flat row count)
   int maps_B = -1;
   CUtensorMap tm_melT_A, tm_h1_O, tm_h1_A, tm_x_O3, tm_xn_A, tm_qkv_O, tm_qkv_att, tm_attn_A, tm_x_red, tm_hff_O, tm_hff_A;
@@ -466,6 +471,23 @@ int al_encoder_set_layer(al_encoder* e, int layer, const float* ln1_g, const flo
   return 0;
 }
 
+static int prof_events(al_encoder* e, int kind, cudaEvent_t* e0, cudaEvent_t* e1) {
+  if (e->ev_used + 2 > e->ev.size()) {
+    if (e->ev.size() >= 2 * 65536) return -1;     // cap: stop recording rather than grow without bound
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t ev;
+      if (cudaEventCreate(&ev) != cudaSuccess) return -1;
+      e->ev.push_back(ev);
+    }
+    e->ev_kind.push_back(kind);
+  }
+  e->ev_kind[e->ev_used / 2] = kind;
+  *e0 = e->ev[e->ev_used];
+  *e1 = e->ev[e->ev_used + 1];
+  e->ev_used += 2;
+  return 0;
+}
+
 static int encoder_maps(al_encoder* e, int B) {
   if (e->maps_B == B) return 0;
   const uint64_t d = e->d, c = e->c_pad, f = e->ffn, rows = (uint64_t)B * 1500;
@@ -501,57 +523,87 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
   cudaStream_t st = (cudaStream_t)stream;
   const int nsm = num_sms();
   const int d = e->d, rows = B * 1500;
-#define RUN(expr)            \
-  do {                       \
-    rc = (expr);             \
-    if (rc) return rc;       \
-    g_launches += 1;         \
+#define RUN(kind, expr)                                                   \
+  do {                                                                    \
+    cudaEvent_t _e0 = nullptr, _e1 = nullptr;                             \
+    if (e->profiling && prof_events(e, kind, &_e0, &_e1) == 0) cudaEventRecord(_e0, st); \
+    rc = (expr);                                                          \
+    if (rc) return rc;                                                    \
+    if (_e1) cudaEventRecord(_e1, st);                                    \
+    g_launches += 1;                                                      \
   } while (0)
-  RUN(launch_pack_mel(mel, e->melT, B, e->n_mels, 3000, e->c_pad, st));
+  RUN(AL_K_PACK, launch_pack_mel(mel, e->melT, B, e->n_mels, 3000, e->c_pad, st));
   {  // conv1 + GELU (modeling_whisper.py:619)
     GemmParams p{};
     p.m_per_batch = 3000; p.batch = B; p.N = d; p.K = 3 * e->c_pad; p.bias = e->conv1_b;
-    RUN(launch_gemm(e->tm_melT_A, e->tm_conv1_w, e->tm_h1_O, p, EPI_GELU, nsm, st));
+    RUN(AL_K_CONV1, launch_gemm(e->tm_melT_A, e->tm_conv1_w, e->tm_h1_O, p, EPI_GELU, nsm, st));
   }
   {  // conv2 (stride 2) + GELU + position table (:620-625) -> fp32 residual stream
     GemmParams p{};
     p.m_per_batch = 1500; p.batch = B; p.N = d; p.K = 3 * d; p.bias = e->conv2_b; p.aux = e->pos; p.aux_ld = d;
-    RUN(launch_gemm(e->tm_h1_A, e->tm_conv2_w, e->tm_x_O3, p, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX, nsm, st));
+    RUN(AL_K_CONV2, launch_gemm(e->tm_h1_A, e->tm_conv2_w, e->tm_x_O3, p, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX, nsm, st));
   }
   for (int l = 0; l < L; ++l) {
     const LayerW& w = e->layers[l];
-    RUN(launch_layernorm(e->x, w.ln1_g, w.ln1_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
+    RUN(AL_K_LN, launch_layernorm(e->x, w.ln1_g, w.ln1_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = 3 * d; p.K = d; p.bias = w.bqkv;
-      RUN(launch_gemm(e->tm_xn_A, w.tm_wqkv, e->tm_qkv_O, p, 0, nsm, st));
+      RUN(AL_K_QKV, launch_gemm(e->tm_xn_A, w.tm_wqkv, e->tm_qkv_O, p, 0, nsm, st));
     }
-    RUN(launch_attention(e->tm_qkv_att, e->attn, B, 1500, e->H, st));
+    RUN(AL_K_ATTN, launch_attention(e->tm_qkv_att, e->attn, B, 1500, e->H, st));
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = d; p.bias = w.bo;
-      RUN(launch_gemm(e->tm_attn_A, w.tm_wo, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
+      RUN(AL_K_OPROJ, launch_gemm(e->tm_attn_A, w.tm_wo, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
     }
-    RUN(launch_layernorm(e->x, w.ln2_g, w.ln2_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
+    RUN(AL_K_LN, launch_layernorm(e->x, w.ln2_g, w.ln2_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = e->ffn; p.K = d; p.bias = w.b1;
-      RUN(launch_gemm(e->tm_xn_A, w.tm_w1, e->tm_hff_O, p, EPI_GELU, nsm, st));
+      RUN(AL_K_FC1, launch_gemm(e->tm_xn_A, w.tm_w1, e->tm_hff_O, p, EPI_GELU, nsm, st));
     }
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = e->ffn; p.bias = w.b2;
-      RUN(launch_gemm(e->tm_hff_A, w.tm_w2, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
+      RUN(AL_K_FC2, launch_gemm(e->tm_hff_A, w.tm_w2, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
     }
   }
-  RUN(launch_layernorm(e->x, e->lnf_g, e->lnf_b, out, rows, d, 1e-5f, out_dtype, d, rows, 0, 0, st));
+  RUN(AL_K_LN, launch_layernorm(e->x, e->lnf_g, e->lnf_b, out, rows, d, 1e-5f, out_dtype, d, rows, 0, 0, st));
 #undef RUN
   return 0;
 }
 
 float* al_encoder_hidden(al_encoder* e) { return e ? e->x : nullptr; }
 
+int al_encoder_set_profiling(al_encoder* e, int on) {
+  AL_REQUIRE(e != nullptr, "al_encoder_set_profiling: NULL plan");
+  e->profiling = on != 0;
+  e->ev_used = 0;
+  return 0;
+}
+
+int al_encoder_profile_read(al_encoder* e, float* ms_by_kind_host, int* launches_by_kind_host) {
+  AL_REQUIRE(e && ms_by_kind_host && launches_by_kind_host, "al_encoder_profile_read: NULL argument");
+  for (int k = 0; k < AL_K_COUNT; ++k) {
+    ms_by_kind_host[k] = 0.f;
+    launches_by_kind_host[k] = 0;
+  }
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    AL_CHECK_CUDA(cudaEventSynchronize(e->ev[i + 1]));
+    float ms = 0.f;
+    AL_CHECK_CUDA(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+    const int k = e->ev_kind[i / 2];
+    ms_by_kind_host[k] += ms;
+    launches_by_kind_host[k] += 1;
+  }
+  e->ev_used = 0;
+  return 0;
+}
+
 int al_encoder_destroy(al_encoder* e) {
+  if (e)
+    for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
   delete e;
   return 0;
 }

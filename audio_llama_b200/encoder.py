@@ -114,6 +114,18 @@ class WhisperEncoderB200:
 
     __call__ = forward
 
+    KINDS = ("pack_mel", "conv1", "conv2", "layernorm", "qkv", "attention", "out_proj", "fc1", "fc2")
+
+    def set_profiling(self, on: bool):
+        check(lib().al_encoder_set_profiling(self._h, 1 if on else 0), "al_encoder_set_profiling")
+
+    def read_profile(self):
+        """{kind: (milliseconds, launches)} accumulated since the last read (synchronises)."""
+        ms = (C.c_float * len(self.KINDS))()
+        n = (C.c_int * len(self.KINDS))()
+        check(lib().al_encoder_profile_read(self._h, ms, n), "al_encoder_profile_read")
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KINDS)}
+
     def hidden_state(self, B: int) -> torch.Tensor:
         """Copy of the fp32 residual stream [B, 1500, d] after the last forward (tests only)."""
         n = B * self.cfg.n_ctx * self.cfg.d_model

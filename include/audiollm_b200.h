@@ -96,6 +96,12 @@ int al_encoder_set_layer(al_encoder* e, int layer, const float* ln1_g, const flo
 /* mel [B][n_mels][3000] f32 -> out [B][1500][d] (out_dtype 0 bf16 / 1 f32). n_layers_run < 0 = all. */
 int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
                        al_stream_t stream);
+/* Live per-kernel timing of the plan's launches (CUDA events recorded on the launch stream around every
+ * kernel while profiling is on). al_encoder_profile_read synchronises, sums milliseconds and launch counts per
+ * kind since the last read / set, and resets. Kinds index ms_by_kind_host[AL_K_COUNT]. */
+enum { AL_K_PACK = 0, AL_K_CONV1, AL_K_CONV2, AL_K_LN, AL_K_QKV, AL_K_ATTN, AL_K_OPROJ, AL_K_FC1, AL_K_FC2, AL_K_COUNT };
+int al_encoder_set_profiling(al_encoder* e, int on);
+int al_encoder_profile_read(al_encoder* e, float* ms_by_kind_host, int* launches_by_kind_host);
 /* fp32 residual stream [max_batch*1500][d] inside the workspace (tests read intermediate states). */
 float* al_encoder_hidden(al_encoder* e);
 int al_encoder_destroy(al_encoder* e);
