@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaudiollm_sm100.so")
+# AUDIOLLM_B200_LIB lets kernel experiments (tools/) load an alternative build of the same library
+LIB_PATH = os.environ.get("AUDIOLLM_B200_LIB") or os.path.join(_HERE, "libaudiollm_sm100.so")
 
 _lib = None
 
@@ -27,7 +28,7 @@ SIGNATURES = {
     "al_mel_forward": (i32, [vp, vp, i32, i64, i32, i32, vp, vp, vp]),
     "al_mel_filterbank_host": (i32, [i32, i32, vp]),
     "al_mel_set_filterbank_host": (i32, [i32, i32, vp]),
-    "al_gemm_bf16": (i32, [vp, i64, i64, i32, i32, vp, i32, i32, vp, vp, i64, i64, i32, vp, i32, vp]),
+    "al_gemm_bf16": (i32, [vp, i64, i64, i32, i32, vp, i32, i32, vp, vp, i64, i64, i32, vp, i32, vp, vp]),
     "al_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, i32, i64, i32, i64, i64, vp]),
     "al_attention": (i32, [vp, vp, i32, i32, i32, vp]),
     "al_pack_mel": (i32, [vp, vp, i32, i32, i32, i32, vp]),

@@ -334,12 +334,15 @@ int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host) {
 // ----------------------------------------------------------------------------- building blocks
 int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride, int m_per_batch, int batch,
                  const void* W, int N, int K, const float* bias, void* out, long long o_row_stride,
-                 long long o_batch_stride, int flags, const float* aux, int aux_ld, al_stream_t stream) {
+                 long long o_batch_stride, int flags, const float* aux, int aux_ld, const float* resid,
+                 al_stream_t stream) {
   AL_REQUIRE(m_per_batch > 0 && batch > 0 && N > 0 && K > 0, "al_gemm_bf16: bad shape m=%d batch=%d N=%d K=%d",
              m_per_batch, batch, N, K);
   AL_REQUIRE(K % 8 == 0, "al_gemm_bf16: K=%d must be a multiple of 8", K);
   AL_REQUIRE(((flags & AL_EPI_ROWAUX) != 0) == (aux != nullptr), "al_gemm_bf16: AL_EPI_ROWAUX and aux must come together");
   AL_REQUIRE(!(flags & AL_EPI_REDUCE_ADD) || (flags & AL_EPI_OUT_F32), "al_gemm_bf16: REDUCE_ADD needs OUT_F32");
+  AL_REQUIRE(((flags & AL_EPI_RESIDUAL) != 0) == (resid != nullptr), "al_gemm_bf16: AL_EPI_RESIDUAL and resid must come together");
+  AL_REQUIRE(!(flags & AL_EPI_RESIDUAL) || (flags & AL_EPI_OUT_F32), "al_gemm_bf16: RESIDUAL needs OUT_F32");
   CUtensorMap ta, tb, to;
   int rc = tmap_rows3d(&ta, A, 2, K, m_per_batch, batch, a_row_stride, a_batch_stride, 64, 128);
   if (rc) return rc;
@@ -356,6 +359,9 @@ int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride
   p.bias = bias;
   p.aux = aux;
   p.aux_ld = aux_ld;
+  p.resid = resid;                       // same strides as the output
+  p.resid_ld = o_row_stride;
+  p.resid_batch_stride = o_batch_stride;
   rc = launch_gemm(ta, tb, to, p, flags, num_sms(), (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
@@ -555,6 +561,7 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = d; p.bias = w.bo;
+      // residual: TMA reduce-add into the fp32 stream (measured faster than reading x in the epilogue threads)
       RUN(AL_K_OPROJ, launch_gemm(e->tm_attn_A, w.tm_wo, e->tm_x_red, p, EPI_OUT_F32 | EPI_REDUCE_ADD, nsm, st));
     }
     RUN(AL_K_LN, launch_layernorm(e->x, w.ln2_g, w.ln2_b, e->xn, rows, d, 1e-5f, 0, d, rows, 0, 0, st));
@@ -615,10 +622,10 @@ int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_ou
                          long long out_group_stride, long long out_row_offset, al_stream_t stream) {
   AL_REQUIRE(x && W1 && b1 && W2 && b2 && gamma && beta && h_ws && y_ws && out, "al_projector_forward: NULL argument");
   int rc = al_gemm_bf16(x, d_in, (long long)rows * d_in, rows, 1, W1, hidden, d_in, b1, h_ws, hidden,
-                        (long long)rows * hidden, AL_EPI_GELU, nullptr, 0, stream);
+                        (long long)rows * hidden, AL_EPI_GELU, nullptr, 0, nullptr, stream);
   if (rc) return rc;
   rc = al_gemm_bf16(h_ws, hidden, (long long)rows * hidden, rows, 1, W2, d_out, hidden, b2, y_ws, d_out,
-                    (long long)rows * d_out, AL_EPI_OUT_F32, nullptr, 0, stream);
+                    (long long)rows * d_out, AL_EPI_OUT_F32, nullptr, 0, nullptr, stream);
   if (rc) return rc;
   return al_layernorm(y_ws, gamma, beta, out, rows, d_out, 1e-5f, out_dtype, out_ld, rows_per_group, out_group_stride,
                       out_row_offset, stream);

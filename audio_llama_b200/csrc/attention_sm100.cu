@@ -5,14 +5,21 @@
 //   qkv [B][T][3*H*64] bf16  (q | k | v, head h at columns h*64..h*64+63 of each third)
 //   out [B][T][H*64]   bf16
 //
-// One CTA = 2 query tiles of 128 rows of one (batch, head). 12 warps:
-//   warp 0   TMA producer: Q tiles once, then K/V tiles through a 3-stage ring
-//   warp 1   MMA issuer:   S_i = Q_i K_j^T (SS, fp32 in TMEM), O_i = P_i V_j (A = P from TMEM, B = V MN-major smem)
-//   warp 2   TMEM allocator (512 columns: S0 S1 | O0 O1 | P0 P1)
-//   warps 4-7 / 8-11  softmax warpgroup for query tile 0 / 1: one thread per query row, online softmax in fp32,
-//            P written back to TMEM as bf16, per-tile O read back and accumulated in registers with the running
-//            rescale (so O in TMEM never needs a correction pass).
-// The two warpgroups ping-pong on the MUFU (exp2) while the other tile's MMAs run.
+// One CTA = one query tile of 128 rows of one (batch, head); TWO CTAs are resident per SM (256 TMEM columns and
+// ~82 KB of shared memory each), so one CTA's start-up, barrier waits and MMAs run under the other's exps. 8 warps:
+//   warp 0   TMA producer: Q tile once, then K/V tiles through a 2-stage ring
+//   warp 1   MMA issuer:   S = Q K_j^T (SS, fp32 in TMEM), O += P V_j (A = P from TMEM, B = V MN-major smem)
+//   warp 2   TMEM allocator (256 columns: S | O | P)
+//   warps 4-7  softmax warpgroup, one thread per query row.
+// Softmax design (the kernel is exp-bound at head_dim 64: 128x128 exps per 2x 256-cycle MMAs):
+//   * a tile's 128 scores are pulled from TMEM into registers in one go and the S buffer is released at once, so
+//     Q K_{j+1}^T runs under the softmax of tile j;
+//   * O accumulates in TMEM across kv tiles. The running reference max is only advanced when a row's tile max
+//     exceeds it by more than 2^8 (P stays well inside bf16 / fp32 range), and only then is O rescaled in TMEM;
+//     the final O / l is exact whatever reference was used;
+//   * scale-and-subtract, row sums and the polynomial run as packed fp32x2 (FFMA2 / FADD2), the max as 3-input
+//     FMNMX3; POLY_PAIRS of every 4 element pairs take exp2 on the FMA pipe (Cody-Waite split + degree-3
+//     minimax, rel. error 7.7e-5, far below P's bf16 rounding) to relieve the MUFU.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -21,39 +28,64 @@ namespace al {
 constexpr int ATT_BQ = 128;       // query rows per tile
 constexpr int ATT_BKV = 128;      // kv rows per tile
 constexpr int ATT_HD = 64;
-constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // 16 KB: any of Q / K / V tile
-constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + ATT_KV_STAGES * 2 * ATT_TILE_BYTES + 256 + 1024;
+constexpr int ATT_SMEM = ATT_TILE_BYTES + ATT_KV_STAGES * 2 * ATT_TILE_BYTES + 256 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr float ATT_TAU = 8.0f;   // lazy-rescale threshold, log2 units
+constexpr int POLY_PAIRS = 1;     // of every 4 pairs, how many use the FMA-pipe exp2
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair, x <= ~9, on the FMA / ALU pipes.
+__device__ __forceinline__ void poly_exp2_pair(unsigned long long x2, float& o0, float& o1) {
+  float x0, x1;
+  unpk2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const unsigned long long xc = pk2(x0, x1);
+  const unsigned long long MAGIC = pk2(12582912.0f, 12582912.0f);          // 1.5 * 2^23
+  const unsigned long long NMAGIC = pk2(-12582912.0f, -12582912.0f);
+  const unsigned long long NEG1 = pk2(-1.0f, -1.0f);
+  const unsigned long long t = fadd2(xc, MAGIC);                           // low mantissa bits = round(x)
+  const unsigned long long xr = fadd2(t, NMAGIC);
+  const unsigned long long f = ffma2(xr, NEG1, xc);                        // x - round(x) in [-0.5, 0.5]
+  unsigned long long p = ffma2(pk2(0.05508868396282196f, 0.05508868396282196f), f,
+                               pk2(0.24260404706001282f, 0.24260404706001282f));
+  p = ffma2(p, f, pk2(0.6932762265205383f, 0.6932762265205383f));
+  p = ffma2(p, f, pk2(0.9999289512634277f, 0.9999289512634277f));
+  float t0, t1, p0, p1;
+  unpk2(t, t0, t1);
+  unpk2(p, p0, p1);
+  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int H) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 2 tiles
-  uint8_t* sKV = smem + 2 * ATT_TILE_BYTES;             // stages x {K, V}
+  uint8_t* sQ = smem;                                   // 1 tile
+  uint8_t* sKV = smem + ATT_TILE_BYTES;                 // stages x {K, V}
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES);
   uint64_t* q_full = bars;                              // 1
   uint64_t* kv_full = bars + 1;                         // KV_STAGES
   uint64_t* kv_empty = kv_full + ATT_KV_STAGES;         // KV_STAGES
-  uint64_t* s_full = kv_empty + ATT_KV_STAGES;          // 2
-  uint64_t* s_empty = s_full + 2;                       // 2
-  uint64_t* p_full = s_empty + 2;                       // 2
-  uint64_t* o_full = p_full + 2;                        // 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = kv_empty + ATT_KV_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* o_full = p_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int d = H * ATT_HD;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int q0 = blockIdx.x * 2 * ATT_BQ;
+  const int q0 = blockIdx.x * ATT_BQ;
   const int nkv = (T + ATT_BKV - 1) / ATT_BKV;
 
   if (threadIdx.x == 0) {
@@ -63,198 +95,232 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 128);
-      mbar_init(&p_full[i], 128);
-      mbar_init(&o_full[i], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  if (warp == 2) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tS = tmem_base;            // + i*128
-  const uint32_t tO = tmem_base + 256;      // + i*64
-  const uint32_t tP = tmem_base + 384;      // + i*64 (bf16 pairs: 128 kv -> 64 columns)
+  const uint32_t tS = tmem_base;            // 128 columns
+  const uint32_t tO = tmem_base + 128;      // 64 columns
+  const uint32_t tP = tmem_base + 192;      // 64 columns (bf16 pairs: 128 kv -> 64 columns)
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-      tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
-      tma_load_3d(sQ + ATT_TILE_BYTES, &tmQKV, q_full, h * ATT_HD, q0 + ATT_BQ, b);
+  // Register budget: launched with 128 regs x 256 threads (2 CTAs / SM). The 4 control warps drop to 48, which
+  // frees 80 x 128 = 10240 registers; the 4 softmax warps grow to 208, which takes 80 x 128 = 10240. (Asking for
+  // more than was freed makes setmaxnreg.inc wait forever.)
+  if (warp < 4) {
+    setmaxnreg_dec<48>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+        tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
+          uint8_t* kdst = sKV + s * 2 * ATT_TILE_BYTES;
+          tma_load_3d(kdst, &tmQKV, &kv_full[s], d + h * ATT_HD, j * ATT_BKV, b);
+          tma_load_3d(kdst + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * d + h * ATT_HD, j * ATT_BKV, b);
+          if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
+      constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
+      const uint32_t q_addr = smem_u32(sQ);
+      const uint32_t kv_addr = smem_u32(sKV);
+      auto issue_s = [&](int stage) {
+        const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
+        const uint64_t kd = umma_desc_sw128(kv_addr + stage * 2 * ATT_TILE_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
+        umma_commit(s_full);
+      };
+      auto issue_o = [&](int stage, bool first_tile) {
+        // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B
+        // = +128 in the descriptor's (>>4) start-address field.
+        const uint64_t vd = umma_desc_sw128(kv_addr + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_BKV / 16; ++k)
+          umma_ts(tO, tP + k * 8, vd + 128 * k, IDESC_O, (k != 0) || !first_tile);
+        umma_commit(o_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      if (lane == 0) issue_s(0);
+      __syncwarp();
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
-        uint8_t* kdst = sKV + s * 2 * ATT_TILE_BYTES;
-        tma_load_3d(kdst, &tmQKV, &kv_full[s], d + h * ATT_HD, j * ATT_BKV, b);
-        tma_load_3d(kdst + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * d + h * ATT_HD, j * ATT_BKV, b);
-        if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
-    constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
-    auto issue_s = [&](int i, int stage) {
-      const uint64_t qd = umma_desc_sw128(smem_u32(sQ + i * ATT_TILE_BYTES), 16, 1024);
-      const uint64_t kd = umma_desc_sw128(smem_u32(sKV + stage * 2 * ATT_TILE_BYTES), 16, 1024);
-#pragma unroll
-      for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS + i * 128, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
-      umma_commit(&s_full[i]);
-    };
-    auto issue_o = [&](int i, int stage) {
-      // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B.
-      const uint32_t vbase = smem_u32(sKV + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES);
-#pragma unroll
-      for (int k = 0; k < ATT_BKV / 16; ++k) {
-        const uint64_t vd = umma_desc_sw128(vbase + k * 2048, 1024, 1024);
-        umma_ts(tO + i * 64, tP + i * 64 + k * 8, vd, IDESC_O, k != 0);
-      }
-      umma_commit(&o_full[i]);
-    };
-    mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
-    tc_fence_after();
-    if (lane == 0) {
-      issue_s(0, 0);
-      issue_s(1, 0);
-    }
-    __syncwarp();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < nkv; ++j) {
-      int sn = s + 1;
-      uint32_t phn = ph;
-      if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
-      const bool has_next = (j + 1 < nkv);
-      if (has_next) mbar_wait(&kv_full[sn], phn);
-      for (int i = 0; i < 2; ++i) {
-        if (has_next) {
-          mbar_wait(&s_empty[i], j & 1);
+        int sn = s + 1;
+        uint32_t phn = ph;
+        if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
+        if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
+          mbar_wait(&kv_full[sn], phn);
+          mbar_wait(s_empty, j & 1);
           tc_fence_after();
-          if (lane == 0) issue_s(i, sn);
+          if (lane == 0) issue_s(sn);
           __syncwarp();
         }
-        mbar_wait(&p_full[i], j & 1);
+        mbar_wait(p_full, j & 1);
         tc_fence_after();
-        if (lane == 0) issue_o(i, s);
+        if (lane == 0) {
+          issue_o(s, j == 0);
+          umma_commit(&kv_empty[s]);
+        }
         __syncwarp();
+        s = sn;
+        ph = phn;
       }
-      if (lane == 0) umma_commit(&kv_empty[s]);
-      __syncwarp();
-      s = sn;
-      ph = phn;
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax warpgroups
-    const int i = (warp - 4) >> 2;                 // query tile of this warpgroup
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroup
+    setmaxnreg_inc<208>();
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tSi = tS + i * 128 + lane_off;
-    const uint32_t tOi = tO + i * 64 + lane_off;
-    const uint32_t tPi = tP + i * 64 + lane_off;
-    float m = -INFINITY, l = 0.f;
-    float acc[ATT_HD];
-#pragma unroll
-    for (int c = 0; c < ATT_HD; ++c) acc[c] = 0.f;
+    const uint32_t tSi = tS + lane_off;
+    const uint32_t tOi = tO + lane_off;
+    const uint32_t tPi = tP + lane_off;
+    float m_ref = -INFINITY;                       // reference max, log2 units (score * log2 e)
+    unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);   // row-sum accumulators (4 partial sums)
+    const unsigned long long LOG2E2 = pk2(LOG2E, LOG2E);
 
     for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(ATT_BKV, T - j * ATT_BKV);   // columns >= kv_valid are padding (zero K rows)
-      mbar_wait(&s_full[i], j & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tSi + c * 32, r);
+      uint32_t s[128];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+        tmem_ld_32x32(tSi, s0);
+        tmem_ld_32x32(tSi + 32, s1);
+        tmem_ld_32x32(tSi + 64, s2);
+        tmem_ld_32x32(tSi + 96, s3);
         tmem_ld_wait();
-        if (c * 32 + 32 <= kv_valid) {
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);                        // S is in registers: Q K_{j+1}^T may overwrite it now
+      if (j == nkv - 1) {                          // kv tail: columns >= kv_valid are zero-filled K rows
+        const int kv_valid = T - j * ATT_BKV;
+        if (kv_valid < ATT_BKV) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) mx = fmaxf(mx, __uint_as_float(r[k]));
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (c * 32 + k < kv_valid) mx = fmaxf(mx, __uint_as_float(r[k]));
+          for (int k = 0; k < 128; ++k)
+            if (k >= kv_valid) s[k] = 0xff800000u;  // -inf
         }
       }
-      const float scale = fast_exp2((m - mx) * LOG2E);    // first tile: exp2(-inf) = 0
-      // fold in the previous tile's P V (relative to the old max), then rescale to the new max
-      if (j > 0) {
-        mbar_wait(&o_full[i], (j - 1) & 1);
-        tc_fence_after();
+      // row max: 4 independent FMNMX3 chains
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(tOi + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 32; ++k) acc[c * 32 + k] = (acc[c * 32 + k] + __uint_as_float(r[k])) * scale;
+      for (int k = 4; k < 128; k += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        if (k + 4 < 128) {
+          mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
         }
       }
-      l *= scale;
-      m = mx;
-      const float msc = mx * LOG2E;
-      // pass 2: p = exp2(s*log2e - m*log2e), row sum, P -> TMEM as bf16
-#pragma unroll 1
+      const float mx_s = fmaxf(fmax3(mx0, mx1, mx2), mx3) * LOG2E;
+      bool o_ready = (j == 0);
+      if (__any_sync(0xffffffffu, mx_s > m_ref + ATT_TAU)) {
+        // advance the reference (whole warp, so the TMEM ld/st below stay warp-uniform) and rescale l and O
+        const float new_ref = fmaxf(m_ref, mx_s);
+        const float scale = fast_exp2(m_ref - new_ref);        // 0 on the first tile (m_ref = -inf)
+        m_ref = new_ref;
+        const unsigned long long sc2 = pk2(scale, scale);
+        l2a = fmul2(l2a, sc2);
+        l2b = fmul2(l2b, sc2);
+        if (j > 0) {
+          mbar_wait(o_full, (j - 1) & 1);                      // P V of the previous tile has landed in O
+          tc_fence_after();
+          o_ready = true;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tOi + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * scale);
+            tmem_st_32x32(tOi + c * 32, r);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float nm = -m_ref;
+      const unsigned long long nm2 = pk2(nm, nm);
+      // p = 2^(s*log2e - m_ref); P -> TMEM as bf16 (columns kk/2), row sums in fp32
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tSi + c * 32, r);
-        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[k]), LOG2E, -msc));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[k + 1]), LOG2E, -msc));
-          if (c * 32 + k >= kv_valid) p0 = 0.f;
-          if (c * 32 + k + 1 >= kv_valid) p1 = 0.f;
-          l += p0 + p1;
+          const int idx = c * 32 + k;
+          const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[idx]), __uint_as_float(s[idx + 1])), LOG2E2, nm2);
+          float p0, p1;
+          if (((k >> 1) & 3) < POLY_PAIRS) {
+            poly_exp2_pair(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpk2(x2, x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+          }
+          if ((k >> 1) & 1) l2b = fadd2(l2b, pk2(p0, p1));
+          else l2a = fadd2(l2a, pk2(p0, p1));
           pk[k >> 1] = pack_bf16(p0, p1);
+        }
+        if (c == 0 && !o_ready) {                  // P is still being read by the previous tile's P V until then
+          mbar_wait(o_full, (j - 1) & 1);
+          tc_fence_after();
         }
         tmem_st_32x16(tPi + c * 16, pk);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&s_empty[i]);
-      mbar_arrive(&p_full[i]);
+      mbar_arrive(p_full);
     }
-    // last tile's P V
-    mbar_wait(&o_full[i], (nkv - 1) & 1);
+    // normalise and store
+    mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const int q = q0 + i * ATT_BQ + row;
+    float la, lb, lc, ld;
+    unpk2(l2a, la, lb);
+    unpk2(l2b, lc, ld);
+    const float inv_l = 1.0f / ((la + lb) + (lc + ld));
+    const int q = q0 + row;
+    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q) * d + h * ATT_HD);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t r[32];
       tmem_ld_32x32(tOi + c * 32, r);
       tmem_ld_wait();
+      if (q < T) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) acc[c * 32 + k] = (acc[c * 32 + k] + __uint_as_float(r[k])) * inv_l;
-    }
-    if (q < T) {
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q) * d + h * ATT_HD);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint4 v;
-        v.x = pack_bf16(acc[8 * u], acc[8 * u + 1]);
-        v.y = pack_bf16(acc[8 * u + 2], acc[8 * u + 3]);
-        v.z = pack_bf16(acc[8 * u + 4], acc[8 * u + 5]);
-        v.w = pack_bf16(acc[8 * u + 6], acc[8 * u + 7]);
-        dst[u] = v;
+        for (int u = 0; u < 4; ++u) {
+          uint4 v;
+          v.x = pack_bf16(__uint_as_float(r[8 * u]) * inv_l, __uint_as_float(r[8 * u + 1]) * inv_l);
+          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * inv_l, __uint_as_float(r[8 * u + 3]) * inv_l);
+          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * inv_l, __uint_as_float(r[8 * u + 5]) * inv_l);
+          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * inv_l, __uint_as_float(r[8 * u + 7]) * inv_l);
+          dst[c * 4 + u] = v;
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
 
 int launch_attention(const CUtensorMap& tm_qkv, void* out, int B, int T, int H, cudaStream_t stream) {
@@ -263,8 +329,8 @@ int launch_attention(const CUtensorMap& tm_qkv, void* out, int B, int T, int H, 
     AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
-  dim3 grid((T + 2 * ATT_BQ - 1) / (2 * ATT_BQ), H, B);
-  attention_fwd_kernel<<<grid, 384, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<__nv_bfloat16*>(out), T, H);
+  dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
+  attention_fwd_kernel<<<grid, 256, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<__nv_bfloat16*>(out), T, H);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -6,9 +6,9 @@
 //   W   : [N][K] bf16 (nn.Linear weight layout), K contiguous.
 //   out : [batch][m_per_batch][N] bf16 or fp32.
 //
-// Roles (256 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> swizzled smem -> TMA store /
-// TMA reduce-add). Operands are staged by TMA into 128B-swizzled K-major tiles; the fp32 accumulator lives
+// Roles (384 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-7 and 8-11 = two epilogue warpgroups that take alternate column chunks of
+// the tile (TMEM -> registers -> bias / GELU / residual -> swizzled smem -> TMA store). Operands are staged by TMA into 128B-swizzled K-major tiles; the fp32 accumulator lives
 // in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // M / N / K tails need no code: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
 //
@@ -30,13 +30,14 @@ constexpr int gemm_smem_bytes() {
 }
 
 template <int BN, int STAGES, int FLAGS>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
   constexpr bool OUT_F32 = (FLAGS & EPI_OUT_F32) != 0;
   constexpr bool DO_GELU = (FLAGS & EPI_GELU) != 0;
   constexpr bool REDUCE = (FLAGS & EPI_REDUCE_ADD) != 0;
   constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
+  constexpr bool RESID = (FLAGS & EPI_RESIDUAL) != 0;
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 B per row)
@@ -67,7 +68,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 128);
+      mbar_init(&tempty[a], 256);
     }
     fence_barrier_init();
   }
@@ -125,13 +126,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (2 warpgroups)
+    const int wg = (warp - 4) >> 2;               // chunks c with c % 2 == wg
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;          // row inside the 128-row tile
-    const int etid = threadIdx.x - 128;
+    const int etid = threadIdx.x - 128 - wg * 128;
+    uint8_t* stg = sStg + wg * STG_BYTES;         // one staging buffer per warpgroup
+    uint8_t* rowp = stg + row * 128;
     int as = 0;
     uint32_t aph = 0;
-    uint32_t chunk_counter = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int nt = t % p.tiles_n;
       const int mt = t / p.tiles_n;
@@ -141,25 +144,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int grow = min(m0 + row, p.m_per_batch - 1);     // clamped row for aux / residual reads
 #pragma unroll 1
-      for (int c = 0; c < NCHUNK; ++c, ++chunk_counter) {
+      for (int c = wg; c < NCHUNK; c += 2) {
         float v[CH];
         {
-          uint32_t r[32];
-          tmem_ld_32x32(t_row + c * CH, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          uint32_t r0[32];
+          tmem_ld_32x32(t_row + c * CH, r0);
           if constexpr (CH == 64) {
-            tmem_ld_32x32(t_row + c * CH + 32, r);
+            uint32_t r1[32];
+            tmem_ld_32x32(t_row + c * CH + 32, r1);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(r1[j]);
+          } else {
+            tmem_ld_wait();
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
         }
         const int col0 = n0 + c * CH;
+        const bool full = col0 + CH <= p.N;
         if (p.bias != nullptr) {
-          if (col0 + CH <= p.N) {
+          if (full) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
@@ -172,12 +179,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (DO_GELU) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < CH; ++j) v[j] = gelu_erf_fast(v[j]);
         }
         if constexpr (ROWAUX) {
-          const int arow = min(m0 + row, p.m_per_batch - 1);
-          const float* ap = p.aux + static_cast<size_t>(arow) * p.aux_ld;
-          if (col0 + CH <= p.N) {
+          const float* ap = p.aux + static_cast<size_t>(grow) * p.aux_ld;
+          if (full) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 av = __ldg(reinterpret_cast<const float4*>(ap + col0 + j));
@@ -188,11 +194,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < CH; ++j) v[j] += __ldg(ap + min(col0 + j, p.N - 1));
           }
         }
+        if constexpr (RESID) {
+          // residual stream, possibly the output buffer itself: this CTA is the only reader and writer of this
+          // tile, and the read happens before its own TMA store -> plain (coherent) loads, no atomics
+          const float* rp = p.resid + (static_cast<size_t>(b) * p.resid_batch_stride + static_cast<size_t>(grow) * p.resid_ld);
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+              const float4 rv = *reinterpret_cast<const float4*>(rp + col0 + j);
+              v[j] += rv.x; v[j + 1] += rv.y; v[j + 2] += rv.z; v[j + 3] += rv.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] += rp[min(col0 + j, p.N - 1)];
+          }
+        }
         // stage into 128B-swizzled smem (row = 128 B; 16 B unit u of row r lives at u ^ (r & 7))
-        uint8_t* stg = sStg + (chunk_counter & 1) * STG_BYTES;
-        if (etid == 0) tma_wait_group_read<1>();   // the store that used this buffer two chunks ago has drained
-        named_bar_sync(1, 128);
-        uint8_t* rowp = stg + row * 128;
+        if (etid == 0) tma_wait_group_read<0>();   // this warpgroup's previous store has drained the buffer
+        named_bar_sync(1 + 2 * wg, 128);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           uint4 q;
@@ -206,7 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           *reinterpret_cast<uint4*>(rowp + ((u ^ (row & 7)) << 4)) = q;
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
+        named_bar_sync(2 + 2 * wg, 128);
         if (etid == 0) {
           if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stg, col0, m0, b);
           else tma_store_3d(&tmO, stg, col0, m0, b);
@@ -238,7 +257,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   const int tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 256, smem, stream>>>(tmA, tmB, tmO, p);
+  kern<<<grid, 384, smem, stream>>>(tmA, tmB, tmO, p);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -256,6 +275,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     case EPI_OUT_F32: return launch_one<256, 4, EPI_OUT_F32>(tmA, tmB, tmO, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_REDUCE_ADD:
       return launch_one<256, 4, EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, p, num_sms, stream);
+    case EPI_OUT_F32 | EPI_RESIDUAL:
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
       return launch_one<256, 4, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, p, num_sms, stream);
     default:

@@ -12,6 +12,7 @@ enum GemmEpilogue : int {
   EPI_OUT_F32 = 2,      // fp32 output (default bf16)
   EPI_REDUCE_ADD = 4,   // out += result (TMA reduce-add; residual connection on the fp32 stream)
   EPI_ROWAUX = 8,       // + aux[row_in_batch][col] (fp32; Whisper's position table)
+  EPI_RESIDUAL = 16,    // + resid[batch][row][col] (fp32, may alias out: in-place residual add, no atomics)
 };
 
 struct GemmParams {
@@ -24,6 +25,9 @@ struct GemmParams {
   const float* bias;       // [N] or nullptr
   const float* aux;        // [m_per_batch][aux_ld] or nullptr
   int aux_ld;
+  const float* resid;      // [batch][m_per_batch][resid_ld] or nullptr (EPI_RESIDUAL)
+  long long resid_ld;
+  long long resid_batch_stride;
 };
 
 int gemm_out_box_cols(int flags);   // inner box extent of the output tensor map (32 fp32 / 64 bf16)

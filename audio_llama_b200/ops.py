@@ -8,7 +8,7 @@ import torch
 
 from ._lib import check, lib, ptr, stream_ptr
 
-EPI_GELU, EPI_OUT_F32, EPI_REDUCE_ADD, EPI_ROWAUX = 1, 2, 4, 8
+EPI_GELU, EPI_OUT_F32, EPI_REDUCE_ADD, EPI_ROWAUX, EPI_RESIDUAL = 1, 2, 4, 8, 16
 MEL_WHISPER, MEL_TRAIN = 0, 1
 N_FRAMES = 3000
 
@@ -80,9 +80,10 @@ def mel_filterbank(n_mels: int, mode: int = MEL_WHISPER):
 
 
 def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0,
-              out: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+              resid: Optional[torch.Tensor] = None) -> torch.Tensor:
     """epilogue(a @ w.T + bias): a [M, K] or [batch, M, K] bf16, w [N, K] bf16. With EPI_REDUCE_ADD `out` (fp32)
-    is accumulated into."""
+    is accumulated into; with EPI_RESIDUAL `resid` (fp32, same shape as out, may be out itself) is added."""
     _req(a, torch.bfloat16, "a")
     _req(w, torch.bfloat16, "w")
     a3 = a if a.dim() == 3 else a.unsqueeze(0)
@@ -98,8 +99,11 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
         _req(bias, torch.float32, "bias")
     if aux is not None:
         _req(aux, torch.float32, "aux")
+    if resid is not None:
+        _req(resid, torch.float32, "resid")
     check(lib().al_gemm_bf16(ptr(a), K, M * K, M, batch, ptr(w), N, K, ptr(bias), ptr(out), N, M * N, flags,
-                             ptr(aux), aux.shape[-1] if aux is not None else 0, stream_ptr()), "al_gemm_bf16")
+                             ptr(aux), aux.shape[-1] if aux is not None else 0, ptr(resid), stream_ptr()),
+          "al_gemm_bf16")
     return out
 
 
@@ -110,7 +114,7 @@ def gemm_bf16_strided(a_base: torch.Tensor, a_row_stride: int, a_batch_stride: i
     N, K = w.shape
     check(lib().al_gemm_bf16(ptr(a_base), a_row_stride, a_batch_stride, m_per_batch, batch, ptr(w), N, K, ptr(bias),
                              ptr(out_base), o_row_stride, o_batch_stride, flags, ptr(aux),
-                             aux.shape[-1] if aux is not None else 0, stream_ptr()), "al_gemm_bf16")
+                             aux.shape[-1] if aux is not None else 0, None, stream_ptr()), "al_gemm_bf16")
     return out_base
 
 

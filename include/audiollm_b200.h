@@ -56,14 +56,17 @@ int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host);
 #define AL_EPI_OUT_F32 2
 #define AL_EPI_REDUCE_ADD 4
 #define AL_EPI_ROWAUX 8
+#define AL_EPI_RESIDUAL 16
 
 /* out = epilogue(A @ W^T + bias).  A [batch][m_per_batch][K] bf16 with row / batch strides in ELEMENTS
  * (rows may overlap — the conv stem uses that), W [N][K] bf16 (nn.Linear layout), bias [N] f32 or NULL,
- * out [batch][m_per_batch][N] bf16 (or f32 with AL_EPI_OUT_F32), aux [m_per_batch][aux_ld] f32.
+ * out [batch][m_per_batch][N] bf16 (or f32 with AL_EPI_OUT_F32), aux [m_per_batch][aux_ld] f32, resid (with
+ * AL_EPI_RESIDUAL) f32 with the output's strides — it may BE the output buffer (in-place x += ...).
  * Replaces nn.Linear / nn.Conv1d forward (cuBLAS / cuDNN in the reference's stack). */
 int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride, int m_per_batch, int batch,
                  const void* W, int N, int K, const float* bias, void* out, long long o_row_stride,
-                 long long o_batch_stride, int flags, const float* aux, int aux_ld, al_stream_t stream);
+                 long long o_batch_stride, int flags, const float* aux, int aux_ld, const float* resid,
+                 al_stream_t stream);
 
 /* LayerNorm(x[rows][d] f32) -> out (out_dtype 0 bf16 / 1 f32). Output row of input row r:
  * (r / rows_per_group) * out_group_stride + out_row_offset + r % rows_per_group, rows of out_ld elements. */

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from audio_llama_b200 import ops
-from audio_llama_b200.ops import EPI_GELU, EPI_OUT_F32, EPI_REDUCE_ADD, EPI_ROWAUX
+from audio_llama_b200.ops import EPI_GELU, EPI_OUT_F32, EPI_REDUCE_ADD, EPI_RESIDUAL, EPI_ROWAUX
 
 
 def rnd(*shape, seed=0, s=1.0):
@@ -53,6 +53,12 @@ def test_gemm_f32_and_reduce_add(M, N, K):
     check(x, x0 + ref, False)
     ops.gemm_bf16(a.cuda(), w.cuda(), None, flags=EPI_OUT_F32 | EPI_REDUCE_ADD, out=x)       # no bias
     check(x, x0 + 2 * ref - b, False)
+    # in-place residual add (what out_proj / fc2 use): x <- x + a w^T + b, no atomics
+    x = x0.clone().cuda()
+    ops.gemm_bf16(a.cuda(), w.cuda(), b.cuda(), flags=EPI_OUT_F32 | EPI_RESIDUAL, out=x, resid=x)
+    check(x, x0 + ref, False)
+    y2 = ops.gemm_bf16(a.cuda(), w.cuda(), b.cuda(), flags=EPI_OUT_F32 | EPI_RESIDUAL, resid=x0.cuda())   # out of place
+    check(y2, x0 + ref, False)
 
 
 def test_gemm_batched_rowaux():
