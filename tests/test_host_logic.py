@@ -1,0 +1,153 @@
+"""CPU: host-side logic — API surface mirrors the reference, LoRA low-rank path == the reference's dense path,
+checkpoint key names, sharding, error behaviour, and the world_size-2 gradient exchange over gloo."""
+import inspect
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from audio_llama_b200 import parallel, synth
+from audio_llama_b200.config import WHISPER_LARGE_V3_TURBO, projector_hidden
+from audio_llama_b200.models.lora import LoRALayer, apply_lora_to_llama, lora_forward_hook
+from audio_llama_b200.models.projector import AudioProjector
+
+
+def test_api_surface_matches_reference():
+    """Names / signatures of SURVEY.md §8b."""
+    from audio_llama_b200.models import allm, base, lora, projector
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(allm.AudioLLM.__init__) == ["self", "llama_path", "whisper_path", "lora_rank"]
+    assert inspect.signature(allm.AudioLLM.__init__).parameters["lora_rank"].default == 64
+    assert sig(allm.AudioLLM.forward)[:5] == ["self", "input_ids", "attention_mask", "audio_features", "labels"]
+    assert sig(allm.AudioLLM.generate)[:8] == ["self", "input_ids", "attention_mask", "audio_features",
+                                               "max_new_tokens", "temperature", "top_p", "do_sample"]
+    g = inspect.signature(allm.AudioLLM.generate).parameters
+    assert (g["max_new_tokens"].default, g["temperature"].default, g["top_p"].default, g["do_sample"].default) == (256, 0.7, 0.9, True)
+    for m in ("_combine_text_and_audio_embeddings", "_extend_attention_mask", "_process_audio_features",
+              "get_trainable_params", "to"):
+        assert hasattr(allm.AudioLLM, m)
+    assert sig(allm.AudioLLM._combine_text_and_audio_embeddings) == ["self", "text_embeddings", "audio_features", "input_ids"]
+    assert sig(allm.AudioLLM._extend_attention_mask) == ["self", "attention_mask", "audio_seq_len", "has_special_tokens"]
+    assert sig(projector.AudioProjector.__init__) == ["self", "input_dim", "output_dim", "hidden_dim"]
+    assert sig(lora.LoRALayer.__init__) == ["self", "in_dim", "out_dim", "rank", "alpha"]
+    assert sig(lora.apply_lora_to_llama) == ["llama_model", "rank", "alpha", "target_modules"]
+    assert sig(lora.lora_forward_hook) == ["module", "input", "output", "lora_layer"]
+    assert sig(base.load_base_models) == ["llama_model_path", "whisper_model_path"]
+    assert {"forward", "to"} <= set(dir(base.FrozenModelWrapper))
+    w = base.FrozenModelWrapper(nn.Linear(2, 2))
+    assert hasattr(w, "model") and not any(q.requires_grad for q in w.model.parameters())
+
+
+def test_projector_state_dict_keys_and_param_count():
+    p = AudioProjector(1280, 3072)
+    assert sorted(p.state_dict()) == ["layers.0.bias", "layers.0.weight", "layers.2.bias", "layers.2.weight",
+                                      "layers.3.bias", "layers.3.weight"]
+    assert p.layers[0].out_features == projector_hidden(1280, 3072) == 2176
+    assert sum(x.numel() for x in p.parameters()) == 9481344          # /root/reference/src/training.log:243 (part)
+    assert sum(x.numel() for x in AudioProjector(1280, 2048).parameters()) == 5545600
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p(torch.zeros(1, 2, 1280))
+
+
+def test_trainable_count_readme_config():
+    """95 726 720 = projector + LoRA r=64 on q,k,v,gate,up,down x 28 layers (SURVEY.md §4 vi)."""
+    shapes = {"q_proj": (3072, 3072), "k_proj": (3072, 1024), "v_proj": (3072, 1024),
+              "gate_proj": (3072, 8192), "up_proj": (3072, 8192), "down_proj": (8192, 3072)}
+    lora = sum(64 * (i + o) for i, o in shapes.values()) * 28
+    assert lora == 86245376 and lora + 9481344 == 95726720
+
+
+def test_lora_matches_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "reference_modules.npz"))
+    lin = nn.Linear(96, 160)
+    lora = LoRALayer(96, 160, rank=8, alpha=16)
+    with torch.no_grad():
+        lin.weight.copy_(torch.from_numpy(g["lora_W"])); lin.bias.copy_(torch.from_numpy(g["lora_b"]))
+        lora.lora_A.copy_(torch.from_numpy(g["lora_A"])); lora.lora_B.copy_(torch.from_numpy(g["lora_B"]))
+    x = torch.from_numpy(g["lora_x"])
+    y = lora_forward_hook(lin, (x,), lin(x), lora)
+    np.testing.assert_allclose(y.detach().numpy(), g["lora_y"], rtol=0, atol=1e-6)
+    assert lora.scaling == 2.0
+    # init: A zeros, B ~ N(0, 0.01) -> the update is identically zero at init (lora.py:9-18)
+    fresh = LoRALayer(32, 48, rank=4)
+    assert (fresh.lora_A == 0).all() and 0.003 < fresh.lora_B.std() < 0.03
+    assert (fresh(torch.randn(2, 32)) == 0).all()
+
+
+def test_apply_lora_targets_by_substring():
+    class Blk(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj, self.k_proj, self.v_proj, self.o_proj = (nn.Linear(8, 8) for _ in range(4))
+            self.gate_proj, self.up_proj, self.down_proj = nn.Linear(8, 16), nn.Linear(8, 16), nn.Linear(16, 8)
+            self.norm = nn.LayerNorm(8)
+    m = nn.ModuleDict({"layers": nn.ModuleList([Blk(), Blk()])})
+    ll = apply_lora_to_llama(m, rank=2)
+    assert len(ll) == 12 and all("o_proj" not in k for k in ll)
+    assert ll["layers.0.down_proj"].lora_A.shape == (2, 16) and ll["layers.0.down_proj"].lora_B.shape == (8, 2)
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 32, 255, 256):
+        for world in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 2, 2)
+
+
+def test_synth_recipe_is_deterministic():
+    a, b = synth.synth_clip(3), synth.synth_clip(3)
+    assert a.dtype == np.float32 and a.shape == (480000,) and (a == b).all() and np.abs(a).max() <= 1.0
+    assert (synth.synth_batch(2, first=3)[0] == a).all()
+    w = synth.init_encoder_weights(WHISPER_LARGE_V3_TURBO.__class__(64, 1, 1, 128, 80))
+    assert "layers.0.self_attn.k_proj.weight" in w and "layers.0.self_attn.k_proj.bias" not in w
+
+
+def _ddp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                   # identical trainable weights on every rank
+    proj = nn.Sequential(nn.Linear(6, 5), nn.GELU(), nn.Linear(5, 4), nn.LayerNorm(4))
+    lora = LoRALayer(4, 3, rank=2)
+    with torch.no_grad():
+        lora.lora_A.normal_(0, 0.1)
+    params = list(proj.parameters()) + list(lora.parameters())
+    bucket = parallel.FlatGradBucket(params)
+    g = torch.Generator().manual_seed(123)
+    x_all, y_all = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    lo, hi = parallel.shard_range(8, rank, world)
+    bucket.zero()
+    loss = ((lora(proj(x_all[lo:hi])) - y_all[lo:hi]) ** 2).mean()
+    loss.backward()
+    flat = bucket.allreduce_mean().clone()
+    if rank == 0:
+        # single-process reference on the full batch
+        for p in params:
+            p.grad = None
+        ((lora(proj(x_all)) - y_all) ** 2).mean().backward()
+        ref = torch.cat([p.grad.flatten() for p in params])
+        out.put((flat, ref))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    """One flat-bucket allreduce of projector + LoRA grads over 2 ranks == the gradient of the full batch."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flat, ref = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert torch.allclose(flat, ref, atol=1e-6)
