@@ -40,6 +40,28 @@ def test_api_surface_matches_reference():
     assert hasattr(w, "model") and not any(q.requires_grad for q in w.model.parameters())
 
 
+def test_compat_shim_resolves_reference_import_lines():
+    """`from models.allm import AudioLLM` etc. (R/src/train.py:13-16) resolve to the B200 modules."""
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "audio_llama_b200", "compat"))
+    try:
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        allm = importlib.import_module("models.allm")
+        proj = importlib.import_module("models.projector")
+        lora = importlib.import_module("models.lora")
+        base = importlib.import_module("models.base")
+        assert allm.AudioLLM.__module__ == "audio_llama_b200.models.allm"
+        assert proj.AudioProjector is AudioProjector and lora.LoRALayer is LoRALayer
+        assert callable(base.load_base_models) and callable(lora.lora_forward_hook)
+    finally:
+        sys.path.pop(0)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+
+
 def test_projector_state_dict_keys_and_param_count():
     p = AudioProjector(1280, 3072)
     assert sorted(p.state_dict()) == ["layers.0.bias", "layers.0.weight", "layers.2.bias", "layers.2.weight",
