@@ -631,6 +631,34 @@ int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_ou
                       out_row_offset, stream);
 }
 
+// ----------------------------------------------------------------------------- LoRA linear
+int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W, const float* bias,
+                           const void* lora_A, const void* lora_B_scaled, void* t_ws, void* out, int out_dtype,
+                           al_stream_t stream) {
+  AL_REQUIRE(x && W && lora_A && lora_B_scaled && t_ws && out, "al_lora_linear_forward: NULL argument");
+  AL_REQUIRE(rows > 0 && in_dim % 8 == 0 && rank % 8 == 0 && rank > 0 && out_dim > 0,
+             "al_lora_linear_forward: bad shape rows=%d in=%d out=%d rank=%d", rows, in_dim, out_dim, rank);
+  // 1. T = x A^T  [rows, rank] (bf16)
+  int rc = al_gemm_bf16(x, in_dim, (long long)rows * in_dim, rows, 1, lora_A, rank, in_dim, nullptr, t_ws, rank,
+                        (long long)rows * rank, 0, nullptr, 0, nullptr, stream);
+  if (rc) return rc;
+  // 2. out = x W^T + T (s B)^T + bias: the rank-r product rides in the frozen GEMM's TMEM accumulator
+  CUtensorMap ta, tb, ta2, tb2, to;
+  if ((rc = tmap_rows3d(&ta, x, 2, in_dim, rows, 1, in_dim, (uint64_t)rows * in_dim, 64, 128))) return rc;
+  if ((rc = tmap_weight(&tb, W, out_dim, in_dim))) return rc;
+  if ((rc = tmap_rows3d(&ta2, t_ws, 2, rank, rows, 1, rank, (uint64_t)rows * rank, 64, 128))) return rc;
+  if ((rc = tmap_weight(&tb2, lora_B_scaled, out_dim, rank))) return rc;
+  const int flags = out_dtype == 1 ? AL_EPI_OUT_F32 : 0;
+  if ((rc = tmap_rows3d(&to, out, out_dtype == 1 ? 4 : 2, out_dim, rows, 1, out_dim, (uint64_t)rows * out_dim,
+                        gemm_out_box_cols(flags), 128)))
+    return rc;
+  GemmParams p{};
+  p.m_per_batch = rows; p.batch = 1; p.N = out_dim; p.K = in_dim; p.K2 = rank; p.bias = bias;
+  rc = launch_gemm2(ta, tb, to, ta2, tb2, p, flags, num_sms(), (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
 // ----------------------------------------------------------------------------- splice
 int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
               const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,

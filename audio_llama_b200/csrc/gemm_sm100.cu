@@ -32,7 +32,8 @@ constexpr int gemm_smem_bytes() {
 template <int BN, int STAGES, int FLAGS>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmO, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
   constexpr bool OUT_F32 = (FLAGS & EPI_OUT_F32) != 0;
   constexpr bool DO_GELU = (FLAGS & EPI_GELU) != 0;
   constexpr bool REDUCE = (FLAGS & EPI_REDUCE_ADD) != 0;
@@ -79,7 +80,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   const int num_tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
-  const int num_kb = (p.K + BK - 1) / BK;
+  // K blocks of the main product, then (LoRA) K2 more blocks of a second operand pair accumulated into the same
+  // TMEM accumulator: out = A W^T + A2 W2^T, with A2 = x A_lora^T [M, r] and W2 = scaling * B_lora [N, r].
+  const int num_kb1 = (p.K + BK - 1) / BK;
+  const int num_kb = num_kb1 + (p.K2 + BK - 1) / BK;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -94,8 +98,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
-          tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0, b);
-          tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          if (kb < num_kb1) {
+            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0, b);
+            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          } else {
+            tma_load_3d(sA + s * A_BYTES, &tmA2, &full[s], (kb - num_kb1) * BK, m0, b);
+            tma_load_2d(sB + s * B_BYTES, &tmB2, &full[s], (kb - num_kb1) * BK, nt * BN);
+          }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -246,8 +255,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ----------------------------------------------------------------------------- host launch
 template <int BN, int STAGES, int FLAGS>
-static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmParams& p,
-                      int num_sms, cudaStream_t stream) {
+static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                      const CUtensorMap& tmB2, const GemmParams& p, int num_sms, cudaStream_t stream) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<BN, STAGES, FLAGS>;
@@ -257,7 +266,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   const int tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 384, smem, stream>>>(tmA, tmB, tmO, p);
+  kern<<<grid, 384, smem, stream>>>(tmA, tmB, tmO, tmA2, tmB2, p);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -267,18 +276,24 @@ int gemm_out_box_cols(int flags) { return (flags & EPI_OUT_F32) ? 32 : 64; }
 
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
                 int num_sms, cudaStream_t stream) {
+  p.K2 = 0;
+  return launch_gemm2(tmA, tmB, tmO, tmA, tmB, p, flags, num_sms, stream);
+}
+
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                 const CUtensorMap& tmB2, GemmParams p, int flags, int num_sms, cudaStream_t stream) {
   p.tiles_m_per_batch = (p.m_per_batch + BM - 1) / BM;
   p.tiles_n = (p.N + 255) / 256;
   switch (flags) {
-    case 0: return launch_one<256, 4, 0>(tmA, tmB, tmO, p, num_sms, stream);
-    case EPI_GELU: return launch_one<256, 4, EPI_GELU>(tmA, tmB, tmO, p, num_sms, stream);
-    case EPI_OUT_F32: return launch_one<256, 4, EPI_OUT_F32>(tmA, tmB, tmO, p, num_sms, stream);
+    case 0: return launch_one<256, 4, 0>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_GELU: return launch_one<256, 4, EPI_GELU>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_OUT_F32: return launch_one<256, 4, EPI_OUT_F32>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_REDUCE_ADD:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, p, num_sms, stream);
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_RESIDUAL:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, p, num_sms, stream);
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, p, num_sms, stream);
+      return launch_one<256, 4, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     default:
       set_error("launch_gemm: unsupported epilogue flags %d", flags);
       return -1;

@@ -20,6 +20,7 @@ struct GemmParams {
   int batch;
   int N;
   int K;
+  int K2;                  // extra contraction length of the second operand pair (LoRA rank), 0 = none
   int tiles_m_per_batch;   // filled by launch_gemm
   int tiles_n;             // filled by launch_gemm
   const float* bias;       // [N] or nullptr
@@ -33,6 +34,9 @@ struct GemmParams {
 int gemm_out_box_cols(int flags);   // inner box extent of the output tensor map (32 fp32 / 64 bf16)
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
                 int num_sms, cudaStream_t stream);
+// out = epilogue(A W^T + A2 W2^T + bias): second operand pair over p.K2, same accumulator (fused LoRA update).
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                 const CUtensorMap& tmB2, GemmParams p, int flags, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------ attention (attention_sm100.cu)
 // qkv: [B][T][3*H*64] bf16 (q pre-scaled), out: [B][T][H*64] bf16. tm_qkv: 3-D map, box {64,128,1}, SW128.

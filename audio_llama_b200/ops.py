@@ -195,5 +195,30 @@ def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optiona
     return out, mask_out, labels_out
 
 
+def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: torch.Tensor,
+                lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16) -> torch.Tensor:
+    """Frozen linear + LoRA (L1): x [..., in] bf16, w [out, in] bf16, lora_a [r, in], lora_b [out, r] (any float dtype).
+    out = x w^T + bias + scaling * (x a^T) b^T with the rank-r product accumulated inside the frozen GEMM."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    out_dim, in_dim = w.shape
+    r = lora_a.shape[0]
+    r_pad = (r + 7) // 8 * 8
+    a = torch.zeros(r_pad, in_dim, dtype=torch.bfloat16, device=x.device)
+    a[:r] = lora_a.detach().to(torch.bfloat16)
+    b = torch.zeros(out_dim, r_pad, dtype=torch.bfloat16, device=x.device)
+    b[:, :r] = (lora_b.detach().float() * scaling).to(torch.bfloat16)
+    x2 = x.reshape(-1, in_dim)
+    rows = x2.shape[0]
+    t_ws = torch.empty(rows, r_pad, dtype=torch.bfloat16, device=x.device)
+    out = torch.empty(*x.shape[:-1], out_dim, dtype=out_dtype, device=x.device)
+    if bias is not None:
+        bias = _req(bias.detach().float().contiguous(), torch.float32, "bias")
+    check(lib().al_lora_linear_forward(ptr(x2), rows, in_dim, out_dim, r_pad, ptr(w), ptr(bias), ptr(a), ptr(b),
+                                       ptr(t_ws), ptr(out), 1 if out_dtype == torch.float32 else 0, stream_ptr()),
+          "al_lora_linear_forward")
+    return out
+
+
 def launch_count() -> int:
     return int(lib().al_launch_count())

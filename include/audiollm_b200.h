@@ -120,6 +120,18 @@ int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_ou
                          float* y_ws, void* out, int out_dtype, long long out_ld, int rows_per_group,
                          long long out_group_stride, long long out_row_offset, al_stream_t stream);
 
+/* ---- L1: frozen linear + LoRA update ---------------------------------------------------------------
+ * Replaces lora_forward_hook(module, input, output, lora_layer) = output + (x @ (B @ A).T) * scaling
+ * (/root/reference/src/models/lora.py:20-21, 41-43) together with the frozen nn.Linear it hooks:
+ *   out = x W^T + bias + (x A^T)(s B)^T
+ * as two launches: T = x A^T ([rows][rank] bf16, t_ws) and one GEMM whose K loop runs over in_dim and then over
+ * rank, both into the same TMEM accumulator — the dense [out][in] delta of the reference is never formed.
+ * x [rows][in] bf16, W [out][in] bf16, bias [out] f32 or NULL, lora_A [rank][in] bf16, lora_B_scaled = scaling*B
+ * [out][rank] bf16 (rank a multiple of 8), out [rows][out] bf16 (out_dtype 0) or f32 (1). */
+int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W,
+                           const float* bias, const void* lora_A, const void* lora_B_scaled, void* t_ws, void* out,
+                           int out_dtype, al_stream_t stream);
+
 /* ---- S1 / S2: splice ------------------------------------------------------------------------------
  * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask
  * (allm.py:176-196) and the label extension (allm.py:81-89). Row map per sample (bit-exact contract):
