@@ -7,7 +7,8 @@
 //
 // One CTA = one query tile of 128 rows of one (batch, head); TWO CTAs are resident per SM (256 TMEM columns and
 // ~82 KB of shared memory each), so one CTA's start-up, barrier waits and MMAs run under the other's exps. 8 warps:
-//   warp 0   TMA producer: Q tile once, then K/V tiles through a 2-stage ring
+//   warp 0   TMA producer: Q tile once, then K tiles through a 3-stage ring and V tiles through a 2-stage ring
+//            (a K stage is free as soon as Q K_j^T has run, long before V_j is consumed)
 //   warp 1   MMA issuer:   S = Q K_j^T (SS, fp32 in TMEM), O += P V_j (A = P from TMEM, B = V MN-major smem)
 //   warp 2   TMEM allocator (256 columns: S | O | P)
 //   warps 4-7  softmax warpgroup, one thread per query row.
@@ -28,9 +29,10 @@ namespace al {
 constexpr int ATT_BQ = 128;       // query rows per tile
 constexpr int ATT_BKV = 128;      // kv rows per tile
 constexpr int ATT_HD = 64;
-constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_K_STAGES = 3;
+constexpr int ATT_V_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // 16 KB: any of Q / K / V tile
-constexpr int ATT_SMEM = ATT_TILE_BYTES + ATT_KV_STAGES * 2 * ATT_TILE_BYTES + 256 + 1024;
+constexpr int ATT_SMEM = (1 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 256 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float ATT_TAU = 8.0f;   // lazy-rescale threshold, log2 units
 constexpr int POLY_PAIRS = 1;     // of every 4 pairs, how many use the FMA-pipe exp2
@@ -69,12 +71,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // 1 tile
-  uint8_t* sKV = smem + ATT_TILE_BYTES;                 // stages x {K, V}
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ATT_KV_STAGES * 2 * ATT_TILE_BYTES);
+  uint8_t* sK = smem + ATT_TILE_BYTES;                  // K ring
+  uint8_t* sV = sK + ATT_K_STAGES * ATT_TILE_BYTES;     // V ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_V_STAGES * ATT_TILE_BYTES);
   uint64_t* q_full = bars;                              // 1
-  uint64_t* kv_full = bars + 1;                         // KV_STAGES
-  uint64_t* kv_empty = kv_full + ATT_KV_STAGES;         // KV_STAGES
-  uint64_t* s_full = kv_empty + ATT_KV_STAGES;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + ATT_K_STAGES;
+  uint64_t* v_full = k_empty + ATT_K_STAGES;
+  uint64_t* v_empty = v_full + ATT_V_STAGES;
+  uint64_t* s_full = v_empty + ATT_V_STAGES;
   uint64_t* s_empty = s_full + 1;
   uint64_t* p_full = s_empty + 1;
   uint64_t* o_full = p_full + 1;
@@ -91,9 +96,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < ATT_KV_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < ATT_K_STAGES; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+    }
+    for (int s = 0; s < ATT_V_STAGES; ++s) {
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(s_empty, 128);
@@ -120,15 +129,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       if (lane == 0) {
         mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
         tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
-        int s = 0;
-        uint32_t ph = 0;
+        // K runs ahead of V: K_{j+1} is requested before V_j so that Q K_{j+1}^T is never starved
+        int ks = 0, vs = 0;
+        uint32_t kph = 0, vph = 0;
+        auto load_k = [&](int j) {
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_arrive_expect_tx(&k_full[ks], ATT_TILE_BYTES);
+          tma_load_3d(sK + ks * ATT_TILE_BYTES, &tmQKV, &k_full[ks], d + h * ATT_HD, j * ATT_BKV, b);
+          if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
+        };
+        load_k(0);
         for (int j = 0; j < nkv; ++j) {
-          mbar_wait(&kv_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * ATT_TILE_BYTES);
-          uint8_t* kdst = sKV + s * 2 * ATT_TILE_BYTES;
-          tma_load_3d(kdst, &tmQKV, &kv_full[s], d + h * ATT_HD, j * ATT_BKV, b);
-          tma_load_3d(kdst + ATT_TILE_BYTES, &tmQKV, &kv_full[s], 2 * d + h * ATT_HD, j * ATT_BKV, b);
-          if (++s == ATT_KV_STAGES) { s = 0; ph ^= 1; }
+          if (j + 1 < nkv) load_k(j + 1);
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_arrive_expect_tx(&v_full[vs], ATT_TILE_BYTES);
+          tma_load_3d(sV + vs * ATT_TILE_BYTES, &tmQKV, &v_full[vs], 2 * d + h * ATT_HD, j * ATT_BKV, b);
+          if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
         }
       }
     } else if (warp == 1) {
@@ -136,50 +152,48 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
       constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
       const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t kv_addr = smem_u32(sKV);
+      const uint32_t k_addr = smem_u32(sK);
+      const uint32_t v_addr = smem_u32(sV);
       auto issue_s = [&](int stage) {
         const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
-        const uint64_t kd = umma_desc_sw128(kv_addr + stage * 2 * ATT_TILE_BYTES, 16, 1024);
+        const uint64_t kd = umma_desc_sw128(k_addr + stage * ATT_TILE_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
+        umma_commit(&k_empty[stage]);          // the K stage is free once these MMAs have run
         umma_commit(s_full);
       };
       auto issue_o = [&](int stage, bool first_tile) {
         // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B
         // = +128 in the descriptor's (>>4) start-address field.
-        const uint64_t vd = umma_desc_sw128(kv_addr + stage * 2 * ATT_TILE_BYTES + ATT_TILE_BYTES, 1024, 1024);
+        const uint64_t vd = umma_desc_sw128(v_addr + stage * ATT_TILE_BYTES, 1024, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
           umma_ts(tO, tP + k * 8, vd + 128 * k, IDESC_O, (k != 0) || !first_tile);
+        umma_commit(&v_empty[stage]);
         umma_commit(o_full);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
       if (lane == 0) issue_s(0);
       __syncwarp();
-      int s = 0;
-      uint32_t ph = 0;
+      int ks = 1, vs = 0;                            // next K stage to consume, current V stage
+      uint32_t kph = 0, vph = 0;
       for (int j = 0; j < nkv; ++j) {
-        int sn = s + 1;
-        uint32_t phn = ph;
-        if (sn == ATT_KV_STAGES) { sn = 0; phn ^= 1; }
         if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
-          mbar_wait(&kv_full[sn], phn);
+          mbar_wait(&k_full[ks], kph);
           mbar_wait(s_empty, j & 1);
           tc_fence_after();
-          if (lane == 0) issue_s(sn);
+          if (lane == 0) issue_s(ks);
           __syncwarp();
+          if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
         }
+        mbar_wait(&v_full[vs], vph);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        if (lane == 0) {
-          issue_o(s, j == 0);
-          umma_commit(&kv_empty[s]);
-        }
+        if (lane == 0) issue_o(vs, j == 0);
         __syncwarp();
-        s = sn;
-        ph = phn;
+        if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
       }
     }
   } else {
