@@ -9,7 +9,7 @@ namespace al {
 // Replaces nn.LayerNorm of HF WhisperEncoderLayer (modeling_whisper.py:393, 403), the encoder's final
 // layer_norm (:643) and AudioProjector.layers[3] (/root/reference/src/models/projector.py:15).
 template <int MAXV, bool OUT_F32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MAXV <= 12) ? 4 : 1)   // d <= 1536: <= 64 registers, 32 warps / SM in flight
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  void* __restrict__ out, int rows, int d, float eps, long long out_ld, int rows_per_group,
                  long long out_group_stride, long long out_row_offset) {

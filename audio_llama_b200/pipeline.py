@@ -20,6 +20,29 @@ from .encoder import WhisperEncoderB200
 from .models.projector import projector_forward_raw
 
 
+class HostBatch:
+    """Pinned host buffers of one batch in the reference dataloader's layout (waveforms instead of CPU-made mel):
+    wave [B, 480000] f32, input_ids / attention_mask / labels [B, T] i64, plus the output buffers the step's
+    result is copied back into."""
+
+    def __init__(self, B: int, T: int, d_out: int, dtype, n_samples: int = 480000):
+        pin = lambda *shape, dt: torch.empty(*shape, dtype=dt).pin_memory()
+        S = N_CTX + 2 + T
+        self.wave = pin(B, n_samples, dt=torch.float32)
+        self.ids = pin(B, T, dt=torch.int64)
+        self.mask = pin(B, T, dt=torch.int64)
+        self.labels = pin(B, T, dt=torch.int64)
+        self.out_embeds = pin(B, S, d_out, dt=dtype)
+        self.out_mask = pin(B, S, dt=torch.float32)
+        self.out_labels = pin(B, S, dt=torch.int64)
+
+    def h2d_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.wave, self.ids, self.mask, self.labels))
+
+    def d2h_bytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.out_embeds, self.out_mask, self.out_labels))
+
+
 class AudioConditioner:
     def __init__(self, cfg: EncoderConfig, encoder_weights: Dict[str, torch.Tensor],
                  projector_weights: Dict[str, torch.Tensor], embed_table: torch.Tensor, start_id: int, end_id: int,
@@ -38,6 +61,67 @@ class AudioConditioner:
         self.d_out = self.pw["layers.2.weight"].shape[0]
         self._mel = torch.empty(max_batch, cfg.n_mels, N_FRAMES, dtype=torch.float32, device=self.device)
         self._enc = torch.empty(max_batch, N_CTX, cfg.d_model, dtype=torch.bfloat16, device=self.device)
+
+    # ------------------------------------------------------------------ host-buffer entry point
+    def _host_state(self, B, T):
+        key = (B, T)
+        st = getattr(self, "_hs", None)
+        if st is None or st["key"] != key:
+            dev = self.device
+            S = N_CTX + 2 + T
+            mk = lambda: dict(
+                wave=torch.empty(B, 480000, dtype=torch.float32, device=dev), ids=torch.empty(B, T, dtype=torch.int64, device=dev),
+                mask=torch.empty(B, T, dtype=torch.int64, device=dev), labels=torch.empty(B, T, dtype=torch.int64, device=dev),
+                emb=torch.empty(B, S, self.d_out, dtype=self.table.dtype, device=dev),
+                h2d_done=torch.cuda.Event(), compute_done=torch.cuda.Event(), d2h_done=torch.cuda.Event())
+            st = dict(key=key, slots=[mk(), mk()], i=0, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), primed=None)
+            self._hs = st
+        return st
+
+    @torch.no_grad()
+    def run_host(self, batches):
+        """Host buffers in, host buffers out: for each HostBatch, copy its inputs to the GPU, run the path, copy
+        inputs_embeds / mask / labels back into the batch's pinned output buffers. Copies run on their own
+        streams with two device slots, so the H2D of batch i+1 and the D2H of batch i-1 overlap the kernels of
+        batch i. Returns when every output is on the host."""
+        batches = list(batches)
+        if not batches:
+            return
+        B, T = batches[0].ids.shape
+        st = self._host_state(B, T)
+        cur = torch.cuda.current_stream(self.device)
+
+        def upload(hb, slot):
+            with torch.cuda.stream(st["h2d"]):
+                st["h2d"].wait_event(slot["compute_done"])        # the slot's previous kernels have read its inputs
+                slot["wave"].copy_(hb.wave, non_blocking=True)
+                slot["ids"].copy_(hb.ids, non_blocking=True)
+                slot["mask"].copy_(hb.mask, non_blocking=True)
+                slot["labels"].copy_(hb.labels, non_blocking=True)
+                slot["h2d_done"].record(st["h2d"])
+
+        slots = st["slots"]
+        slots[0]["compute_done"].record(cur)
+        slots[1]["compute_done"].record(cur)
+        upload(batches[0], slots[0])
+        for i, hb in enumerate(batches):
+            slot = slots[i & 1]
+            if i + 1 < len(batches):
+                upload(batches[i + 1], slots[(i + 1) & 1])
+            cur.wait_event(slot["h2d_done"])
+            cur.wait_event(slot["d2h_done"])                      # the slot's previous result has left `emb`
+            emb, mo, lo = self(slot["wave"], slot["ids"], slot["mask"], slot["labels"], out=slot["emb"])
+            slot["compute_done"].record(cur)
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(slot["compute_done"])
+                hb.out_embeds.copy_(emb, non_blocking=True)
+                hb.out_mask.copy_(mo, non_blocking=True)
+                hb.out_labels.copy_(lo, non_blocking=True)
+                slot["d2h_done"].record(st["d2h"])
+                mo.record_stream(st["d2h"])
+                lo.record_stream(st["d2h"])
+        cur.wait_stream(st["d2h"])
+        cur.wait_stream(st["h2d"])
 
     @torch.no_grad()
     def mel(self, wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -227,30 +227,23 @@ def run_product(args):
     del ew
 
     # this rank's shard of the global batch (weak scaling: 32 clips per rank), pinned host buffers
-    wave_h = torch.from_numpy(synth.synth_batch(B, first=rank * B)).pin_memory()
-    ids, mask, labels = synth.synth_text(B, T_TXT, VOCAB, seed=7 + rank)
-    ids_h, mask_h, labels_h = ids.pin_memory(), mask.pin_memory(), labels.pin_memory()
+    from audio_llama_b200.pipeline import HostBatch
     S = 1502 + T_TXT
-    emb_h = torch.empty(B, S, D_LLAMA, dtype=torch.bfloat16).pin_memory()
-    mask_o_h = torch.empty(B, S, dtype=torch.float32).pin_memory()
-    lab_o_h = torch.empty(B, S, dtype=torch.int64).pin_memory()
-    wave_d, ids_d, mask_d, labels_d = (t.to(dev) for t in (wave_h, ids_h, mask_h, labels_h))
+    hb = HostBatch(B, T_TXT, D_LLAMA, torch.bfloat16)
+    hb.wave.copy_(torch.from_numpy(synth.synth_batch(B, first=rank * B)))
+    ids, mask, labels = synth.synth_text(B, T_TXT, VOCAB, seed=7 + rank)
+    hb.ids.copy_(ids); hb.mask.copy_(mask); hb.labels.copy_(labels)
+    wave_d, ids_d, mask_d, labels_d = (t.to(dev) for t in (hb.wave, hb.ids, hb.mask, hb.labels))
     emb_d = torch.empty(B, S, D_LLAMA, dtype=torch.bfloat16, device=dev)
-    h2d = sum(t.numel() * t.element_size() for t in (wave_h, ids_h, mask_h, labels_h))
-    d2h = sum(t.numel() * t.element_size() for t in (emb_h, mask_o_h, lab_o_h))
+    h2d, d2h = hb.h2d_bytes(), hb.d2h_bytes()
 
     def step_resident():
         return cond(wave_d, ids_d, mask_d, labels_d, out=emb_d)
 
-    def step_e2e():
-        w = wave_h.to(dev, non_blocking=True)
-        i = ids_h.to(dev, non_blocking=True)
-        m = mask_h.to(dev, non_blocking=True)
-        l = labels_h.to(dev, non_blocking=True)
-        e, mo, lo = cond(w, i, m, l, out=emb_d)
-        emb_h.copy_(e, non_blocking=True)
-        mask_o_h.copy_(mo, non_blocking=True)
-        lab_o_h.copy_(lo, non_blocking=True)
+    def run_e2e(steps):
+        # the public host-buffer call: every step uploads its waveforms / ids from pinned host memory and downloads
+        # inputs_embeds + mask + labels; copies of neighbouring steps overlap the kernels (two device slots)
+        cond.run_host([hb] * steps)
 
     def barrier():
         if world > 1:
@@ -311,10 +304,28 @@ def run_product(args):
     enc_ms = float(np.mean([ev[4 * i + 1].elapsed_time(ev[4 * i + 2]) for i in range(args.steps)]))
     tail_ms = float(np.mean([ev[4 * i + 2].elapsed_time(ev[4 * i + 3]) for i in range(args.steps)]))
 
-    # --- timed region 2: end to end with host buffers
-    for _ in range(2):
-        step_e2e()
-    e2e_ms = timed(step_e2e, args.steps)
+    # --- timed region 2: end to end with host buffers (all K steps inside one timed call)
+    run_e2e(2)
+    torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_e2e(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item())
+    assert torch.equal(hb.out_embeds[:, 1502:], table[hb.ids])          # the result really is on the host
+    # splice alone (HBM-bound): text + delimiter rows gathered, mask + labels written, audio rows already in place
+    sp0, sp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sp0.record()
+    for _ in range(20):
+        ops.splice(cond.table, ids_d, mask_d, labels_d, 1500, cond.start_id, cond.end_id, audio_rows=None, out=emb_d)
+    sp1.record()
+    torch.cuda.synchronize()
+    splice_ms = sp0.elapsed_time(sp1) / 20
 
     if rank != 0:
         if world > 1:
@@ -350,6 +361,10 @@ def run_product(args):
     kernels["mel (2 launches)"] = {"ms_per_step": mel_ms, "gbs_algorithmic": mel_bytes / (mel_ms / 1e3) / 1e9,
                                    "gbs_incl_floor_pass": mel_bytes_2pass / (mel_ms / 1e3) / 1e9,
                                    "frac_of_hbm": mel_bytes / (mel_ms / 1e3) / 1e9 / pk["hbm"]}
+    splice_bytes = B * (2 * (T_TXT + 2) * D_LLAMA * 2 + S * (4 + 8) + T_TXT * 24)   # rows read+written, mask+labels out, ids/mask/labels in
+    kernels["splice (1 launch, L2-warm repeat)"] = {"ms": splice_ms, "gbs_algorithmic": splice_bytes / (splice_ms / 1e3) / 1e9,
+                                                    "frac_of_hbm": splice_bytes / (splice_ms / 1e3) / 1e9 / pk["hbm"],
+                                                    "note": "138 MB per call fits the 126 MB L2 only partly; repeat calls re-read the same table rows"}
     kernels["projector+splice (4 launches)"] = {"ms_per_step": tail_ms,
                                                 "projector_tflops_lower_bound": fl["projector"] * B / (tail_ms / 1e3) / 1e12}
     kernels["encoder (all launches)"] = {"ms_per_step": enc_ms,
