@@ -81,7 +81,7 @@ static int tmap_rows3d(CUtensorMap* m, const void* base, int elem_bytes, uint64_
 static int tmap_weight(CUtensorMap* m, const void* W, uint64_t N, uint64_t K) {
   const uint64_t dims[2] = {K, N};
   const uint64_t str[2] = {2, K * 2};
-  const uint32_t box[2] = {64, 256};
+  const uint32_t box[2] = {64, 128};   // half of a 256-row weight tile: one CTA of a pair stages one box
   return make_tmap(m, W, 2, 2, dims, str, box, true);
 }
 
@@ -279,7 +279,11 @@ static void encoder_carve(al_encoder* e, bool assign) {
 
 extern "C" {
 
-int al_version(void) { return 100; }
+int al_version(void) { return 101; }
+int al_gemm_set_mode(int pair) {
+  gemm_set_mode(pair);
+  return 0;
+}
 const char* al_last_error(void) { return g_err; }
 long long al_launch_count(void) { return g_launches; }
 

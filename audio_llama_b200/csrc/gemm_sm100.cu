@@ -6,6 +6,8 @@
 //   W   : [N][K] bf16 (nn.Linear weight layout), K contiguous.
 //   out : [batch][m_per_batch][N] bf16 or fp32.
 //
+// Two forms, same code path (template flag CTA2): one CTA per 128x256 tile, or a CTA PAIR per 256x256 tile with
+// tcgen05.mma.cta_group::2 (default; AUDIOLLM_B200_GEMM=single selects the former).
 // Roles (384 threads): warp 0 = TMA producer (one lane), warp 1 = tcgen05.mma issuer (one lane),
 // warp 2 = TMEM allocator, warps 4-7 and 8-11 = two epilogue warpgroups that take alternate column chunks of
 // the tile (TMEM -> registers -> bias / GELU / residual -> swizzled smem -> TMA store). Operands are staged by TMA into 128B-swizzled K-major tiles; the fp32 accumulator lives
@@ -15,35 +17,51 @@
 // Replaces, on the reference's path: every nn.Linear / Conv1d of HF WhisperEncoder
 // (modeling_whisper.py:279-282, 310, 404-406, 567-568, 619-620) and of AudioProjector
 // (/root/reference/src/models/projector.py:11-16).
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
 namespace al {
 
-constexpr int BM = 128;
+constexpr int BM = 128;            // rows per CTA
 constexpr int BK = 64;
 constexpr int STG_BYTES = 16384;   // one epilogue staging buffer: 128 rows x 128 B
 
-template <int BN, int STAGES>
-constexpr int gemm_smem_bytes() {
-  return STAGES * (BM * BK * 2 + BN * BK * 2) + 2 * STG_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+// CTA2 = false: one CTA per 128 x 256 tile (A 16 KB + B 32 KB per stage, 4 stages).
+// CTA2 = true : a CTA PAIR (cluster of 2, one tcgen05.mma.cta_group::2 per K step) per 256 x 256 tile. Each CTA
+//               stages its own 128 rows of A and HALF of B (128 of the 256 weight rows): 32 KB per stage, 6 stages.
+//               Per SM that is 2/3 of the shared-memory fill + operand-read traffic of the single-CTA form for
+//               the same MMA rate (ncu showed the single-CTA kernel at ~80 % tensor-active with shared memory
+//               the busiest unit), and half the L2 -> SM weight traffic.
+template <bool CTA2>
+__host__ __device__ constexpr int gemm_stages() { return CTA2 ? 6 : 4; }
+template <bool CTA2>
+__host__ __device__ constexpr int gemm_smem_bytes() {
+  return gemm_stages<CTA2>() * (BM * BK * 2 + (CTA2 ? 128 : 256) * BK * 2) + 2 * STG_BYTES + 256 /*barriers*/ +
+         1024 /*alignment slack*/;
 }
 
-template <int BN, int STAGES, int FLAGS>
+template <int FLAGS, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+  constexpr int BN = 256;
+  constexpr int STAGES = gemm_stages<CTA2>();
   constexpr bool OUT_F32 = (FLAGS & EPI_OUT_F32) != 0;
   constexpr bool DO_GELU = (FLAGS & EPI_GELU) != 0;
   constexpr bool REDUCE = (FLAGS & EPI_REDUCE_ADD) != 0;
   constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
   constexpr bool RESID = (FLAGS & EPI_RESIDUAL) != 0;
   constexpr int A_BYTES = BM * BK * 2;
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_ROWS = CTA2 ? 128 : 256;       // weight rows staged by this CTA
+  constexpr int B_BYTES = B_ROWS * BK * 2;
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 B per row)
   constexpr int NCHUNK = BN / CH;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BM, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
+  constexpr int TILE_M = CTA2 ? 256 : 128;       // rows per scheduled tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,62 +76,76 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0;        // 0 = leader (issues the MMAs)
+  const int worker = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;  // tile-scheduler slot
+  const int n_workers = CTA2 ? (gridDim.x >> 1) : gridDim.x;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 1);                    // (pair: only the leader's is used; both CTAs' TMA bytes land on it)
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 256);
+      mbar_init(&tempty[a], CTA2 ? 512 : 256);   // (pair: the leader's collects both CTAs' epilogue threads)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_alloc_pair<2 * BN>(tmem_ptr);
+    else tmem_alloc<2 * BN>(tmem_ptr);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
+  const int tiles_m = (p.m_per_batch + TILE_M - 1) / TILE_M;
+  const int num_tiles = p.batch * tiles_m * p.tiles_n;
   // K blocks of the main product, then (LoRA) K2 more blocks of a second operand pair accumulated into the same
   // TMEM accumulator: out = A W^T + A2 W2^T, with A2 = x A_lora^T [M, r] and W2 = scaling * B_lora [N, r].
   const int num_kb1 = (p.K + BK - 1) / BK;
   const int num_kb = num_kb1 + (p.K2 + BK - 1) / BK;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (one per CTA)
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = worker; t < num_tiles; t += n_workers) {
         const int nt = t % p.tiles_n;
         const int mt = t / p.tiles_n;
-        const int m0 = (mt % p.tiles_m_per_batch) * BM;
-        const int b = mt / p.tiles_m_per_batch;
+        const int m0 = (mt % tiles_m) * TILE_M + rank * BM;
+        const int b = mt / tiles_m;
+        const int n0 = nt * BN + rank * B_ROWS;                  // pair: this CTA's half of the weight rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
-          if (kb < num_kb1) {
-            tma_load_3d(sA + s * A_BYTES, &tmA, &full[s], kb * BK, m0, b);
-            tma_load_2d(sB + s * B_BYTES, &tmB, &full[s], kb * BK, nt * BN);
+          const bool second = kb >= num_kb1;
+          const int k0 = (second ? kb - num_kb1 : kb) * BK;
+          const CUtensorMap* ma = second ? &tmA2 : &tmA;
+          const CUtensorMap* mb = second ? &tmB2 : &tmB;
+          if constexpr (CTA2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+            tma_load_3d_pair(sA + s * A_BYTES, ma, &full[s], k0, m0, b);
+            tma_load_2d_pair(sB + s * B_BYTES, mb, &full[s], k0, n0);
           } else {
-            tma_load_3d(sA + s * A_BYTES, &tmA2, &full[s], (kb - num_kb1) * BK, m0, b);
-            tma_load_2d(sB + s * B_BYTES, &tmB2, &full[s], (kb - num_kb1) * BK, nt * BN);
+            mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+            tma_load_3d(sA + s * A_BYTES, ma, &full[s], k0, m0, b);
+            tma_load_2d(sB + s * B_BYTES, mb, &full[s], k0, n0);
+            tma_load_2d(sB + s * B_BYTES + B_BYTES / 2, mb, &full[s], k0, n0 + 128);
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = worker; t < num_tiles; t += n_workers) {
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -124,10 +156,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-          umma_commit(&empty[s]);
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field
+            if constexpr (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          if constexpr (CTA2) {
+            umma_commit_pair(&empty[s]);
+            if (kb == num_kb - 1) umma_commit_pair(&tfull[as]);
+          } else {
+            umma_commit(&empty[s]);
+            if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -135,20 +174,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (2 warpgroups)
+    // ------------------------------------------------------------------ epilogue (2 warpgroups per CTA)
     const int wg = (warp - 4) >> 2;               // chunks c with c % 2 == wg
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-    const int row = quarter * 32 + lane;          // row inside the 128-row tile
+    const int row = quarter * 32 + lane;          // row inside this CTA's 128 rows
     const int etid = threadIdx.x - 128 - wg * 128;
     uint8_t* stg = sStg + wg * STG_BYTES;         // one staging buffer per warpgroup
     uint8_t* rowp = stg + row * 128;
     int as = 0;
     uint32_t aph = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = worker; t < num_tiles; t += n_workers) {
       const int nt = t % p.tiles_n;
       const int mt = t / p.tiles_n;
-      const int m0 = (mt % p.tiles_m_per_batch) * BM;
-      const int b = mt / p.tiles_m_per_batch;
+      const int m0 = (mt % tiles_m) * TILE_M + rank * BM;
+      const int b = mt / tiles_m;
       const int n0 = nt * BN;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -173,9 +212,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
         }
         const int col0 = n0 + c * CH;
-        const bool full = col0 + CH <= p.N;
+        const bool fullc = col0 + CH <= p.N;
         if (p.bias != nullptr) {
-          if (full) {
+          if (fullc) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
@@ -192,7 +231,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (ROWAUX) {
           const float* ap = p.aux + static_cast<size_t>(grow) * p.aux_ld;
-          if (full) {
+          if (fullc) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 av = __ldg(reinterpret_cast<const float4*>(ap + col0 + j));
@@ -207,7 +246,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // residual stream, possibly the output buffer itself: this CTA is the only reader and writer of this
           // tile, and the read happens before its own TMA store -> plain (coherent) loads, no atomics
           const float* rp = p.resid + (static_cast<size_t>(b) * p.resid_batch_stride + static_cast<size_t>(grow) * p.resid_ld);
-          if (full) {
+          if (fullc) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
               const float4 rv = *reinterpret_cast<const float4*>(rp + col0 + j);
@@ -235,43 +274,73 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_proxy_async_smem();
         named_bar_sync(2 + 2 * wg, 128);
-        if (etid == 0) {
+        if (etid == 0 && m0 < p.m_per_batch) {     // (pair: the peer's rows may lie wholly past the end)
           if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stg, col0, m0, b);
           else tma_store_3d(&tmO, stg, col0, m0, b);
           tma_commit_group();
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      if constexpr (CTA2) mbar_arrive_cluster(&tempty[as], 0);   // accumulator stage drained: tell the leader's MMA warp
+      else mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
     if (etid == 0) tma_wait_group<0>();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // pair: the peer's smem / barriers stay alive until both are done
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_dealloc_pair<2 * BN>(tmem_base);
+    else tmem_dealloc<2 * BN>(tmem_base);
+  }
 }
 
 // ----------------------------------------------------------------------------- host launch
-template <int BN, int STAGES, int FLAGS>
+static int g_use_pair = -1;   // -1 = read AUDIOLLM_B200_GEMM (pair | single) once; default pair
+
+static bool use_pair() {
+  if (g_use_pair < 0) {
+    const char* e = getenv("AUDIOLLM_B200_GEMM");
+    g_use_pair = (e && strcmp(e, "single") == 0) ? 0 : 1;
+  }
+  return g_use_pair == 1;
+}
+void gemm_set_mode(int pair) { g_use_pair = pair ? 1 : 0; }
+
+template <int FLAGS, bool CTA2>
 static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                       const CUtensorMap& tmB2, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  constexpr int smem = gemm_smem_bytes<CTA2>();
   static bool attr_set = false;
-  auto kern = gemm_bf16_kernel<BN, STAGES, FLAGS>;
+  auto kern = gemm_bf16_kernel<FLAGS, CTA2>;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const int tiles = p.batch * p.tiles_m_per_batch * p.tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, 384, smem, stream>>>(tmA, tmB, tmO, tmA2, tmB2, p);
-  AL_CHECK_CUDA(cudaGetLastError());
+  const int tile_m = CTA2 ? 256 : 128;
+  const int tiles = p.batch * ((p.m_per_batch + tile_m - 1) / tile_m) * p.tiles_n;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  if (CTA2) {
+    const int pairs = num_sms / 2;
+    cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+  }
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  AL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmA2, tmB2, p));
   return 0;
 }
 
-int gemm_tile_n(int flags) { (void)flags; return 256; }
 int gemm_out_box_cols(int flags) { return (flags & EPI_OUT_F32) ? 32 : 64; }
 
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
@@ -280,20 +349,27 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   return launch_gemm2(tmA, tmB, tmO, tmA, tmB, p, flags, num_sms, stream);
 }
 
+template <int FLAGS>
+static int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                       const CUtensorMap& tmB2, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (use_pair()) return launch_one<FLAGS, true>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+  return launch_one<FLAGS, false>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+}
+
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                  const CUtensorMap& tmB2, GemmParams p, int flags, int num_sms, cudaStream_t stream) {
-  p.tiles_m_per_batch = (p.m_per_batch + BM - 1) / BM;
+  p.tiles_m_per_batch = 0;   // (derived in the kernel from the tile height of the chosen form)
   p.tiles_n = (p.N + 255) / 256;
   switch (flags) {
-    case 0: return launch_one<256, 4, 0>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
-    case EPI_GELU: return launch_one<256, 4, EPI_GELU>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
-    case EPI_OUT_F32: return launch_one<256, 4, EPI_OUT_F32>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case 0: return launch_mode<0>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_GELU: return launch_mode<EPI_GELU>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_OUT_F32: return launch_mode<EPI_OUT_F32>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_REDUCE_ADD:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_RESIDUAL:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
-      return launch_one<256, 4, EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     default:
       set_error("launch_gemm: unsupported epilogue flags %d", flags);
       return -1;

@@ -31,6 +31,7 @@ struct GemmParams {
   long long resid_batch_stride;
 };
 
+void gemm_set_mode(int pair);        // 1 = CTA-pair (cta_group::2) kernel, 0 = single-CTA kernel
 int gemm_out_box_cols(int flags);   // inner box extent of the output tensor map (32 fp32 / 64 bf16)
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
                 int num_sms, cudaStream_t stream);

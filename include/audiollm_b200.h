@@ -68,6 +68,10 @@ int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride
                  long long o_batch_stride, int flags, const float* aux, int aux_ld, const float* resid,
                  al_stream_t stream);
 
+/* GEMM kernel form: 1 = CTA pair per 256x256 tile (tcgen05.mma.cta_group::2, default), 0 = one CTA per 128x256
+ * tile. Same results; the environment variable AUDIOLLM_B200_GEMM=single|pair sets the default. */
+int al_gemm_set_mode(int pair);
+
 /* LayerNorm(x[rows][d] f32) -> out (out_dtype 0 bf16 / 1 f32). Output row of input row r:
  * (r / rows_per_group) * out_group_stride + out_row_offset + r % rows_per_group, rows of out_ld elements. */
 int al_layernorm(const float* x, const float* gamma, const float* beta, void* out, int rows, int d, float eps,
