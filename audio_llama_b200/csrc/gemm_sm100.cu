@@ -227,7 +227,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if constexpr (DO_GELU) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = gelu_erf_fast(v[j]);
+          for (int j = 0; j < CH; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
         }
         if constexpr (ROWAUX) {
           const float* ap = p.aux + static_cast<size_t>(grow) * p.aux_ld;
