@@ -115,6 +115,21 @@ def test_audiollm_error_and_text_only(model):
         model._process_audio_features(torch.zeros(1, 1, 128, 2999).cuda())
 
 
+def test_audiollm_generate(model):
+    """generate(): same conditioning, stock HF sampling on inputs_embeds; returns only the new tokens (allm.py:333-346)."""
+    ids, mask, _ = (t.cuda() for t in synth.synth_text(1, 8, VOCAB))
+    feats = LogMelExtractor(128)([synth.synth_clip(0)], sampling_rate=16000).input_features.unsqueeze(1)
+    tok = model.tokenizer
+    tok.pad_token_id, tok.bos_token_id, tok.eos_token_id = 0, 1, None
+    tok.decode = lambda t, skip_special_tokens=True: " ".join(str(int(x)) for x in t)
+    out = model.generate(input_ids=ids, attention_mask=mask, audio_features=feats, max_new_tokens=5, do_sample=False,
+                         temperature=None, top_p=None)
+    assert isinstance(out, str)
+    out2 = model.generate(input_ids=ids, attention_mask=mask, audio_features=feats, max_new_tokens=5, do_sample=False,
+                          temperature=None, top_p=None)
+    assert out == out2                                         # greedy + deterministic kernels
+
+
 def test_feature_extractor_api():
     fe = LogMelExtractor(80)
     x = synth.synth_clip(1, n_samples=50000)
