@@ -177,12 +177,51 @@ def allm_golden():
     np.savez_compressed(os.path.join(HERE, "allm_config1.npz"), **out)
 
 
+def checkpoint_golden():
+    """A checkpoint.pt written by the REFERENCE's own save_checkpoint (train.py:102-131) for a tiny model."""
+    import argparse
+    import shutil
+    import tempfile
+    from types import SimpleNamespace
+    from models.projector import AudioProjector
+    from models.lora import LoRALayer
+    import importlib.util
+    # train.py configures logging / imports wandb at import time; load only save_checkpoint's source
+    src = open("/root/reference/src/train.py").read()
+    start = src.index("def save_checkpoint(")
+    end = src.index("def evaluate(")
+    ns = {"os": os, "torch": torch, "logger": SimpleNamespace(info=lambda *a, **k: None)}
+    exec(src[start:end], ns)
+    torch.manual_seed(3)
+    model = SimpleNamespace(projector=AudioProjector(16, 24),
+                            lora_layers={"model.layers.0.self_attn.q_proj": LoRALayer(24, 24, rank=4),
+                                         "model.layers.0.mlp.down_proj": LoRALayer(48, 24, rank=4)})
+    for l in model.lora_layers.values():
+        torch.nn.init.normal_(l.lora_A, std=0.02)
+    params = list(model.projector.parameters()) + [p for l in model.lora_layers.values() for p in l.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    x = torch.randn(5, 16)
+    (model.projector(x).sum()).backward()
+    opt.step(); sched.step()
+    tmp = tempfile.mkdtemp()
+    args = argparse.Namespace(output_dir=tmp, learning_rate=1e-3, lora_rank=4)
+    ns["save_checkpoint"](model, opt, sched, 7, 1, args, dataset_config={"text_key": "text"})
+    shutil.copy(os.path.join(tmp, "checkpoint-7", "checkpoint.pt"), os.path.join(HERE, "reference_checkpoint.pt"))
+    with torch.no_grad():
+        y = model.projector(x)
+    np.savez_compressed(os.path.join(HERE, "reference_checkpoint_io.npz"), x=x.numpy(), y=y.numpy(),
+                        lora_A0=model.lora_layers["model.layers.0.self_attn.q_proj"].lora_A.detach().numpy())
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     mel_golden()
     encoder_golden()
     reference_modules_golden()
     allm_golden()
+    checkpoint_golden()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -173,3 +173,59 @@ def test_gradient_allreduce_world2_gloo():
         p.join(60)
         assert p.exitcode == 0
     assert torch.allclose(flat, ref, atol=1e-6)
+
+
+def test_checkpoint_reference_format_roundtrip(golden_dir, tmp_path):
+    """A checkpoint.pt written by the reference's own save_checkpoint loads; ours has the same layout; resume works."""
+    import argparse
+    from types import SimpleNamespace
+    from audio_llama_b200 import checkpoint as C
+    ref_file = os.path.join(golden_dir, "reference_checkpoint.pt")
+    g = np.load(os.path.join(golden_dir, "reference_checkpoint_io.npz"))
+
+    def fresh():
+        torch.manual_seed(99)
+        m = SimpleNamespace(projector=nn.Sequential(), lora_layers={})
+        m.projector = _RefShapedProjector(16, 24)
+        m.lora_layers = {"model.layers.0.self_attn.q_proj": LoRALayer(24, 24, rank=4),
+                         "model.layers.0.mlp.down_proj": LoRALayer(48, 24, rank=4)}
+        return m
+
+    m = fresh()
+    params = list(m.projector.parameters()) + [p for l in m.lora_layers.values() for p in l.parameters()]
+    opt = torch.optim.AdamW(params, lr=1e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0 / (1 + s))
+    info = C.load_checkpoint(m, ref_file, optimizer=opt, scheduler=sched)
+    assert info["step"] == 7 and info["epoch"] == 1 and info["dataset_config"] == {"text_key": "text"}
+    assert info["args"]["lora_rank"] == 4
+    with torch.no_grad():
+        np.testing.assert_allclose(m.projector.layers(torch.from_numpy(g["x"])).numpy(), g["y"], atol=1e-6)
+    np.testing.assert_array_equal(m.lora_layers["model.layers.0.self_attn.q_proj"].lora_A.detach().numpy(), g["lora_A0"])
+    assert opt.state_dict()["state"] and sched.last_epoch == 1                 # resumed
+    # our writer produces the same top-level / nested keys as the reference's file
+    args = argparse.Namespace(output_dir=str(tmp_path), learning_rate=1e-3, lora_rank=4)
+    mine = C.save_checkpoint(m, opt, sched, 7, 1, args, dataset_config={"text_key": "text"})
+    assert mine.endswith(os.path.join("checkpoint-7", "checkpoint.pt"))
+    a = torch.load(mine, weights_only=False)
+    b = torch.load(ref_file, weights_only=False)
+    assert sorted(a) == sorted(b) and sorted(a["model"]) == sorted(b["model"])
+    assert sorted(a["model"]["projector"]) == sorted(b["model"]["projector"])
+    assert sorted(a["model"]["lora_layers"]) == sorted(b["model"]["lora_layers"])
+    for k in b["model"]["projector"]:
+        assert torch.equal(a["model"]["projector"][k], b["model"]["projector"][k])
+    # flat format (inference.py:62-67) also loads
+    flat = str(tmp_path / "flat.pt")
+    torch.save(b["model"], flat)
+    m2 = fresh()
+    assert C.load_checkpoint(m2, flat)["step"] is None
+    assert torch.equal(m2.projector.layers[0].weight, m.projector.layers[0].weight)
+    assert C.save_checkpoint(m, None, None, 9, 2, args, final=True).endswith(os.path.join("final_checkpoint", "checkpoint.pt"))
+
+
+class _RefShapedProjector(nn.Module):
+    """CPU stand-in with AudioProjector's parameter layout (the real one refuses CPU tensors in forward)."""
+
+    def __init__(self, i, o):
+        super().__init__()
+        h = (i + o) // 2
+        self.layers = nn.Sequential(nn.Linear(i, h), nn.GELU(), nn.Linear(h, o), nn.LayerNorm(o))
