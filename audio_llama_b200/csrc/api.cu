@@ -217,6 +217,62 @@ static int get_mel_tables(int n_mels, int mode, MelTables* out) {
   return 0;
 }
 
+// ----------------------------------------------------------------------------- resample tables
+// torchaudio functional._get_sinc_resample_kernel (TA functional.py:1305-1403), fp64 then cast to fp32.
+static std::map<long long, ResampleTable> g_resample_tables;
+
+static int get_resample_table(int orig_freq, int new_freq, ResampleTable* out) {
+  std::lock_guard<std::mutex> lk(g_mel_mu);
+  const long long key = (static_cast<long long>(orig_freq) << 32) | (unsigned)new_freq;
+  auto it = g_resample_tables.find(key);
+  if (it != g_resample_tables.end()) {
+    *out = it->second;
+    return 0;
+  }
+  int a = orig_freq, b = new_freq;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int orig = orig_freq / a, nw = new_freq / a;
+  const double PI = 3.14159265358979323846, lpw = 6.0, rolloff = 0.99;
+  const double base = (orig < nw ? orig : nw) * rolloff;
+  const int width = (int)ceil(lpw * orig / base);
+  const int L = 2 * width + orig;
+  std::vector<float> dense((size_t)nw * L);
+  int max_taps = 1;
+  std::vector<int> first(nw, 0), count(nw, 0);
+  for (int p = 0; p < nw; ++p) {
+    int f = -1, l = -1;
+    for (int k = 0; k < L; ++k) {
+      double t = ((double)(-p) / nw + (double)(k - width) / orig) * base;
+      t = t < -lpw ? -lpw : (t > lpw ? lpw : t);
+      const double c = cos(t * PI / lpw / 2.0);
+      const double window = c * c;
+      t *= PI;
+      const double sinc = (t == 0.0) ? 1.0 : sin(t) / t;
+      const float w = (float)(sinc * window * (base / orig));
+      dense[(size_t)p * L + k] = w;
+      if (w != 0.f) {
+        if (f < 0) f = k;
+        l = k;
+      }
+    }
+    first[p] = f < 0 ? 0 : f;
+    count[p] = f < 0 ? 0 : l - f + 1;
+    if (count[p] > max_taps) max_taps = count[p];
+  }
+  std::vector<float> packed((size_t)nw * max_taps, 0.f);
+  for (int p = 0; p < nw; ++p)
+    for (int i = 0; i < count[p]; ++i) packed[(size_t)p * max_taps + i] = dense[(size_t)p * L + first[p] + i];
+  void *pw, *pf;
+  AL_CHECK_CUDA(cudaMalloc(&pw, packed.size() * 4));
+  AL_CHECK_CUDA(cudaMalloc(&pf, first.size() * 4));
+  AL_CHECK_CUDA(cudaMemcpy(pw, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  AL_CHECK_CUDA(cudaMemcpy(pf, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+  ResampleTable t{(const float*)pw, (const int*)pf, orig, nw, width, max_taps};
+  g_resample_tables[key] = t;
+  *out = t;
+  return 0;
+}
+
 }  // namespace al
 
 using namespace al;
@@ -333,6 +389,28 @@ int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host) {
              "al_mel_set_filterbank_host: the (n_mels=%d, mode=%d) tables are already on the device", n_mels, mode);
   g_mel_override[key].assign(fb_host, fb_host + (size_t)201 * n_mels);
   return 0;
+}
+
+// ----------------------------------------------------------------------------- ingest
+int al_ingest_forward(const float* in, long long clip_stride, long long chan_stride, int n_chan, const int* n_in,
+                      int n_in_cap, int orig_freq, int new_freq, float* out, long long out_stride, int out_cap,
+                      int* n_out, int n_clips, al_stream_t stream) {
+  AL_REQUIRE(in && out, "al_ingest_forward: NULL argument");
+  AL_REQUIRE(n_clips >= 0 && n_chan >= 1 && n_in_cap >= 0 && out_cap > 0 && out_stride >= out_cap,
+             "al_ingest_forward: bad shape clips=%d chan=%d n_in_cap=%d out_cap=%d", n_clips, n_chan, n_in_cap, out_cap);
+  AL_REQUIRE(orig_freq > 0 && new_freq > 0, "al_ingest_forward: bad rates %d -> %d", orig_freq, new_freq);
+  int rc;
+  if (orig_freq == new_freq) {
+    rc = launch_ingest(in, clip_stride, chan_stride, n_chan, n_in, n_in_cap, nullptr, out, out_stride, out_cap, n_out,
+                       n_clips, (cudaStream_t)stream);
+  } else {
+    ResampleTable tb;
+    if ((rc = get_resample_table(orig_freq, new_freq, &tb))) return rc;
+    rc = launch_ingest(in, clip_stride, chan_stride, n_chan, n_in, n_in_cap, &tb, out, out_stride, out_cap, n_out,
+                       n_clips, (cudaStream_t)stream);
+  }
+  if (rc == 0 && n_clips > 0) g_launches += 1;
+  return rc;
 }
 
 // ----------------------------------------------------------------------------- building blocks

@@ -78,4 +78,17 @@ int launch_mel(const float* wave, const int* n_samples, int B, long long wave_st
                float* out, unsigned int* clip_max_bits, cudaStream_t stream);
 int launch_mel_finalize(float* out, const unsigned int* clip_max_bits, int B, int n_mels, cudaStream_t stream);
 
+// ------------------------------------------------------------------ ingest (ingest.cu)
+struct ResampleTable {
+  const float* weights;   // [new_f][max_taps] non-zero run of each phase's filter (zero padded)
+  const int* first;       // [new_f] index of the run's first tap inside the dense 2*width + orig_f filter
+  int orig_f, new_f;      // gcd-reduced rates
+  int width;              // torchaudio's `width` (left zero padding of the dense convolution)
+  int max_taps;
+};
+// in: [B][n_chan][..] fp32 (strides in elements); tb == nullptr means same rate (channel mean + pad only).
+int launch_ingest(const float* in, long long clip_stride, long long chan_stride, int n_chan, const int* n_in,
+                  int n_in_cap, const ResampleTable* tb, float* out, long long out_stride, int out_cap, int* n_out,
+                  int B, cudaStream_t stream);
+
 }  // namespace al

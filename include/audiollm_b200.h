@@ -50,6 +50,20 @@ int al_mel_filterbank_host(int n_mels, int mode, double* out_host);
  * narrow low filters by ~1e-3 relative, so the bank is rebuilt with the same torch ops and handed in. */
 int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host);
 
+/* ---- waveform ingest ----------------------------------------------------------
+ * Channel mean + sinc resampling to `new_freq` + zero padding / truncation to out_cap samples, one launch.
+ * Replaces torch.mean(waveform, dim=0) and torchaudio.transforms.Resample(orig_freq, new_freq) of
+ * /root/reference/src/inference.py:87-98 and /root/reference/src/dataset.py:105-123 (torchaudio's default
+ * sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99).
+ *   in     [n_clips][n_chan][...] f32: clip b channel c sample s at in[b*clip_stride + c*chan_stride + s]
+ *   n_in   [n_clips] int32 valid samples per clip (NULL = n_in_cap); every clip is first cut to n_in_cap samples
+ *          (the training path truncates BEFORE resampling, dataset.py:106-112; pass a large cap otherwise)
+ *   out    [n_clips][out_stride] f32, samples >= n_out[b] zero — the layout al_mel_forward reads
+ *   n_out  [n_clips] int32 = min(ceil(new*len/orig), out_cap), or NULL */
+int al_ingest_forward(const float* in, long long clip_stride, long long chan_stride, int n_chan, const int* n_in,
+                      int n_in_cap, int orig_freq, int new_freq, float* out, long long out_stride, int out_cap,
+                      int* n_out, int n_clips, al_stream_t stream);
+
 /* ---- building blocks ------------------------------------------------------------------------------ */
 /* epilogue flags for al_gemm_bf16* */
 #define AL_EPI_GELU 1

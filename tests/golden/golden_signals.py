@@ -24,3 +24,12 @@ def encoder_input(cfg, B):
     b = np.arange(B, dtype=np.float64)[:, None, None]
     x = 0.6 * np.sin(0.013 * t + 0.31 * m + b) + 0.4 * np.cos(0.0007 * t * m + 0.5 * b) - 0.2
     return x.astype(np.float32)
+
+
+def resample_input(sr: int) -> np.ndarray:
+    """Stereo test signal [2, ~0.2 s] at `sr` Hz (noise + a 330 Hz tone on channel 0), float32."""
+    n = int(sr * 0.2) + 13
+    rng = np.random.default_rng(5 + sr)
+    x = (0.3 * rng.standard_normal((2, n))).astype(np.float32)
+    x[0] += (0.4 * np.sin(2 * np.pi * 330.0 * np.arange(n) / sr)).astype(np.float32)
+    return x

@@ -177,6 +177,21 @@ def allm_golden():
     np.savez_compressed(os.path.join(HERE, "allm_config1.npz"), **out)
 
 
+def resample_golden():
+    """torchaudio.transforms.Resample exactly as inference.py:91-93 / dataset.py:119-123 construct it."""
+    import torchaudio
+    from golden_signals import resample_input
+    out = {}
+    for sr in (44100, 48000, 8000, 22050, 32000):
+        x = resample_input(sr)
+        res = torchaudio.transforms.Resample(orig_freq=sr, new_freq=16000)
+        y = res(torch.from_numpy(x)).numpy()
+        mono = res(torch.mean(torch.from_numpy(x), dim=0, keepdim=True)).numpy()[0]
+        out[f"y_{sr}"] = y
+        out[f"mono_{sr}"] = mono
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), **out)
+
+
 def checkpoint_golden():
     """A checkpoint.pt written by the REFERENCE's own save_checkpoint (train.py:102-131) for a tiny model."""
     import argparse
@@ -222,6 +237,7 @@ if __name__ == "__main__":
     reference_modules_golden()
     allm_golden()
     checkpoint_golden()
+    resample_golden()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -216,3 +216,31 @@ def test_ragged_degenerates_to_s1():
     assert (out == a).all()
     assert (m == O.extend_mask(mask, 1500)).all()
     assert (lab == O.extend_labels(labels, 1502)).all()
+
+
+@pytest.mark.parametrize("sr", [44100, 48000, 8000, 22050, 32000])
+def test_resample_oracle_matches_torchaudio(golden_dir, sr):
+    """Waveform ingest (§8f-2): oracle resampler vs torchaudio.transforms.Resample outputs. torchaudio convolves in
+    float32 over every tap of the (mostly zero) filter bank, the oracle accumulates in float64: 2e-5 absolute."""
+    from golden_signals import resample_input
+    from oracle import resample as R
+    g = np.load(os.path.join(golden_dir, "resample.npz"))
+    x = resample_input(sr)
+    y = R.resample(x, sr, 16000)
+    assert y.shape == g[f"y_{sr}"].shape
+    assert np.abs(y - g[f"y_{sr}"]).max() <= 2e-5
+    assert np.abs(R.ingest_inference(x, sr) - g[f"mono_{sr}"]).max() <= 2e-5
+    k, width, orig, new = R.sinc_kernel_bank(sr, 16000)
+    assert (k != 0).sum(axis=1).max() <= 2 * width + 2          # the sparsity the CUDA kernel relies on
+
+
+def test_ingest_orders():
+    from oracle import resample as R
+    x = np.ones((2, 100), np.float32)
+    x[1] = 3.0
+    assert np.allclose(R.ingest_inference(x, 16000), 2.0) and R.ingest_inference(x, 16000).shape == (100,)
+    t = R.ingest_train(x, 16000)
+    assert t.shape == (480000,) and np.allclose(t[:100], 2.0) and (t[100:] == 0).all()
+    long = np.zeros((1, 16000 * 31), np.float32)
+    assert R.ingest_inference(long, 16000).shape == (480000,)
+    assert R.ingest_train(np.zeros((1, 48000 * 31), np.float32), 48000).shape == (160000,)   # truncated BEFORE resampling
