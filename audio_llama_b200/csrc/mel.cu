@@ -6,8 +6,10 @@
 // per-clip max-8 floor -> (x+4)/4) as called by /root/reference/src/inference.py:100-105, and, in mode 1,
 // the torchaudio MelSpectrogram + log(x+1e-9) of /root/reference/src/dataset.py:125-133.
 //
-// One CTA = 24 consecutive frames of one clip (3000 = 125 x 24). The 4080 samples those frames touch are
-// read from HBM once into shared memory (the 2.5x frame overlap is served from there). The real FFT of 400
+// One CTA = 8 consecutive frames of one clip (3000 = 375 x 8; 320 threads = one radix-5 butterfly per thread per
+// stage; ~32 KB of shared memory so 6 CTAs share an SM — measured sweep in DESIGN.md: 24 frames / 256 threads
+// 299 us, 8 / 320 162 us for 32 clips). The 1520 samples those frames touch are read from HBM once into shared
+// memory (the 2.5x frame overlap is served from there). The real FFT of 400
 // points is a 200-point complex FFT of (even + i*odd) samples — Stockham, radices 5,5,8, twiddles from an
 // fp64-built table — plus the split post-pass. The mel filter bank is applied sparse (<= 9 non-zeros per mel
 // bin, 394 in total at 128 bins; CSC built on the host in fp64 exactly as HF audio_utils.mel_filter_bank).
@@ -18,9 +20,15 @@
 
 namespace al {
 
-constexpr int MEL_FR = 24;                                  // frames per CTA
+#ifndef MEL_FR_CFG
+#define MEL_FR_CFG 8
+#endif
+#ifndef MEL_THREADS_CFG
+#define MEL_THREADS_CFG 320
+#endif
+constexpr int MEL_FR = MEL_FR_CFG;                          // frames per CTA (must divide 3000)
 constexpr int MEL_NS = (MEL_FR - 1) * 160 + 400;            // 4080 samples staged per CTA
-constexpr int MEL_THREADS = 256;
+constexpr int MEL_THREADS = MEL_THREADS_CFG;
 constexpr int N_CLIP = 480000;
 constexpr int N_FRAMES = 3000;
 
@@ -176,7 +184,8 @@ mel_kernel(const float* __restrict__ wave, const int* __restrict__ n_samples, lo
     for (int i = __ldg(tb.col_start + m); i < e; ++i) acc = fmaf(__ldg(tb.nz_w + i), P[__ldg(tb.nz_freq + i)], acc);
     float v;
     if (mode == 0) {
-      v = log10f(fmaxf(acc, 1e-10f));
+      // log10 via MUFU lg2 (abs. error ~1e-7 on values in [-10, 5]; the parity budget is 1e-5 * max)
+      v = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
       lmax = fmaxf(lmax, v);
     } else {
       v = logf(acc + 1e-9f);
