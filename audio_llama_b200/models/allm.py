@@ -43,6 +43,29 @@ class AudioLLM(nn.Module):
         self.audio_end_token = "</audio>"
         self.tokenizer = None
 
+    # ------------------------------------------------------------------ fused LoRA (B200 extension)
+    def enable_fused_lora(self):
+        """Swap every hooked frozen linear's forward for the fused GEMM (frozen product + rank-r update in one
+        accumulator, `al_lora_linear_forward`) and drop the forward hooks. Needs the LLaMA weights in bf16 on the
+        GPU; other inputs fall back to the module's own forward + the reference-style hook arithmetic."""
+        import types
+        from .lora import fused_lora_forward
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+        for name, module in self.llama.model.named_modules():
+            if name in self.lora_layers:
+                lora = self.lora_layers[name]
+
+                def fwd(mod, x, _lora=lora, _orig=type(module).forward):
+                    if x.is_cuda and x.dtype == torch.bfloat16 and mod.weight.dtype == torch.bfloat16:
+                        return fused_lora_forward(mod, _lora, x)
+                    return _orig(mod, x) + _lora(x)
+
+                module.forward = types.MethodType(fwd, module)
+        self.fused_lora = True
+        return self
+
     # ------------------------------------------------------------------ forward (allm.py:47-106)
     def forward(self, input_ids=None, attention_mask=None, audio_features=None, labels=None, **kwargs):
         device = input_ids.device

@@ -48,3 +48,37 @@ def apply_lora_to_llama(llama_model, rank=8, alpha=16, target_modules=None):
 def lora_forward_hook(module, input, output, lora_layer):
     """Add LoRA output to the original linear layer output (lora.py:41-43)."""
     return output + lora_layer(input[0])
+
+
+# ----------------------------------------------------------------------------- fused path (B200)
+class _FusedLoRALinearFn(torch.autograd.Function):
+    """y = x W^T + b + s (x A^T) B^T through `al_lora_linear_forward` (the rank-r product rides in the frozen GEMM's
+    TMEM accumulator). Backward keeps W frozen: dx = dy W + s (dy B) A, dA = s (dy B)^T x, dB = s dy^T (x A^T)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_A, lora_B, scaling):
+        from .. import ops
+        y = ops.lora_linear(x.contiguous(), weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype)
+        ctx.save_for_backward(x, weight, lora_A, lora_B)
+        ctx.scaling = scaling
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, lora_A, lora_B = ctx.saved_tensors
+        s = ctx.scaling
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        a = lora_A.to(dy.dtype)
+        b = lora_B.to(dy.dtype)
+        u = dy2 @ b                                          # [M, r]
+        dx = (dy2 @ weight + (u @ a) * s).view_as(x) if ctx.needs_input_grad[0] else None
+        dA = ((u.T @ x2) * s).to(lora_A.dtype)
+        dB = ((dy2.T @ (x2 @ a.T)) * s).to(lora_B.dtype)
+        return dx, None, None, dA, dB, None
+
+
+def fused_lora_forward(module: nn.Linear, lora_layer: LoRALayer, x: torch.Tensor) -> torch.Tensor:
+    """Replacement for `module(x)` + lora_forward_hook when x / W are bf16 CUDA tensors."""
+    return _FusedLoRALinearFn.apply(x, module.weight, module.bias, lora_layer.lora_A, lora_layer.lora_B,
+                                    lora_layer.scaling)

@@ -39,3 +39,42 @@ def test_lora_linear_matches_reference_hook_golden(golden_dir):
     y = ops.lora_linear(t("lora_x").cuda().bfloat16(), t("lora_W").cuda().bfloat16(), t("lora_b").cuda(), t("lora_A").cuda(),
                         t("lora_B").cuda(), float(g["lora_scaling"][0]), out_dtype=torch.float32).cpu()
     assert O.rel_l2(y, t("lora_y")) <= 2e-2
+
+
+def test_fused_lora_in_llama_matches_hooks():
+    """AudioLLM.enable_fused_lora(): logits and LoRA gradients of a bf16 LLaMA equal the hook path's."""
+    from unittest.mock import patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as B
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200 import synth
+
+    def fake(lp, wp):
+        torch.manual_seed(0)
+        lc = LlamaConfig(vocab_size=320, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=4)
+        ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+        return (B.FrozenModelWrapper(LlamaForCausalLM(lc).to(torch.bfloat16)),
+                B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=2)))
+
+    def run(fused):
+        with patch.object(B, "load_base_models", fake):
+            m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+        g = torch.Generator().manual_seed(3)
+        for l in m.lora_layers.values():
+            with torch.no_grad():
+                l.lora_A.copy_(torch.randn(l.lora_A.shape, generator=g) * 0.05)
+                l.lora_B.copy_(torch.randn(l.lora_B.shape, generator=g) * 0.05)
+        if fused:
+            m.enable_fused_lora()
+        ids, mask, labels = (t.cuda() for t in synth.synth_text(2, 16, 320))
+        out = m(input_ids=ids, attention_mask=mask, labels=labels)            # text-only: isolates the LLaMA linears
+        out.loss.backward()
+        l0 = m.lora_layers["model.layers.0.self_attn.q_proj"]
+        return out.logits.float().cpu(), l0.lora_A.grad.float().cpu(), l0.lora_B.grad.float().cpu()
+
+    a, b = run(False), run(True)
+    assert O.rel_l2(b[0], a[0]) <= 3e-2                       # bf16 LLaMA both ways; different rounding points
+    assert O.rel_l2(b[1], a[1]) <= 1e-1 and O.rel_l2(b[2], a[2]) <= 1e-1

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--rank_lora", type=int, default=64)
+    ap.add_argument("--fused-lora", action="store_true", help="AudioLLM.enable_fused_lora(): fused frozen+LoRA GEMM")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -62,6 +63,8 @@ def main():
     tok.convert_tokens_to_ids = lambda t: {"<audio>": vocab - 2, "</audio>": vocab - 1}[t]
     model.tokenizer = tok
     model = model.to(dev)
+    if args.fused_lora:
+        model.enable_fused_lora()
     model.projector.to(torch.float32)
     for l in model.lora_layers.values():
         torch.nn.init.normal_(l.lora_A, std=0.01)
@@ -95,9 +98,9 @@ def main():
         t_step.append(t3 - t0)
         t_ar.append(t2 - t1)
     if rank == 0:
-        print(json.dumps({"world": world, "llama": args.llama, "encoder": args.encoder, "batch_per_gpu": args.batch,
+        print(json.dumps({"world": world, "llama": args.llama, "encoder": args.encoder, "batch_per_gpu": args.batch, "fused_lora": bool(args.fused_lora),
                           "trainable_params": bucket.numel, "bucket_mb": bucket.numel * 4 / 1e6,
-                          "step_s": t_step, "allreduce_s": t_ar, "loss": float(out.loss),
+                          "step_s": t_step, "allreduce_s": t_ar, "loss": float(out.loss.detach()),
                           "allreduce_bus_gbs": (2 * (world - 1) / world * bucket.numel * 4 / 1e9 / min(t_ar[1:] or t_ar)) if world > 1 else None}))
     if world > 1:
         dist.destroy_process_group()
