@@ -148,3 +148,29 @@ class AudioConditioner:
         emb, mask, lab = ops.splice(self.table, input_ids, attention_mask, labels, N_CTX, self.start_id, self.end_id,
                                     audio_rows=None, out=out)
         return emb, mask, lab
+
+    # ------------------------------------------------------------------ config 5: ragged clips, several spans per sample
+    @torch.no_grad()
+    def forward_ragged(self, wave: torch.Tensor, n_samples: torch.Tensor, spans_per_sample, input_ids: torch.Tensor,
+                       attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
+        """EXTENSION (not in the reference, SURVEY.md §8 extension row). wave [n_clips, <=480000] fp32 with n_samples
+        [n_clips] int32 valid samples (all clips of all samples, in sample order); spans_per_sample[b] = number of
+        clips of sample b. Every clip is zero-padded to 30 s and encoded exactly as the reference would encode it
+        (the encoder is never masked, HF modeling_whisper.py:607-610); only its first
+        ((n // 160) - 1) // 2 + 1 encoder rows are kept and spliced as <audio> rows </audio> spans before the text.
+        Returns (inputs_embeds [B, S_max, d_l], mask fp32, labels | None, span_start int32 [B, max_spans])."""
+        from .splice import encoder_rows_for_samples, splice_ragged
+        n_clips = wave.shape[0]
+        if sum(spans_per_sample) != n_clips:
+            raise ValueError("spans_per_sample must add up to the number of clips")
+        mel = ops.mel_forward(wave, n_samples, n_mels=self.cfg.n_mels)
+        enc = self.encoder(mel)                                             # chunks of max_batch internally
+        proj = torch.empty(n_clips, N_CTX, self.d_out, dtype=self.table.dtype, device=self.device)
+        projector_forward_raw(self.pw, enc.view(n_clips * N_CTX, self.cfg.d_model), out=proj.view(n_clips * N_CTX, self.d_out),
+                              rows_per_group=n_clips * N_CTX, out_group_stride=0, out_row_offset=0, cache=self._pcache)
+        lens = n_samples.tolist()
+        rows, i = [], 0
+        for k in spans_per_sample:
+            rows.append([encoder_rows_for_samples(n) for n in lens[i:i + k]])
+            i += k
+        return splice_ragged(self.table, input_ids, attention_mask, labels, proj, rows, self.start_id, self.end_id)

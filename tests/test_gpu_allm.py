@@ -189,3 +189,41 @@ def test_ragged_splice_extension():
     o1, m1, l1, _ = splice_ragged(E.cuda(), ids.cuda(), mask.cuda(), labels.cuda(), flat[:3], [[1500]] * 3, vocab - 2, vocab - 1)
     s1 = O.combine(E, ids, flat[:3].cpu(), vocab - 2, vocab - 1)
     assert torch.equal(o1.cpu(), s1) and torch.equal(m1.cpu(), O.extend_mask(mask, 1500))
+
+
+def test_pipeline_ragged_config5():
+    """Config 5 end to end (variable-length clips, 1-3 spans per sample) against the oracle chain."""
+    cfg = EncoderConfig(d_model=128, n_layers=2, n_heads=2, ffn_dim=256, n_mels=80)
+    d_l, vocab, T = 64, 100, 10
+    ew = synth.init_encoder_weights(cfg, seed=0, ln_jitter=0.1)
+    pw = synth.init_projector_weights(cfg.d_model, d_l, seed=1, ln_jitter=0.1)
+    table = torch.randn(vocab, d_l, generator=torch.Generator().manual_seed(2))
+    spans = [1, 3, 2]
+    rng = np.random.default_rng(11)
+    lens = [480000] + [int(rng.integers(16000, 480001)) for _ in range(5)]
+    clips = [synth.synth_clip(i, n_samples=n) for i, n in enumerate(lens)]
+    buf = np.zeros((6, 480000), np.float32)
+    for i, c in enumerate(clips):
+        buf[i, : len(c)] = c
+    ids, mask, labels = synth.synth_text(3, T, vocab)
+    cond = AudioConditioner(cfg, ew, pw, table.cuda(), vocab - 2, vocab - 1, max_batch=4)      # 6 clips through a 4-clip plan
+    out, m, lab, starts = cond.forward_ragged(torch.from_numpy(buf).cuda(), torch.tensor(lens, dtype=torch.int32).cuda(),
+                                              spans, ids.cuda(), mask.cuda(), labels.cuda())
+    # oracle chain
+    mel = torch.from_numpy(M.log_mel_whisper(clips, cfg.n_mels))
+    enc = O.encoder_forward(ew, cfg, mel)
+    proj = O.projector_forward(pw, enc)
+    per_sample, i = [], 0
+    for k in spans:
+        per_sample.append([proj[c][: M.encoder_frames_for_samples(lens[c])] for c in range(i, i + k)])
+        i += k
+    ref, ref_m, ref_lab = O.combine_ragged(table, ids, mask, labels, per_sample, vocab - 2, vocab - 1)
+    assert out.shape == ref.shape
+    assert torch.equal(m.cpu(), ref_m) and torch.equal(lab.cpu(), ref_lab)                # layout bit-exact
+    audio = ref_m.bool() & (ref_lab == -100)
+    assert O.rel_l2(out.cpu()[audio], ref[audio]) <= 2e-2                                   # bf16 encoder / projector rows
+    text = ref_lab != -100
+    assert torch.equal(out.cpu()[text], ref[text])                                          # gathered rows bit-exact
+    _, _, total, S = O.ragged_layout([[p.shape[0] for p in ps] for ps in per_sample], T)
+    for b in range(3):
+        assert (out[b, total[b]:].cpu() == 0).all() and (m[b, total[b]:].cpu() == 0).all()   # right padding rows
