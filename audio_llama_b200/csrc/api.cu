@@ -713,6 +713,103 @@ int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_ou
                       out_row_offset, stream);
 }
 
+// ----------------------------------------------------------------------------- projector backward
+static int gemm_plain(const void* A, long long lda, int M, const void* W, long long ldw, int N, int K, const float* bias,
+                      void* out, long long ldo, int flags, const void* grad_in, long long grad_ld, int want_items,
+                      cudaStream_t st) {
+  // A [M][lda] (K valid columns), W [N][ldw], out [M][ldo]; optional split-K for small outputs
+  CUtensorMap ta, tb, to;
+  int rc;
+  if ((rc = tmap_rows3d(&ta, A, 2, K, M, 1, lda, (uint64_t)M * lda, 64, 128))) return rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    const uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    const uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap(&tb, W, 2, 2, dims, str, box, true))) return rc;
+  }
+  const int oe = (flags & EPI_OUT_F32) ? 4 : 2;
+  if ((rc = tmap_rows3d(&to, out, oe, N, M, 1, ldo, (uint64_t)M * ldo, gemm_out_box_cols(flags), 128))) return rc;
+  GemmParams p{};
+  p.m_per_batch = M; p.batch = 1; p.N = N; p.K = K; p.bias = bias;
+  p.grad_in = reinterpret_cast<const __nv_bfloat16*>(grad_in);
+  p.grad_ld = grad_ld;
+  if (want_items > 0 && (flags & EPI_REDUCE_ADD)) {
+    const int out_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const int num_kb = (K + 63) / 64;
+    int ks = (want_items + out_tiles - 1) / out_tiles;
+    if (ks > num_kb) ks = num_kb;
+    if (ks < 1) ks = 1;
+    const int per = (num_kb + ks - 1) / ks;
+    p.k_splits = (num_kb + per - 1) / per;          // every slice non-empty
+  }
+  rc = launch_gemm(ta, tb, to, p, flags, num_sms(), st);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+size_t al_projector_backward_workspace_bytes(int rows, int d_in, int hidden, int d_out) {
+  const size_t rp = (size_t)(rows + 7) / 8 * 8;
+  size_t b = 0;
+  auto add = [&](size_t n) { b += (n + 1023) / 1024 * 1024; };
+  add((size_t)rows * d_out * 2);   // dy
+  add(rp * d_out * 2);             // dyT
+  add(rp * hidden * 2);            // hT / daT
+  add((size_t)hidden * d_out * 2); // W2T
+  add((size_t)rows * hidden * 2);  // dh
+  add((size_t)rows * hidden * 2);  // da
+  add(rp * d_in * 2);              // xT
+  return b;
+}
+
+int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_out, const void* W1, const float* b1,
+                          const void* W2, const float* gamma, const void* h_saved, const float* y_saved,
+                          const float* dout, void* workspace, float* dW1, float* db1, float* dW2, float* db2,
+                          float* dgamma, float* dbeta, al_stream_t stream) {
+  AL_REQUIRE(x && W1 && b1 && W2 && gamma && h_saved && y_saved && dout && workspace && dW1 && db1 && dW2 && db2 && dgamma && dbeta,
+             "al_projector_backward: NULL argument");
+  AL_REQUIRE(rows > 0 && d_in % 8 == 0 && hidden % 8 == 0 && d_out % 8 == 0, "al_projector_backward: bad shape");
+  AL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "al_projector_backward: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rp = (rows + 7) / 8 * 8;
+  uint8_t* w = (uint8_t*)workspace;
+  auto take = [&](size_t n) { void* p = w; w += (n + 1023) / 1024 * 1024; return p; };
+  void* dy = take((size_t)rows * d_out * 2);
+  void* dyT = take((size_t)rp * d_out * 2);
+  void* hT = take((size_t)rp * hidden * 2);
+  void* W2T = take((size_t)hidden * d_out * 2);
+  void* dh = take((size_t)rows * hidden * 2);
+  void* da = take((size_t)rows * hidden * 2);
+  void* xT = take((size_t)rp * d_in * 2);
+  AL_CHECK_CUDA(cudaMemsetAsync(dW1, 0, (size_t)hidden * d_in * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(db1, 0, (size_t)hidden * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(dW2, 0, (size_t)d_out * hidden * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(db2, 0, (size_t)d_out * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)d_out * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)d_out * 4, st));
+  int rc;
+#define STEP(expr) do { rc = (expr); if (rc) return rc; g_launches += 1; } while (0)
+  // 1. LayerNorm backward: dy (bf16), dgamma, dbeta, db2 = colsum(dy)
+  STEP(launch_layernorm_bwd(y_saved, dout, gamma, dy, dgamma, dbeta, db2, rows, d_out, 1e-5f, st));
+  // 2. dW2 = dy^T h : both operands transposed to K-major, split-K reduce-add
+  STEP(launch_transpose_bf16(dy, dyT, rows, d_out, rp, st));
+  STEP(launch_transpose_bf16(h_saved, hT, rows, hidden, rp, st));
+  if ((rc = gemm_plain(dyT, rp, d_out, hT, rp, hidden, rp, nullptr, dW2, hidden, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
+                       2 * num_sms(), st))) return rc;
+  // 3. dh = dy W2
+  STEP(launch_transpose_bf16(W2, W2T, d_out, hidden, d_out, st));
+  if ((rc = gemm_plain(dy, d_out, rows, W2T, d_out, hidden, d_out, nullptr, dh, hidden, 0, nullptr, 0, 0, st))) return rc;
+  // 4. da = dh * gelu'(x W1^T + b1)  (pre-activation recomputed inside the GEMM)
+  if ((rc = gemm_plain(x, d_in, rows, W1, d_in, hidden, d_in, b1, da, hidden, EPI_GELU_GRAD, dh, hidden, 0, st))) return rc;
+  // 5. db1 = colsum(da); dW1 = da^T x
+  STEP(launch_colsum_bf16(da, db1, rows, hidden, st));
+  STEP(launch_transpose_bf16(da, hT, rows, hidden, rp, st));
+  STEP(launch_transpose_bf16(x, xT, rows, d_in, rp, st));
+  if ((rc = gemm_plain(hT, rp, hidden, xT, rp, d_in, rp, nullptr, dW1, d_in, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
+                       2 * num_sms(), st))) return rc;
+#undef STEP
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- LoRA linear
 int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W, const float* bias,
                            const void* lora_A, const void* lora_B_scaled, void* t_ws, void* out, int out_dtype,

@@ -55,6 +55,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool REDUCE = (FLAGS & EPI_REDUCE_ADD) != 0;
   constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
   constexpr bool RESID = (FLAGS & EPI_RESIDUAL) != 0;
+  constexpr bool GELU_GRAD = (FLAGS & EPI_GELU_GRAD) != 0;
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_ROWS = CTA2 ? 128 : 256;       // weight rows staged by this CTA
   constexpr int B_BYTES = B_ROWS * BK * 2;
@@ -104,11 +105,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   const int tiles_m = (p.m_per_batch + TILE_M - 1) / TILE_M;
-  const int num_tiles = p.batch * tiles_m * p.tiles_n;
+  const int out_tiles = p.batch * tiles_m * p.tiles_n;
+  // split-K (weight-gradient GEMMs: small output, very long contraction): work item = (output tile, K slice);
+  // every slice reduce-adds its partial tile into the fp32 output, slice 0 also adds the bias.
+  const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int num_tiles = out_tiles * k_splits;
   // K blocks of the main product, then (LoRA) K2 more blocks of a second operand pair accumulated into the same
   // TMEM accumulator: out = A W^T + A2 W2^T, with A2 = x A_lora^T [M, r] and W2 = scaling * B_lora [N, r].
   const int num_kb1 = (p.K + BK - 1) / BK;
-  const int num_kb = num_kb1 + (p.K2 + BK - 1) / BK;
+  const int num_kb_all = num_kb1 + (p.K2 + BK - 1) / BK;
+  const int kb_per_split = (num_kb_all + k_splits - 1) / k_splits;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
@@ -116,12 +122,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int t = worker; t < num_tiles; t += n_workers) {
-        const int nt = t % p.tiles_n;
-        const int mt = t / p.tiles_n;
+        const int ot = t % out_tiles, split = t / out_tiles;
+        const int nt = ot % p.tiles_n;
+        const int mt = ot / p.tiles_n;
         const int m0 = (mt % tiles_m) * TILE_M + rank * BM;
         const int b = mt / tiles_m;
         const int n0 = nt * BN + rank * B_ROWS;                  // pair: this CTA's half of the weight rows
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb_begin = split * kb_per_split;
+        const int kb_end = min(kb_begin + kb_per_split, num_kb_all);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           const bool second = kb >= num_kb1;
           const int k0 = (second ? kb - num_kb1 : kb) * BK;
@@ -149,6 +158,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tempty[as], aph ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
+      const int split = t / out_tiles;
+      const int num_kb = min(kb_per_split, num_kb_all - split * kb_per_split);   // >= 1 (host guarantees)
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
@@ -184,8 +195,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     uint32_t aph = 0;
     for (int t = worker; t < num_tiles; t += n_workers) {
-      const int nt = t % p.tiles_n;
-      const int mt = t / p.tiles_n;
+      const int ot = t % out_tiles, split = t / out_tiles;
+      const int nt = ot % p.tiles_n;
+      const int mt = ot / p.tiles_n;
       const int m0 = (mt % tiles_m) * TILE_M + rank * BM;
       const int b = mt / tiles_m;
       const int n0 = nt * BN;
@@ -213,7 +225,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const int col0 = n0 + c * CH;
         const bool fullc = col0 + CH <= p.N;
-        if (p.bias != nullptr) {
+        if (p.bias != nullptr && split == 0) {
           if (fullc) {
 #pragma unroll
             for (int j = 0; j < CH; j += 4) {
@@ -228,6 +240,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (DO_GELU) {
 #pragma unroll
           for (int j = 0; j < CH; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
+        }
+        if constexpr (GELU_GRAD) {
+          // backward of h = gelu(a): v holds the recomputed pre-activation a = x W1^T + b1; out = dh * gelu'(a),
+          // gelu'(a) = Phi(a) + a phi(a). dh is a bf16 [M][N] matrix read row-wise (128 B per thread).
+          const __nv_bfloat16* gp = p.grad_in + (static_cast<size_t>(b) * p.m_per_batch + grow) * p.grad_ld + col0;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            uint4 g = make_uint4(0, 0, 0, 0);
+            if (fullc) g = __ldg(reinterpret_cast<const uint4*>(gp + j));
+            const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float g0 = __uint_as_float(gw[q] << 16), g1 = __uint_as_float(gw[q] & 0xffff0000u);
+              if (!fullc) {
+                g0 = (col0 + j + 2 * q < p.N) ? __bfloat162float(gp[j + 2 * q]) : 0.f;
+                g1 = (col0 + j + 2 * q + 1 < p.N) ? __bfloat162float(gp[j + 2 * q + 1]) : 0.f;
+              }
+              const float a0 = v[j + 2 * q], a1 = v[j + 2 * q + 1];
+              const float cdf0 = 0.5f * (1.0f + erff(a0 * 0.70710678118654752440f));
+              const float cdf1 = 0.5f * (1.0f + erff(a1 * 0.70710678118654752440f));
+              const float pdf0 = 0.3989422804014327f * __expf(-0.5f * a0 * a0);
+              const float pdf1 = 0.3989422804014327f * __expf(-0.5f * a1 * a1);
+              v[j + 2 * q] = g0 * (cdf0 + a0 * pdf0);
+              v[j + 2 * q + 1] = g1 * (cdf1 + a1 * pdf1);
+            }
+          }
         }
         if constexpr (ROWAUX) {
           const float* ap = p.aux + static_cast<size_t>(grow) * p.aux_ld;
@@ -319,7 +357,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     attr_set = true;
   }
   const int tile_m = CTA2 ? 256 : 128;
-  const int tiles = p.batch * ((p.m_per_batch + tile_m - 1) / tile_m) * p.tiles_n;
+  const int tiles = p.batch * ((p.m_per_batch + tile_m - 1) / tile_m) * p.tiles_n * (p.k_splits > 1 ? p.k_splits : 1);
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];
   if (CTA2) {
@@ -370,6 +408,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
       return launch_mode<EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
       return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_GELU_GRAD:
+      return launch_mode<EPI_GELU_GRAD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     default:
       set_error("launch_gemm: unsupported epilogue flags %d", flags);
       return -1;

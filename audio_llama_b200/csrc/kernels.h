@@ -1,6 +1,7 @@
 // Internal launch interface between api.cu (the C ABI) and the kernel translation units.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -13,6 +14,7 @@ enum GemmEpilogue : int {
   EPI_REDUCE_ADD = 4,   // out += result (TMA reduce-add; residual connection on the fp32 stream)
   EPI_ROWAUX = 8,       // + aux[row_in_batch][col] (fp32; Whisper's position table)
   EPI_RESIDUAL = 16,    // + resid[batch][row][col] (fp32, may alias out: in-place residual add, no atomics)
+  EPI_GELU_GRAD = 32,   // out = grad_in[row][col] * gelu'(acc + bias)  (backward of a Linear+GELU, recomputed)
 };
 
 struct GemmParams {
@@ -29,6 +31,9 @@ struct GemmParams {
   const float* resid;      // [batch][m_per_batch][resid_ld] or nullptr (EPI_RESIDUAL)
   long long resid_ld;
   long long resid_batch_stride;
+  const __nv_bfloat16* grad_in;   // [batch*m_per_batch][grad_ld] bf16 (EPI_GELU_GRAD)
+  long long grad_ld;
+  int k_splits;            // > 1: split the contraction over this many work items (needs EPI_REDUCE_ADD, zeroed out)
 };
 
 void gemm_set_mode(int pair);        // 1 = CTA-pair (cta_group::2) kernel, 0 = single-CTA kernel
@@ -62,6 +67,10 @@ int launch_splice_ragged(const void* table, int elem_bytes, int d, const long lo
                          const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
                          long long* labels_out, int* span_start_out, cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, void* out, long long n, cudaStream_t stream);
+int launch_transpose_bf16(const void* in, void* out, int R, int C, int out_ld, cudaStream_t stream);
+int launch_layernorm_bwd(const float* y, const float* dout, const float* gamma, void* dy_bf16, float* dgamma,
+                         float* dbeta, float* dbias, int rows, int d, float eps, cudaStream_t stream);
+int launch_colsum_bf16(const void* x, float* out, int rows, int n, cudaStream_t stream);
 
 // ------------------------------------------------------------------ mel (mel.cu)
 struct MelTables {

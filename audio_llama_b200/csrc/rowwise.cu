@@ -258,6 +258,153 @@ int launch_splice_ragged(const void* table, int elem_bytes, int d, const long lo
   return 0;
 }
 
+// ----------------------------------------------------------------------------- training-side row kernels
+// bf16 [R][C] -> [C][R] (weight-gradient GEMMs contract over the row dimension; the tcgen05 GEMM wants both operands
+// K-major, so dy / h / x are transposed once per step: ~0.1 ms per 100 MB, noise next to the LLaMA backward).
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int C, int out_ld) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? in[static_cast<long long>(r) * C + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < out_ld) out[static_cast<long long>(c) * out_ld + r] = tile[tx][i];   // r in [R, out_ld): zero padding
+  }
+}
+
+int launch_transpose_bf16(const void* in, void* out, int R, int C, int out_ld, cudaStream_t stream) {
+  if (R == 0 || C == 0) return 0;
+  AL_REQUIRE(out_ld >= R, "transpose: out_ld=%d < rows=%d", out_ld, R);
+  dim3 grid((C + 63) / 64, (out_ld + 63) / 64);
+  transpose_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                                  reinterpret_cast<__nv_bfloat16*>(out), R, C, out_ld);
+  AL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// LayerNorm backward (AudioProjector.layers[3]): y fp32 [rows][d] is the saved LN input, dout the upstream
+// gradient (fp32). Per row: yh = (y - mu) rstd ; g = dout * gamma ; dy = rstd (g - mean(g) - yh mean(g yh)).
+// Writes dy as bf16 (the A operand of the two backward GEMMs) and accumulates dgamma += dout*yh, dbeta += dout,
+// dbias2 += dy (column sums) with one atomicAdd per column per CTA.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dout, const float* __restrict__ gamma,
+                     __nv_bfloat16* __restrict__ dy, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dbias, int rows, int d, float eps, int rows_per_cta) {
+  extern __shared__ float sacc[];                 // [3][d] per-CTA column partial sums
+  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = d >> 2;
+  const int row_begin = blockIdx.x * rows_per_cta;
+  const int row_end = min(row_begin + rows_per_cta, rows);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  for (int row = row_begin + warp; row < row_end; row += 8) {
+    const float4* yr = reinterpret_cast<const float4*>(y + static_cast<long long>(row) * d);
+    const float4* dr = reinterpret_cast<const float4*>(dout + static_cast<long long>(row) * d);
+    float4 v[MAXV], g[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        v[i] = yr[idx];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    float sg = 0.f, sgy = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        const float4 dd = dr[idx], gm = __ldg(g4 + idx);
+        v[i].x *= rstd; v[i].y *= rstd; v[i].z *= rstd; v[i].w *= rstd;            // yh
+        // column partial sums: dgamma, dbeta
+        atomicAdd(&sacc[4 * idx + 0], dd.x * v[i].x); atomicAdd(&sacc[4 * idx + 1], dd.y * v[i].y);
+        atomicAdd(&sacc[4 * idx + 2], dd.z * v[i].z); atomicAdd(&sacc[4 * idx + 3], dd.w * v[i].w);
+        atomicAdd(&sacc[d + 4 * idx + 0], dd.x); atomicAdd(&sacc[d + 4 * idx + 1], dd.y);
+        atomicAdd(&sacc[d + 4 * idx + 2], dd.z); atomicAdd(&sacc[d + 4 * idx + 3], dd.w);
+        g[i] = make_float4(dd.x * gm.x, dd.y * gm.y, dd.z * gm.z, dd.w * gm.w);
+        sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        sgy += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+      }
+    }
+    const float mg = warp_sum(sg) / d, mgy = warp_sum(sgy) / d;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nv) {
+        float4 o;
+        o.x = rstd * (g[i].x - mg - v[i].x * mgy);
+        o.y = rstd * (g[i].y - mg - v[i].y * mgy);
+        o.z = rstd * (g[i].z - mg - v[i].z * mgy);
+        o.w = rstd * (g[i].w - mg - v[i].w * mgy);
+        atomicAdd(&sacc[2 * d + 4 * idx + 0], o.x); atomicAdd(&sacc[2 * d + 4 * idx + 1], o.y);
+        atomicAdd(&sacc[2 * d + 4 * idx + 2], o.z); atomicAdd(&sacc[2 * d + 4 * idx + 3], o.w);
+        reinterpret_cast<uint2*>(dy + static_cast<long long>(row) * d)[idx] =
+            make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, sacc[i]);
+    atomicAdd(dbeta + i, sacc[d + i]);
+    atomicAdd(dbias + i, sacc[2 * d + i]);
+  }
+}
+
+int launch_layernorm_bwd(const float* y, const float* dout, const float* gamma, void* dy_bf16, float* dgamma,
+                         float* dbeta, float* dbias, int rows, int d, float eps, cudaStream_t stream) {
+  AL_REQUIRE(d % 4 == 0 && d <= 128 * 24, "layernorm_bwd: d=%d must be a multiple of 4 and <= 3072", d);
+  if (rows == 0) return 0;
+  const int rows_per_cta = 64;
+  const int grid = (rows + rows_per_cta - 1) / rows_per_cta;
+  const size_t smem = static_cast<size_t>(3) * d * sizeof(float);
+  auto* dyp = reinterpret_cast<__nv_bfloat16*>(dy_bf16);
+  if (d <= 128 * 4) layernorm_bwd_kernel<4><<<grid, 256, smem, stream>>>(y, dout, gamma, dyp, dgamma, dbeta, dbias, rows, d, eps, rows_per_cta);
+  else if (d <= 128 * 12) layernorm_bwd_kernel<12><<<grid, 256, smem, stream>>>(y, dout, gamma, dyp, dgamma, dbeta, dbias, rows, d, eps, rows_per_cta);
+  else layernorm_bwd_kernel<24><<<grid, 256, smem, stream>>>(y, dout, gamma, dyp, dgamma, dbeta, dbias, rows, d, eps, rows_per_cta);
+  AL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Column sums of a bf16 [rows][n] matrix into fp32 [n] (bias gradients): out += sum over rows.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int rows, int n, int rows_per_cta) {
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col >= n) return;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  float acc = 0.f;
+  for (int r = r0; r < r1; ++r) acc += __bfloat162float(x[static_cast<long long>(r) * n + col]);
+  atomicAdd(out + col, acc);
+}
+
+int launch_colsum_bf16(const void* x, float* out, int rows, int n, cudaStream_t stream) {
+  if (rows == 0 || n == 0) return 0;
+  const int rows_per_cta = 256;
+  dim3 grid((n + 255) / 256, (rows + rows_per_cta - 1) / rows_per_cta);
+  colsum_bf16_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, n, rows_per_cta);
+  AL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- casts
 __global__ void f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long long n4) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;

@@ -4,8 +4,8 @@
 GEMM1 + bias + erf-GELU epilogue -> GEMM2 + bias (fp32 out) -> LayerNorm, optionally storing straight into
 `inputs_embeds[b, 1 + t]` (the splice for the audio rows).
 
-Forward is the hand-written sm_100a path. Backward (the projector is trainable) is currently expressed with
-torch matmuls on the saved activations — see DESIGN.md "out of scope this round".
+Forward and backward (the projector is the trainable part of the path) both run on the hand-written sm_100a
+kernels: `al_projector_forward` / `al_projector_backward`.
 """
 from __future__ import annotations
 
@@ -61,29 +61,29 @@ class _ProjectorFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        """Native backward (`al_projector_backward`): LayerNorm-backward kernel, split-K tcgen05 GEMMs for dW1 / dW2,
+        dh = dy W2, and the GELU derivative applied in the epilogue of the recomputed x W1^T GEMM."""
+        import ctypes as C
         xb, W1, b1, W2, g, h, y = ctx.saved_tensors
-        d_out = y.shape[-1]
-        x2 = xb.reshape(-1, xb.shape[-1]).float()
-        do = dout.reshape(-1, d_out).float()
-        # LayerNorm backward
-        mu = y.mean(-1, keepdim=True)
-        rstd = torch.rsqrt(y.var(-1, unbiased=False, keepdim=True) + 1e-5)
-        yh = (y - mu) * rstd
-        dg, dbeta = (do * yh).sum(0), do.sum(0)
-        dyh = do * g
-        dy = rstd * (dyh - dyh.mean(-1, keepdim=True) - yh * (dyh * yh).mean(-1, keepdim=True))
-        # Linear 2
-        hf = h.float()
-        dW2, db2 = dy.T @ hf, dy.sum(0)
-        dh = dy @ W2.float()
-        # GELU(erf) backward on the pre-activation
-        a = x2 @ W1.float().T + b1.float()
-        cdf = 0.5 * (1 + torch.erf(a * 0.7071067811865476))
-        pdf = torch.exp(-0.5 * a * a) * 0.3989422804014327
-        da = dh * (cdf + a * pdf)
-        dW1, db1 = da.T @ x2, da.sum(0)
-        dx = (da @ W1.float()).view(xb.shape) if ctx.needs_input_grad[0] else None
-        return dx, dW1, db1, dW2, db2, dg, dbeta
+        dev = xb.device
+        x2 = xb.reshape(-1, xb.shape[-1]).contiguous()
+        rows, d_in = x2.shape
+        hidden, d_out = W1.shape[0], W2.shape[0]
+        do = dout.reshape(rows, d_out).to(torch.float32).contiguous()
+        L = lib()
+        nbytes = L.al_projector_backward_workspace_bytes(rows, d_in, hidden, d_out)
+        buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        ws = buf[(-buf.data_ptr()) % 1024:]
+        f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        dW1, db1, dW2, db2, dg, dbeta = f32(hidden, d_in), f32(hidden), f32(d_out, hidden), f32(d_out), f32(d_out), f32(d_out)
+        w1b = W1.detach().to(torch.bfloat16).contiguous()
+        w2b = W2.detach().to(torch.bfloat16).contiguous()
+        check(L.al_projector_backward(ptr(x2), rows, d_in, hidden, d_out, ptr(w1b), ptr(b1.detach().float().contiguous()),
+                                      ptr(w2b), ptr(g.detach().float().contiguous()), ptr(h), ptr(y), ptr(do), ptr(ws),
+                                      ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(dg), ptr(dbeta), stream_ptr()),
+              "al_projector_backward")
+        cast = lambda t, like: t.to(like.dtype)
+        return None, cast(dW1, W1), cast(db1, b1), cast(dW2, W2), cast(db2, W2), cast(dg, g), cast(dbeta, g)
 
 
 class AudioProjector(nn.Module):

@@ -138,6 +138,18 @@ int al_projector_forward(const void* x, int rows, int d_in, int hidden, int d_ou
                          float* y_ws, void* out, int out_dtype, long long out_ld, int rows_per_group,
                          long long out_group_stride, long long out_row_offset, al_stream_t stream);
 
+/* Backward of the projector (it is the trainable part of the path). Inputs: the forward's operands, the saved
+ * h = gelu(W1 x + b1) (bf16 [rows][hidden]) and y = W2 h + b2 (f32 [rows][d_out], the LayerNorm input), and the
+ * upstream gradient dout (f32 [rows][d_out]). Outputs (f32, overwritten): dW1 [hidden][d_in], db1, dW2
+ * [d_out][hidden], db2, dgamma, dbeta. x has no gradient (the encoder is frozen, base.py:8-9).
+ * LayerNorm backward kernel -> dy; dW2 = dy^T h and dW1 = da^T x as split-K tcgen05 GEMMs on transposed (K-major)
+ * copies with TMA reduce-add; dh = dy W2; da = dh * gelu'(.) with the pre-activation recomputed in the GEMM epilogue. */
+size_t al_projector_backward_workspace_bytes(int rows, int d_in, int hidden, int d_out);
+int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_out, const void* W1, const float* b1,
+                          const void* W2, const float* gamma, const void* h_saved, const float* y_saved,
+                          const float* dout, void* workspace, float* dW1, float* db1, float* dW2, float* db2,
+                          float* dgamma, float* dbeta, al_stream_t stream);
+
 /* ---- L1: frozen linear + LoRA update ---------------------------------------------------------------
  * Replaces lora_forward_hook(module, input, output, lora_layer) = output + (x @ (B @ A).T) * scaling
  * (/root/reference/src/models/lora.py:20-21, 41-43) together with the frozen nn.Linear it hooks:

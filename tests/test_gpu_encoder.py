@@ -92,3 +92,27 @@ def test_projector(d_in, d_out, rows):
     y = projector_forward_raw({k: v.cuda() for k, v in pw.items()}, x.cuda().bfloat16(), out_dtype=torch.float32).cpu()
     assert O.rel_l2(y, ref) <= TOL
     assert (y - ref).abs().max() <= 0.1
+
+
+@pytest.mark.parametrize("d_in,d_out,rows", [(384, 256, 300), (1280, 2048, 3000), (1280, 3072, 1500)])
+def test_projector_backward_native(d_in, d_out, rows):
+    """Gradients of the native projector backward vs torch autograd of the fp32 oracle (on bf16-rounded input)."""
+    from audio_llama_b200.models.projector import AudioProjector
+    pw = synth.init_projector_weights(d_in, d_out, seed=1, ln_jitter=0.1)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(rows, d_in, generator=g).bfloat16()
+    dout = torch.randn(rows, d_out, generator=g) * 0.1
+    # oracle gradients
+    ref_w = {k: v.clone().requires_grad_(True) for k, v in pw.items()}
+    O.projector_forward(ref_w, x.float()).backward(dout)
+    # native
+    proj = AudioProjector(d_in, d_out).cuda()
+    proj.load_state_dict(pw)
+    y = proj(x.cuda())
+    y.backward(dout.cuda().to(y.dtype))
+    names = {"layers.0.weight": proj.layers[0].weight, "layers.0.bias": proj.layers[0].bias,
+             "layers.2.weight": proj.layers[2].weight, "layers.2.bias": proj.layers[2].bias,
+             "layers.3.weight": proj.layers[3].weight, "layers.3.bias": proj.layers[3].bias}
+    for k, p in names.items():
+        rel = O.rel_l2(p.grad.float().cpu(), ref_w[k].grad)
+        assert rel <= 3e-2, (k, rel)
