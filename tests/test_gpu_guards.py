@@ -31,7 +31,13 @@ def test_gemm_tails_do_not_write_outside(M, N, K):
     w = (torch.randn(N, K, generator=g) * 0.05).bfloat16().cuda()
     b = torch.randn(N, generator=g).cuda()
     for flags, dt, fill in ((0, torch.bfloat16, 7.0), (EPI_GELU, torch.bfloat16, 7.0), (EPI_OUT_F32, torch.float32, 7.0)):
-        if flags == 0 and N % 8 or (dt == torch.float32 and N % 4):
+        if (dt == torch.bfloat16 and N % 8) or (dt == torch.float32 and N % 4):
+            # output rows not 16-byte aligned: the library refuses (argument error), it never writes
+            from audio_llama_b200._lib import AudioLLMLibError
+            buf, out = guarded((M, N), dt, fill)
+            with pytest.raises(AudioLLMLibError, match="multiple of 16"):
+                ops.gemm_bf16(a, w, b, flags=flags, out=out)
+            check_guards(buf, fill, M * N)
             continue
         buf, out = guarded((M, N), dt, fill)
         ops.gemm_bf16(a, w, b, flags=flags, out=out)
