@@ -212,6 +212,11 @@ static int get_mel_tables(int n_mels, int mode, MelTables* out) {
   d.t.nz_freq = (const int*)pf;
   d.t.nz_w = (const float*)pz;
   d.t.n_mels = n_mels;
+  d.t.nnz = (int)nz_w.size();
+  if (d.t.nnz > 1024 || n_mels > 256) {
+    set_error("mel filter bank too dense for the kernel's shared-memory tables (nnz=%d, n_mels=%d)", d.t.nnz, n_mels);
+    return -1;
+  }
   g_mel_tables[key] = d;
   *out = d.t;
   return 0;

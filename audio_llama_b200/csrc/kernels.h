@@ -81,6 +81,7 @@ struct MelTables {
   const int* nz_freq;      // [nnz]
   const float* nz_w;       // [nnz]
   int n_mels;
+  int nnz;
 };
 // mode 0: whisper (log10, per-clip max written to clip_max for finalize); mode 1: ln(x + 1e-9).
 int launch_mel(const float* wave, const int* n_samples, int B, long long wave_stride, const MelTables& tb, int mode,

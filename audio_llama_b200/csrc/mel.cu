@@ -29,6 +29,9 @@ namespace al {
 constexpr int MEL_FR = MEL_FR_CFG;                          // frames per CTA (must divide 3000)
 constexpr int MEL_NS = (MEL_FR - 1) * 160 + 400;            // 4080 samples staged per CTA
 constexpr int MEL_THREADS = MEL_THREADS_CFG;
+static_assert(3000 % MEL_FR == 0 && MEL_NS % 4 == 0, "frames per CTA must divide 3000");
+constexpr int MEL_MAX_MELS = 256;
+constexpr int MEL_MAX_NNZ = 1024;
 constexpr int N_CLIP = 480000;
 constexpr int N_FRAMES = 3000;
 
@@ -84,6 +87,9 @@ mel_kernel(const float* __restrict__ wave, const int* __restrict__ n_samples, lo
   cf* bufA = reinterpret_cast<cf*>(sW + MEL_NS);                        // [MEL_FR][200]
   cf* bufB = bufA + MEL_FR * 200;                                       // [MEL_FR][200]
   float* sP = reinterpret_cast<float*>(bufA);                           // [MEL_FR][204] power, aliases bufA
+  int* sColStart = reinterpret_cast<int*>(bufB + MEL_FR * 200);         // [n_mels + 1]
+  int* sNzFreq = sColStart + MEL_MAX_MELS + 1;                          // [nnz]
+  float* sNzW = reinterpret_cast<float*>(sNzFreq + MEL_MAX_NNZ);        // [nnz]
   __shared__ float s_red[MEL_THREADS / 32];
 
   const int b = blockIdx.y;
@@ -92,12 +98,28 @@ mel_kernel(const float* __restrict__ wave, const int* __restrict__ n_samples, lo
   const int nv = n_samples ? min(n_samples[b], N_CLIP) : N_CLIP;       // samples beyond nv are the zero padding
   const float* w = wave + static_cast<long long>(b) * wave_stride;
 
-  // 1. stage the samples of frames f0..f0+23: padded index p = 160*f0 + i  <->  clip index p - 200, reflected
-  for (int i = tid; i < MEL_NS; i += MEL_THREADS) {
-    int s = f0 * 160 + i - 200;
-    if (s < 0) s = -s;
-    if (s >= N_CLIP) s = 2 * (N_CLIP - 1) - s;
-    sW[i] = (s < nv) ? __ldg(w + s) : 0.f;
+  // 1. stage the samples of frames f0..f0+FR-1: padded index p = 160*f0 + i  <->  clip index p - 200, reflected
+  //    at both clip ends (torch.stft center=True, pad_mode="reflect") and zero beyond the clip's own samples.
+  const int s_first = f0 * 160 - 200;
+  if (s_first >= 0 && s_first + MEL_NS <= nv && (reinterpret_cast<uintptr_t>(w + s_first) & 15) == 0) {
+    // interior CTA (all but the first and last two per clip): no reflection, no padding -> 128-bit loads
+    // (s_first is a multiple of 8 samples: f0 is a multiple of MEL_FR = 8 frames of 160, minus 200)
+    const float4* src = reinterpret_cast<const float4*>(w + s_first);
+    float4* dst = reinterpret_cast<float4*>(sW);
+    for (int i = tid; i < MEL_NS / 4; i += MEL_THREADS) dst[i] = __ldg(src + i);
+  } else {
+    for (int i = tid; i < MEL_NS; i += MEL_THREADS) {
+      int s = s_first + i;
+      if (s < 0) s = -s;
+      if (s >= N_CLIP) s = 2 * (N_CLIP - 1) - s;
+      sW[i] = (s < nv) ? __ldg(w + s) : 0.f;
+    }
+  }
+  // the sparse filter bank (CSC) moves to shared memory once per CTA: the mel stage below reads it ~3x per output
+  for (int i = tid; i <= tb.n_mels; i += MEL_THREADS) sColStart[i] = __ldg(tb.col_start + i);
+  for (int i = tid; i < tb.nnz; i += MEL_THREADS) {
+    sNzFreq[i] = __ldg(tb.nz_freq + i);
+    sNzW[i] = __ldg(tb.nz_w + i);
   }
   __syncthreads();
 
@@ -172,25 +194,36 @@ mel_kernel(const float* __restrict__ wave, const int* __restrict__ n_samples, lo
     if (k != 100) P[200 - k] = q.x * q.x + q.y * q.y;
   }
   __syncthreads();
-  // 4. sparse mel + log; thread -> (mel bin, frame) with frame fastest so stores are contiguous per mel row
+  // 4. sparse mel + log: one thread per mel bin for all MEL_FR frames — each filter weight / frequency index is
+  //    read once and used for 8 frames, and the 8 results are one contiguous 32-byte store per mel row.
   float lmax = -INFINITY;
   const int n_mels = tb.n_mels;
-  for (int t = tid; t < n_mels * MEL_FR; t += MEL_THREADS) {
-    const int m = t / MEL_FR, f = t - m * MEL_FR;
-    const int frame = f0 + f;
-    const float* P = sP + f * 204;
-    float acc = 0.f;
-    const int e = __ldg(tb.col_start + m + 1);
-    for (int i = __ldg(tb.col_start + m); i < e; ++i) acc = fmaf(__ldg(tb.nz_w + i), P[__ldg(tb.nz_freq + i)], acc);
-    float v;
-    if (mode == 0) {
-      // log10 via MUFU lg2 (abs. error ~1e-7 on values in [-10, 5]; the parity budget is 1e-5 * max)
-      v = __log2f(fmaxf(acc, 1e-10f)) * 0.30102999566398120f;
-      lmax = fmaxf(lmax, v);
-    } else {
-      v = logf(acc + 1e-9f);
+  for (int m = tid; m < n_mels; m += MEL_THREADS) {
+    float acc[MEL_FR];
+#pragma unroll
+    for (int f = 0; f < MEL_FR; ++f) acc[f] = 0.f;
+    const int e = sColStart[m + 1];
+    for (int i = sColStart[m]; i < e; ++i) {
+      const float wgt = sNzW[i];
+      const float* P = sP + sNzFreq[i];
+#pragma unroll
+      for (int f = 0; f < MEL_FR; ++f) acc[f] = fmaf(wgt, P[f * 204], acc[f]);
     }
-    if (frame < N_FRAMES) out[(static_cast<long long>(b) * n_mels + m) * N_FRAMES + frame] = v;
+    float v[MEL_FR];
+#pragma unroll
+    for (int f = 0; f < MEL_FR; ++f) {
+      if (mode == 0) {
+        // log10 via MUFU lg2 (abs. error ~1e-7 on values in [-10, 5]; the parity budget is 1e-5 * max)
+        v[f] = __log2f(fmaxf(acc[f], 1e-10f)) * 0.30102999566398120f;
+        lmax = fmaxf(lmax, v[f]);
+      } else {
+        v[f] = logf(acc[f] + 1e-9f);
+      }
+    }
+    float* orow = out + (static_cast<long long>(b) * n_mels + m) * N_FRAMES + f0;   // f0 % 8 == 0: 32 B aligned
+    static_assert(MEL_FR % 4 == 0, "frames per CTA must be a multiple of 4 for the vector stores");
+#pragma unroll
+    for (int f = 0; f < MEL_FR; f += 4) *reinterpret_cast<float4*>(orow + f) = make_float4(v[f], v[f + 1], v[f + 2], v[f + 3]);
   }
   if (mode == 0) {
     lmax = warp_max(lmax);
@@ -223,7 +256,7 @@ __global__ void mel_finalize_kernel(float* __restrict__ out, const unsigned int*
 
 int launch_mel(const float* wave, const int* n_samples, int B, long long wave_stride, const MelTables& tb, int mode,
                float* out, unsigned int* clip_max_bits, cudaStream_t stream) {
-  constexpr int smem = MEL_NS * 4 + 2 * MEL_FR * 200 * 8;
+  constexpr int smem = MEL_NS * 4 + 2 * MEL_FR * 200 * 8 + (MEL_MAX_MELS + 1) * 4 + MEL_MAX_NNZ * 8;
   static bool attr_set = false;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
