@@ -28,6 +28,7 @@ SIGNATURES = {
     "al_mel_forward": (i32, [vp, vp, i32, i64, i32, i32, vp, vp, vp]),
     "al_mel_filterbank_host": (i32, [i32, i32, vp]),
     "al_mel_set_filterbank_host": (i32, [i32, i32, vp]),
+    "al_mel_set_mode": (i32, [i32]),
     "al_ingest_forward": (i32, [vp, i64, i64, i32, vp, i32, i32, i32, vp, i64, i32, vp, i32, vp]),
     "al_gemm_bf16": (i32, [vp, i64, i64, i32, i32, vp, i32, i32, vp, vp, i64, i64, i32, vp, i32, vp, vp]),
     "al_gemm_set_mode": (i32, [i32]),

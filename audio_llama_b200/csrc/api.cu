@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -9,8 +10,11 @@
 #include <vector>
 
 #include "../../include/audiollm_b200.h"
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.h"
+#include "mel_bank_struct.h"
 
 namespace al {
 
@@ -156,6 +160,75 @@ static std::mutex g_mel_mu;
 static std::map<int, MelDeviceTables> g_mel_tables;   // key = mode * 1024 + n_mels (one device per process)
 static std::map<int, std::vector<double>> g_mel_override;   // host-supplied banks (al_mel_set_filterbank_host)
 
+// Operands of the tensor-core form (mel_tc.cu): the four folded-DFT twiddle matrices as fp16 hi + lo in the
+// shared-memory image of each CTA of the pair, the windows, and the filter weights in the order of the compiled
+// bank structure (mel_bank_struct.h). A bank whose non-zero pattern matches none of the compiled structures keeps
+// tc_bank = -1 and runs on the FFT kernel.
+static const uint8_t* g_mel_tc_image = nullptr;   // same for every bank
+static int build_mel_tc_tables(const std::vector<double>& fb, int n_mels, int mode, MelTables* t) {
+  const double PI = 3.14159265358979323846;
+  t->tc_bank = -1;
+  t->tc_b_image = nullptr;
+  int bank = -1;
+  std::vector<float> wts(201 * 2, 0.f);
+  for (int c = 0; c < MEL_N_BANKS && bank < 0; ++c) {
+    if (MEL_BANK_NMELS[c] != n_mels || MEL_BANK_MODE[c] != mode) continue;
+    bool same = true;
+    for (int k = 0; k < 201 && same; ++k)
+      for (int m = 0; m < n_mels && same; ++m) {
+        const bool nz = (float)fb[(size_t)k * n_mels + m] != 0.f;
+        same = nz == (m == MEL_BANK_LO[c][k] || m == MEL_BANK_HI[c][k]);
+      }
+    if (same) bank = c;
+  }
+  if (bank < 0) return 0;
+  for (int k = 0; k < 201; ++k) {
+    if (MEL_BANK_LO[bank][k] >= 0) wts[2 * k] = (float)fb[(size_t)k * n_mels + MEL_BANK_LO[bank][k]];
+    if (MEL_BANK_HI[bank][k] >= 0) wts[2 * k + 1] = (float)fb[(size_t)k * n_mels + MEL_BANK_HI[bank][k]];
+  }
+  int rc = mel_tc_set_weights(bank, wts.data());
+  if (rc) return rc;
+  if (g_mel_tc_image == nullptr) {
+    std::vector<float> win(2 * 112, 0.f);
+    for (int kp = 0; kp < 112; ++kp) {           // K position 16 b + e  <->  sample index i = b + 7 e
+      const int i = (kp >> 4) + 7 * (kp & 15);
+      if (i > 100) continue;
+      win[2 * kp] = (float)(0.5 - 0.5 * cos(2.0 * PI * i / 400.0));
+      win[2 * kp + 1] = (float)(0.5 - 0.5 * cos(2.0 * PI * (200 - i) / 400.0));
+    }
+    rc = mel_tc_set_window(win.data());
+    if (rc) return rc;
+    std::vector<uint8_t> img(2 * (size_t)MEL_TC_B_BYTES, 0);
+    for (int rank = 0; rank < 2; ++rank)
+      for (int mat = 0; mat < 4; ++mat) {            // Ce, Se, Co, So
+        const int parity = mat >> 1, is_sin = mat & 1, n_valid = parity ? 100 : 101;
+        for (int nl = 0; nl < 56; ++nl) {
+          const int jn = 56 * rank + nl;
+          for (int kp = 0; kp < 112; ++kp) {         // K position 16 b + e  <->  sample index i = b + 7 e
+            const int i = (kp >> 4) + 7 * (kp & 15);
+            double v = 0.0;
+            if (jn < n_valid && i <= 100) {
+              const double ang = 2.0 * PI * (double)i * (double)(2 * jn + parity) / 400.0;
+              v = (is_sin ? sin(ang) : cos(ang)) * ((i == 0 || i == 100) ? 0.5 : 1.0);
+            }
+            const __half hi = __float2half_rn((float)v);
+            const __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+            const size_t off = (size_t)(kp / 8) * MEL_TC_KCHUNK_BYTES + (size_t)(nl / 8) * 128 + (size_t)(nl % 8) * 16 + (size_t)(kp % 8) * 2;
+            memcpy(&img[(size_t)rank * MEL_TC_B_BYTES + (size_t)(2 * mat) * MEL_TC_MAT_BYTES + off], &hi, 2);
+            memcpy(&img[(size_t)rank * MEL_TC_B_BYTES + (size_t)(2 * mat + 1) * MEL_TC_MAT_BYTES + off], &lo, 2);
+          }
+        }
+      }
+    void* pi;
+    AL_CHECK_CUDA(cudaMalloc(&pi, img.size()));
+    AL_CHECK_CUDA(cudaMemcpy(pi, img.data(), img.size(), cudaMemcpyHostToDevice));
+    g_mel_tc_image = (const uint8_t*)pi;
+  }
+  t->tc_b_image = g_mel_tc_image;
+  t->tc_bank = bank;
+  return 0;
+}
+
 static int get_mel_tables(int n_mels, int mode, MelTables* out) {
   std::lock_guard<std::mutex> lk(g_mel_mu);
   const int key = mode * 1024 + n_mels;
@@ -192,6 +265,7 @@ static int get_mel_tables(int n_mels, int mode, MelTables* out) {
     nz_w.push_back(0.f);
   }
   MelDeviceTables d;
+  int rc_tc = 0;
   void *pw, *p2, *p4, *pc, *pf, *pz;
   AL_CHECK_CUDA(cudaMalloc(&pw, 400 * 4));
   AL_CHECK_CUDA(cudaMalloc(&p2, 200 * 8));
@@ -213,6 +287,8 @@ static int get_mel_tables(int n_mels, int mode, MelTables* out) {
   d.t.nz_w = (const float*)pz;
   d.t.n_mels = n_mels;
   d.t.nnz = (int)nz_w.size();
+  rc_tc = build_mel_tc_tables(fb, n_mels, mode, &d.t);
+  if (rc_tc) return rc_tc;
   if (d.t.nnz > 1024 || n_mels > 256) {
     set_error("mel filter bank too dense for the kernel's shared-memory tables (nnz=%d, n_mels=%d)", d.t.nnz, n_mels);
     return -1;
@@ -349,6 +425,19 @@ const char* al_last_error(void) { return g_err; }
 long long al_launch_count(void) { return g_launches; }
 
 // ----------------------------------------------------------------------------- mel
+static int g_mel_tc = -1;   // -1 = read AUDIOLLM_B200_MEL (tc | fft) once; default tc
+static bool mel_use_tc() {
+  if (g_mel_tc < 0) {
+    const char* e = getenv("AUDIOLLM_B200_MEL");
+    g_mel_tc = (e && strcmp(e, "fft") == 0) ? 0 : 1;
+  }
+  return g_mel_tc == 1;
+}
+int al_mel_set_mode(int tc) {
+  g_mel_tc = tc ? 1 : 0;
+  return 0;
+}
+
 int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels, int mode,
                    float* out, unsigned int* clip_max_ws, al_stream_t stream) {
   AL_REQUIRE(n_clips >= 0 && n_mels > 0 && n_mels <= 256, "al_mel_forward: bad n_clips=%d / n_mels=%d", n_clips, n_mels);
@@ -361,7 +450,8 @@ int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long lo
   int rc = get_mel_tables(n_mels, mode, &tb);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_mel(wave, n_samples, n_clips, wave_stride, tb, mode, out, clip_max_ws, st);
+  if (tb.tc_bank >= 0 && mel_use_tc()) rc = launch_mel_tc(wave, n_samples, n_clips, wave_stride, tb, mode, out, clip_max_ws, num_sms(), st);
+  else rc = launch_mel(wave, n_samples, n_clips, wave_stride, tb, mode, out, clip_max_ws, st);
   if (rc) return rc;
   g_launches += 1;
   if (mode == 0) {

@@ -82,7 +82,20 @@ struct MelTables {
   const float* nz_w;       // [nnz]
   int n_mels;
   int nnz;
+  // tensor-core form (mel_tc.cu): tc_bank = index of the compiled bank structure (mel_bank_struct.h) this bank's
+  // non-zero pattern equals, or -1 (only the FFT kernel applies)
+  const uint8_t* tc_b_image;   // [2 CTA ranks][MEL_TC_B_BYTES] fp16 twiddle operands in their shared-memory layout
+  int tc_bank;
 };
+// twiddle operand image of one CTA of the pair: 8 matrices (Ce, Se, Co, So x hi, lo), each 56 rows x 112 K halves as
+// [14 K chunks of 8 halves][7 row groups][8 rows][16 B]. K position 16 b + e holds sample index i = b + 7 e.
+constexpr int MEL_TC_KCHUNK_BYTES = 7 * 128;
+constexpr int MEL_TC_MAT_BYTES = 14 * MEL_TC_KCHUNK_BYTES;
+constexpr int MEL_TC_B_BYTES = 8 * MEL_TC_MAT_BYTES;
+int mel_tc_set_window(const float* host_win_2x112);
+int mel_tc_set_weights(int bank, const float* host_w_201x2);
+int launch_mel_tc(const float* wave, const int* n_samples, int B, long long wave_stride, const MelTables& tb, int mode,
+                  float* out, unsigned int* clip_max_bits, int num_sms, cudaStream_t stream);
 // mode 0: whisper (log10, per-clip max written to clip_max for finalize); mode 1: ln(x + 1e-9).
 int launch_mel(const float* wave, const int* n_samples, int B, long long wave_stride, const MelTables& tb, int mode,
                float* out, unsigned int* clip_max_bits, cudaStream_t stream);

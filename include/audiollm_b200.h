@@ -49,6 +49,10 @@ int al_mel_filterbank_host(int n_mels, int mode, double* out_host);
  * this for mode 1: torchaudio builds the HTK bank with float32 torch ops whose last-ulp behaviour moves the very
  * narrow low filters by ~1e-3 relative, so the bank is rebuilt with the same torch ops and handed in. */
 int al_mel_set_filterbank_host(int n_mels, int mode, const double* fb_host);
+/* Kernel form of al_mel_forward: 1 = tensor-core folded DFT (fp16 hi/lo operands, fp32 accumulation; default when
+ * the filter bank is banded), 0 = CUDA-core FFT. Same results within the mel tolerance; the environment variable
+ * AUDIOLLM_B200_MEL=tc|fft sets the default. */
+int al_mel_set_mode(int tc);
 
 /* ---- waveform ingest ----------------------------------------------------------
  * Channel mean + sinc resampling to `new_freq` + zero padding / truncation to out_cap samples, one launch.
