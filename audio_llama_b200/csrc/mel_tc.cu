@@ -44,6 +44,7 @@
 // samples i = b + 7e (e = 0..15): every block sum is ~1/7 of the final sum and the partial sums stay at the size of
 // the result (simulated and measured < 1e-5).
 #include <cuda_fp16.h>
+#include <string.h>
 
 #include <type_traits>
 #include <utility>
@@ -57,6 +58,7 @@ namespace al {
 constexpr int TC_N = 112;                               // output bins per parity, padded (101 / 100 used)
 constexpr int TC_SEG = 160, TC_SEG_STRIDE = 164, TC_NSEG = 34;
 constexpr int TC_SLOT_FLOATS = TC_NSEG * TC_SEG_STRIDE;          // 5576
+constexpr int TC_SLOT_PITCH = 5600;                              // floats between slots: tensor copies need 128 B aligned destinations
 constexpr int TC_SLOT_SAMPLES = 31 * 160 + 400;                  // 5360 samples feed 32 frames
 constexpr int TC_NSLOT = 5;
 constexpr int TC_TILES_PER_CLIP = 12;                            // ceil(3000 / 256)
@@ -67,7 +69,8 @@ constexpr uint32_t TC_D_CE = 0, TC_D_SE = 112, TC_D_CO = 224, TC_D_SO = 336, TC_
 
 constexpr int TC_OFF_B = 0;
 constexpr int TC_OFF_SLOTS = TC_OFF_B + MEL_TC_B_BYTES;
-constexpr int TC_OFF_BAR = TC_OFF_SLOTS + TC_NSLOT * TC_SLOT_FLOATS * 4;
+constexpr int TC_OFF_BAR = TC_OFF_SLOTS + TC_NSLOT * TC_SLOT_PITCH * 4;
+static_assert(TC_OFF_SLOTS % 128 == 0 && (TC_SLOT_PITCH * 4) % 128 == 0 && TC_SLOT_PITCH >= TC_SLOT_FLOATS, "slot alignment");
 constexpr int TC_NBAR = 2 * TC_NSLOT + 2 + 2 + 1 + 1 + 1;
 constexpr int TC_OFF_MISC = TC_OFF_BAR + TC_NBAR * 8;
 constexpr int TC_SMEM = TC_OFF_MISC + 128 /*tmem ptr, slot max, scales*/ + 128 /*alignment slack*/;
@@ -176,6 +179,8 @@ struct MelTcArgs {
   float* out;
   unsigned int* clip_max_bits;
   int n_clips;
+  int use_tmap;               // 1: interior slots arrive by one 3-D tensor copy (box 164 x 34 rows of the overlapping-
+                              // row view of the wave buffer), 0: one bulk copy per hop
 };
 
 // ------------------------------------------------------------------ operand builder: one K block of one frame half
@@ -262,7 +267,7 @@ __device__ __forceinline__ void mel_bin(float (&mel)[128], float re, float im) {
 }
 
 template <int BANK>
-__global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_constant__ CUtensorMap tm_wave, const MelTcArgs p) {
   constexpr int N_MELS = MEL_BANK_NMELS[BANK];
   constexpr int MODE = MEL_BANK_MODE[BANK];
   extern __shared__ uint8_t smem_raw[];
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
   const int total_tiles = p.n_clips * TC_TILES_PER_CLIP;
 
   if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_wave);
     for (int s = 0; s < TC_NSLOT; ++s) {
       mbar_init(&slot_full[s], 1);
       mbar_init(&slot_empty[s], 2);
@@ -306,7 +312,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
   // term) and must stay finite
   {
     float4* z = reinterpret_cast<float4*>(sSlots);
-    for (int i = threadIdx.x; i < TC_NSLOT * TC_SLOT_FLOATS / 4; i += TC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < TC_NSLOT * TC_SLOT_PITCH / 4; i += TC_THREADS) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async_smem();
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_ptr);
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
         for (int q = 0; q < 4; ++q, ++u) {
           const int slot = u % TC_NSLOT;
           const uint32_t use = static_cast<uint32_t>(u / TC_NSLOT);
-          float* dst = sSlots + slot * TC_SLOT_FLOATS;
+          float* dst = sSlots + slot * TC_SLOT_PITCH;
           mbar_wait(&slot_empty[slot], (use & 1) ^ 1);
           const int f0 = f_cta + 32 * q;
           if (f0 >= TC_FRAMES) {                 // frames past the clip: never stored, any finite content will do
@@ -343,6 +349,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
             continue;
           }
           const int s_first = f0 * 160 - 200;    // clip index of the slot's first sample (multiple of 8 -> 16 B steps)
+          // Interior slot: rows f0 - 2 .. f0 + 31 of the view [clip][row r = samples 120 + 160 r .. + 163] in ONE tensor
+          // copy; its 34 x 164 box is exactly the slot image (the 4 "pad" floats of a row are the next row's first
+          // samples). Everything it reads must be real audio: the scale scan looks at the whole slot.
+          if (p.use_tmap && s_first >= 0 && s_first + TC_NSEG * TC_SEG + 4 <= nv) {
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&slot_full[slot], TC_SLOT_FLOATS * 4);
+              tma_load_3d(dst, &tm_wave, &slot_full[slot], 0, f0 - 2, b);
+            }
+            continue;
+          }
           // hop h of the slot is copied in bulk when it lies wholly inside [0, nv)
           auto hop_len = [](int h) { return h < TC_NSEG - 1 ? TC_SEG : TC_SLOT_SAMPLES - (TC_NSEG - 1) * TC_SEG; };
           auto hop_bulk = [&](int h) -> bool {
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
       const int u = it * 4 + q;
       const int slot = u % TC_NSLOT;
       const uint32_t use = static_cast<uint32_t>(u / TC_NSLOT);
-      const float* sl = sSlots + slot * TC_SLOT_FLOATS;
+      const float* sl = sSlots + slot * TC_SLOT_PITCH;
       mbar_wait(&slot_full[slot], use & 1);
       // power-of-two scale of this slot: 4 max|x| 2^sh < 2^15 (a folded value is a sum of four samples)
       float mx = 0.f;
@@ -536,7 +552,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const MelTcArgs p
 }
 
 template <int BANK>
-static int launch_bank(const MelTcArgs& a, int num_sms, cudaStream_t stream) {
+static int launch_bank(const CUtensorMap& tm, const MelTcArgs& a, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(mel_tc_kernel<BANK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
@@ -556,7 +572,7 @@ static int launch_bank(const MelTcArgs& a, int num_sms, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  AL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mel_tc_kernel<BANK>, a));
+  AL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, mel_tc_kernel<BANK>, tm, a));
   return 0;
 }
 
@@ -573,10 +589,23 @@ int launch_mel_tc(const float* wave, const int* n_samples, int B, long long wave
   a.out = out;
   a.clip_max_bits = clip_max_bits;
   a.n_clips = B;
+  // Overlapping-row view of the wave buffer for the slot loader: [clip][row r][164] with row r = samples
+  // 120 + 160 r .. 120 + 160 r + 163 of the clip (row stride 640 B). Needs a 16-byte aligned base and clip stride.
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  a.use_tmap = 0;
+  if ((reinterpret_cast<uintptr_t>(wave) & 15) == 0 && wave_stride % 4 == 0 && wave_stride >= 120 + 164) {
+    const uint64_t rows = static_cast<uint64_t>((wave_stride - 120 - 164) / 160 + 1);
+    const uint64_t dims[3] = {164, rows, static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {4, 640, static_cast<uint64_t>(wave_stride) * 4};
+    const uint32_t box[3] = {164, TC_NSEG, 1};
+    if (make_tmap(&tm, wave + 120, 4, 3, dims, str, box, false) != 0) return -1;
+    a.use_tmap = 1;
+  }
   switch (tb.tc_bank) {
-    case 0: return launch_bank<0>(a, num_sms, stream);
-    case 1: return launch_bank<1>(a, num_sms, stream);
-    default: return launch_bank<2>(a, num_sms, stream);
+    case 0: return launch_bank<0>(tm, a, num_sms, stream);
+    case 1: return launch_bank<1>(tm, a, num_sms, stream);
+    default: return launch_bank<2>(tm, a, num_sms, stream);
   }
 }
 
