@@ -49,6 +49,8 @@ SIGNATURES = {
     "al_projector_backward_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "al_projector_backward": (i32, [vp, i32, i32, i32, i32] + [vp] * 15),
     "al_lora_linear_forward": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "al_lora_linear_backward_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "al_lora_linear_backward": (i32, [vp, vp, i32, i32, i32, i32] + [vp] * 9),
     "al_splice": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp]),
     "al_splice_ragged": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i64, i64, vp, vp, vp, vp, vp]),
 }

@@ -933,6 +933,81 @@ int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int
   return rc;
 }
 
+size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim, int rank) {
+  const size_t rp = (size_t)(rows + 7) / 8 * 8;
+  size_t b = 0;
+  auto add = [&](size_t n) { b += (n + 1023) / 1024 * 1024; };
+  add((size_t)rank * out_dim * 2);   // (sB)^T
+  add((size_t)in_dim * rank * 2);    // A^T
+  add((size_t)rows * rank * 2);      // U = dy (sB)
+  add(rp * rank * 2);                // U^T
+  add(rp * rank * 2);                // T^T
+  add(rp * in_dim * 2);              // x^T
+  add(rp * out_dim * 2);             // dy^T
+  return b;
+}
+
+// Backward of out = x W^T + T (sB)^T, T = x A^T, W frozen:
+//   U = dy (sB)              [rows][rank]
+//   dx = dy W + U A          one GEMM, second operand pair in the K loop (same TMEM accumulator)
+//   dA = U^T x               [rank][in]   fp32, split-K reduce-add
+//   dB_raw = dy^T T          [out][rank]  fp32, split-K reduce-add (gradient of the UNSCALED B = scaling * dB_raw)
+int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
+                            const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace, void* dx,
+                            float* dA, float* dB_raw, al_stream_t stream) {
+  AL_REQUIRE(x && dy && lora_A && lora_B_scaled && t_saved && workspace && dA && dB_raw,
+             "al_lora_linear_backward: NULL argument");
+  AL_REQUIRE(dx == nullptr || W_T != nullptr, "al_lora_linear_backward: dx needs W_T ([in][out], the frozen weight transposed)");
+  AL_REQUIRE(rows > 0 && in_dim % 8 == 0 && out_dim % 8 == 0 && rank % 8 == 0 && rank > 0,
+             "al_lora_linear_backward: bad shape rows=%d in=%d out=%d rank=%d", rows, in_dim, out_dim, rank);
+  AL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "al_lora_linear_backward: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rp = (rows + 7) / 8 * 8;
+  uint8_t* w = (uint8_t*)workspace;
+  auto take = [&](size_t n) { void* p = w; w += (n + 1023) / 1024 * 1024; return p; };
+  void* sBT = take((size_t)rank * out_dim * 2);
+  void* AT = take((size_t)in_dim * rank * 2);
+  void* U = take((size_t)rows * rank * 2);
+  void* UT = take((size_t)rp * rank * 2);
+  void* TT = take((size_t)rp * rank * 2);
+  void* xT = take((size_t)rp * in_dim * 2);
+  void* dyT = take((size_t)rp * out_dim * 2);
+  AL_CHECK_CUDA(cudaMemsetAsync(dA, 0, (size_t)rank * in_dim * 4, st));
+  AL_CHECK_CUDA(cudaMemsetAsync(dB_raw, 0, (size_t)out_dim * rank * 4, st));
+  int rc;
+#define STEP(expr) do { rc = (expr); if (rc) return rc; g_launches += 1; } while (0)
+  // 1. U = dy (sB): the weight operand is (sB)^T [rank][out]
+  STEP(launch_transpose_bf16(lora_B_scaled, sBT, out_dim, rank, out_dim, st));
+  if ((rc = gemm_plain(dy, out_dim, rows, sBT, out_dim, rank, out_dim, nullptr, U, rank, 0, nullptr, 0, 0, st))) return rc;
+  // 2. dx = dy W + U A
+  if (dx != nullptr) {
+    STEP(launch_transpose_bf16(lora_A, AT, rank, in_dim, rank, st));
+    CUtensorMap ta, tb, ta2, tb2, to;
+    if ((rc = tmap_rows3d(&ta, dy, 2, out_dim, rows, 1, out_dim, (uint64_t)rows * out_dim, 64, 128))) return rc;
+    if ((rc = tmap_weight(&tb, W_T, in_dim, out_dim))) return rc;
+    if ((rc = tmap_rows3d(&ta2, U, 2, rank, rows, 1, rank, (uint64_t)rows * rank, 64, 128))) return rc;
+    if ((rc = tmap_weight(&tb2, AT, in_dim, rank))) return rc;
+    if ((rc = tmap_rows3d(&to, dx, 2, in_dim, rows, 1, in_dim, (uint64_t)rows * in_dim, gemm_out_box_cols(0), 128))) return rc;
+    GemmParams p{};
+    p.m_per_batch = rows; p.batch = 1; p.N = in_dim; p.K = out_dim; p.K2 = rank;
+    rc = launch_gemm2(ta, tb, to, ta2, tb2, p, 0, num_sms(), st);
+    if (rc) return rc;
+    g_launches += 1;
+  }
+  // 3. dA = U^T x  (contraction over the rows: both operands transposed to K-major, split-K)
+  STEP(launch_transpose_bf16(U, UT, rows, rank, rp, st));
+  STEP(launch_transpose_bf16(x, xT, rows, in_dim, rp, st));
+  if ((rc = gemm_plain(UT, rp, rank, xT, rp, in_dim, rp, nullptr, dA, in_dim, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
+                       2 * num_sms(), st))) return rc;
+  // 4. dB_raw = dy^T T
+  STEP(launch_transpose_bf16(dy, dyT, rows, out_dim, rp, st));
+  STEP(launch_transpose_bf16(t_saved, TT, rows, rank, rp, st));
+  if ((rc = gemm_plain(dyT, rp, out_dim, TT, rp, rank, rp, nullptr, dB_raw, rank, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
+                       2 * num_sms(), st))) return rc;
+#undef STEP
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- splice
 int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
               const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,

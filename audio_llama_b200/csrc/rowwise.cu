@@ -127,30 +127,46 @@ int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c
 //   0 <- E[<audio>] ; 1..A <- audio rows (copied only if `audio_rows` != null — the projector's LayerNorm
 //   normally writes them in place) ; A+1 <- E[</audio>] ; A+2+j <- E[input_ids[b][j]].
 // mask_out = [1.0f x (A+2), attention_mask] (float32, allm.py:192-194); labels_out = [-100 x (A+2), labels].
+// Four 16-byte loads in flight per lane before the first store (a 4 KB row is 8 of them per lane).
 __device__ __forceinline__ void copy_row_16B(void* dst, const void* src, int n16, int lane) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
-  for (int i = lane; i < n16; i += 32) d[i] = __ldg(s + i);
+  int i = lane;
+  for (; i + 96 < n16; i += 128) {
+    const uint4 a = __ldg(s + i), b = __ldg(s + i + 32), c = __ldg(s + i + 64), e = __ldg(s + i + 96);
+    d[i] = a; d[i + 32] = b; d[i + 64] = c; d[i + 96] = e;
+  }
+  for (; i < n16; i += 32) d[i] = __ldg(s + i);
 }
 
+// COPY_AUDIO = true : one warp per output row, audio rows copied from `audio_rows`.
+// COPY_AUDIO = false: the audio rows are already in place (the projector's LayerNorm wrote them), so only the
+//   t_txt + 2 gathered rows of a sample get a warp; the mask / labels entries of the A audio rows are written by the
+//   text-row warps, ceil(A / t_txt) each (or all by the <audio> warp when there is no text).
+template <bool COPY_AUDIO>
 __global__ void __launch_bounds__(256)
 splice_kernel(const uint8_t* __restrict__ table, long long row_bytes, const long long* __restrict__ input_ids,
               const long long* __restrict__ attn_mask, const long long* __restrict__ labels, int B, int t_txt,
               int n_audio, long long start_id, long long end_id, const uint8_t* __restrict__ audio_rows,
               uint8_t* __restrict__ out, float* __restrict__ mask_out, long long* __restrict__ labels_out) {
   const int S = n_audio + 2 + t_txt;
+  const int per_sample = COPY_AUDIO ? S : t_txt + 2;
   const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (gw >= static_cast<long long>(B) * S) return;
+  if (gw >= static_cast<long long>(B) * per_sample) return;
   const int lane = threadIdx.x & 31;
-  const int b = static_cast<int>(gw / S), r = static_cast<int>(gw % S);
-  uint8_t* dst = out + gw * row_bytes;
+  const int b = static_cast<int>(gw / per_sample);
+  int r = static_cast<int>(gw % per_sample);
+  if (!COPY_AUDIO && r >= 1) r += n_audio;               // 0 -> 0, 1 -> A + 1, 2 + j -> A + 2 + j
+  const long long orow = static_cast<long long>(b) * S + r;
+  uint8_t* dst = out + orow * row_bytes;
   const int n16 = static_cast<int>(row_bytes >> 4);
   float mk = 1.0f;
   long long lb = -100;
   if (r == 0) {
     copy_row_16B(dst, table + start_id * row_bytes, n16, lane);
   } else if (r <= n_audio) {
-    if (audio_rows) copy_row_16B(dst, audio_rows + (static_cast<long long>(b) * n_audio + (r - 1)) * row_bytes, n16, lane);
+    if (COPY_AUDIO && audio_rows)
+      copy_row_16B(dst, audio_rows + (static_cast<long long>(b) * n_audio + (r - 1)) * row_bytes, n16, lane);
   } else if (r == n_audio + 1) {
     copy_row_16B(dst, table + end_id * row_bytes, n16, lane);
   } else {
@@ -161,8 +177,25 @@ splice_kernel(const uint8_t* __restrict__ table, long long row_bytes, const long
     if (labels) lb = labels[static_cast<long long>(b) * t_txt + j];
   }
   if (lane == 0) {
-    if (mask_out) mask_out[gw] = mk;
-    if (labels_out) labels_out[gw] = lb;
+    if (mask_out) mask_out[orow] = mk;
+    if (labels_out) labels_out[orow] = lb;
+  }
+  if (!COPY_AUDIO) {
+    // mask 1.0 / labels -100 of the audio rows 1..A (allm.py:81-89, 184-196)
+    int a0, a1;
+    if (t_txt > 0) {
+      const int per = (n_audio + t_txt - 1) / t_txt;
+      const int j = r - n_audio - 2;
+      a0 = j >= 0 ? 1 + j * per : 0;
+      a1 = j >= 0 ? min(a0 + per, n_audio + 1) : 0;
+    } else {
+      a0 = r == 0 ? 1 : 0;
+      a1 = r == 0 ? n_audio + 1 : 0;
+    }
+    for (int a = a0 + lane; a < a1; a += 32) {
+      if (mask_out) mask_out[static_cast<long long>(b) * S + a] = 1.0f;
+      if (labels_out) labels_out[static_cast<long long>(b) * S + a] = -100;
+    }
   }
 }
 
@@ -232,11 +265,18 @@ int launch_splice(const void* table, int elem_bytes, int d, const long long* inp
                   const void* audio_rows, void* out, float* mask_out, long long* labels_out, cudaStream_t stream) {
   const long long row_bytes = static_cast<long long>(d) * elem_bytes;
   AL_REQUIRE(row_bytes % 16 == 0, "splice: row of %lld bytes is not a multiple of 16", row_bytes);
-  const long long rows = static_cast<long long>(B) * (n_audio + 2 + t_txt);
+  const bool copy_audio = audio_rows != nullptr;
+  const long long rows = static_cast<long long>(B) * (copy_audio ? n_audio + 2 + t_txt : t_txt + 2);
   if (rows == 0) return 0;
-  splice_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
-      reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id,
-      end_id, reinterpret_cast<const uint8_t*>(audio_rows), reinterpret_cast<uint8_t*>(out), mask_out, labels_out);
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (copy_audio)
+    splice_kernel<true><<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id,
+        end_id, reinterpret_cast<const uint8_t*>(audio_rows), reinterpret_cast<uint8_t*>(out), mask_out, labels_out);
+  else
+    splice_kernel<false><<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id,
+        end_id, nullptr, reinterpret_cast<uint8_t*>(out), mask_out, labels_out);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -51,31 +51,42 @@ def lora_forward_hook(module, input, output, lora_layer):
 
 
 # ----------------------------------------------------------------------------- fused path (B200)
+_WT_CACHE = {}   # frozen weight (data_ptr, shape) -> its transpose [in, out], built once
+
+
+def _frozen_weight_t(weight: torch.Tensor) -> torch.Tensor:
+    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
+    wt = _WT_CACHE.get(key)
+    if wt is None:
+        wt = weight.detach().t().contiguous()
+        _WT_CACHE[key] = wt
+    return wt
+
+
 class _FusedLoRALinearFn(torch.autograd.Function):
     """y = x W^T + b + s (x A^T) B^T through `al_lora_linear_forward` (the rank-r product rides in the frozen GEMM's
-    TMEM accumulator). Backward keeps W frozen: dx = dy W + s (dy B) A, dA = s (dy B)^T x, dB = s dy^T (x A^T)."""
+    TMEM accumulator). Backward keeps W frozen and is native too (`al_lora_linear_backward`): dx = dy W + s (dy B) A in
+    one GEMM with the low-rank pair in the K loop, dA = s (dy B)^T x and dB = s dy^T (x A^T) as split-K GEMMs."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, lora_A, lora_B, scaling):
         from .. import ops
-        y = ops.lora_linear(x.contiguous(), weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype)
-        ctx.save_for_backward(x, weight, lora_A, lora_B)
+        y, (a_pad, b_pad, t) = ops.lora_linear(x.contiguous(), weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype,
+                                              return_saved=True)
+        ctx.save_for_backward(x, weight, a_pad, b_pad, t)
         ctx.scaling = scaling
+        ctx.rank = lora_A.shape[0]
+        ctx.dtypes = (lora_A.dtype, lora_B.dtype)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, lora_A, lora_B = ctx.saved_tensors
-        s = ctx.scaling
-        dy2 = dy.reshape(-1, dy.shape[-1])
-        x2 = x.reshape(-1, x.shape[-1])
-        a = lora_A.to(dy.dtype)
-        b = lora_B.to(dy.dtype)
-        u = dy2 @ b                                          # [M, r]
-        dx = (dy2 @ weight + (u @ a) * s).view_as(x) if ctx.needs_input_grad[0] else None
-        dA = ((u.T @ x2) * s).to(lora_A.dtype)
-        dB = ((dy2.T @ (x2 @ a.T)) * s).to(lora_B.dtype)
-        return dx, None, None, dA, dB, None
+        from .. import ops
+        x, weight, a_pad, b_pad, t = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dx, dA, dB_raw = ops.lora_linear_backward(x.contiguous(), dy.to(torch.bfloat16), _frozen_weight_t(weight) if need_dx else None,
+                                                  a_pad, b_pad, t, ctx.rank, need_dx=need_dx)
+        return dx, None, None, dA.to(ctx.dtypes[0]), (dB_raw * ctx.scaling).to(ctx.dtypes[1]), None
 
 
 def fused_lora_forward(module: nn.Linear, lora_layer: LoRALayer, x: torch.Tensor) -> torch.Tensor:

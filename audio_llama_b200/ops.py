@@ -196,9 +196,10 @@ def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optiona
 
 
 def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: torch.Tensor,
-                lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16) -> torch.Tensor:
+                lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16, return_saved: bool = False):
     """Frozen linear + LoRA (L1): x [..., in] bf16, w [out, in] bf16, lora_a [r, in], lora_b [out, r] (any float dtype).
-    out = x w^T + bias + scaling * (x a^T) b^T with the rank-r product accumulated inside the frozen GEMM."""
+    out = x w^T + bias + scaling * (x a^T) b^T with the rank-r product accumulated inside the frozen GEMM.
+    return_saved=True also returns (a_pad, b_scaled_pad, t) for lora_linear_backward."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
     out_dim, in_dim = w.shape
@@ -217,7 +218,36 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     check(lib().al_lora_linear_forward(ptr(x2), rows, in_dim, out_dim, r_pad, ptr(w), ptr(bias), ptr(a), ptr(b),
                                        ptr(t_ws), ptr(out), 1 if out_dtype == torch.float32 else 0, stream_ptr()),
           "al_lora_linear_forward")
+    if return_saved:
+        return out, (a, b, t_ws)
     return out
+
+
+def lora_linear_backward(x: torch.Tensor, dy: torch.Tensor, w_t: Optional[torch.Tensor], a_pad: torch.Tensor,
+                         b_scaled_pad: torch.Tensor, t_saved: torch.Tensor, rank: int, need_dx: bool = True):
+    """Backward of lora_linear with the weight frozen. x [..., in], dy [..., out] bf16; w_t = w.t().contiguous()
+    ([in, out] bf16, needed only for dx). Returns (dx or None, dA [rank, in] f32, dB_raw [out, rank] f32) where the
+    gradient of the unscaled lora_B is scaling * dB_raw (dA already carries the scaling)."""
+    _req(x, torch.bfloat16, "x")
+    dy = _req(dy.contiguous(), torch.bfloat16, "dy")
+    r_pad, in_dim = a_pad.shape
+    out_dim = b_scaled_pad.shape[0]
+    x2 = x.reshape(-1, in_dim)
+    dy2 = dy.reshape(-1, out_dim)
+    rows = x2.shape[0]
+    nbytes = int(lib().al_lora_linear_backward_workspace_bytes(rows, in_dim, out_dim, r_pad))
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
+    off = (-ws.data_ptr()) % 1024
+    ws = ws[off:off + nbytes]
+    dx = torch.empty_like(x2) if need_dx else None
+    if need_dx:
+        _req(w_t, torch.bfloat16, "w_t")
+    dA = torch.empty(r_pad, in_dim, dtype=torch.float32, device=x.device)
+    dB = torch.empty(out_dim, r_pad, dtype=torch.float32, device=x.device)
+    check(lib().al_lora_linear_backward(ptr(x2), ptr(dy2), rows, in_dim, out_dim, r_pad, ptr(w_t) if need_dx else None,
+                                        ptr(a_pad), ptr(b_scaled_pad), ptr(t_saved), ptr(ws), ptr(dx), ptr(dA), ptr(dB),
+                                        stream_ptr()), "al_lora_linear_backward")
+    return (dx.view_as(x) if need_dx else None), dA[:rank], dB[:, :rank]
 
 
 def launch_count() -> int:

@@ -166,6 +166,16 @@ int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int
                            const float* bias, const void* lora_A, const void* lora_B_scaled, void* t_ws, void* out,
                            int out_dtype, al_stream_t stream);
 
+/* Backward of al_lora_linear_forward with W frozen (what autograd derives from lora.py:20-21, 41-43 plus the hooked
+ * nn.Linear): U = dy (sB); dx = dy W + U A (one GEMM, second operand pair in the K loop; NULL dx skips it);
+ * dA = U^T x [rank][in] f32; dB_raw = dy^T T [out][rank] f32 with T = x A^T saved by the forward (t_ws) — the
+ * gradient of the UNSCALED lora_B is scaling * dB_raw, and dA already carries the scaling through U.
+ * W_T is the frozen weight transposed, [in][out] bf16 (transposed once by the caller, it never changes). */
+size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim, int rank);
+int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
+                            const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace,
+                            void* dx, float* dA, float* dB_raw, al_stream_t stream);
+
 /* ---- S1 / S2: splice ------------------------------------------------------------------------------
  * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask
  * (allm.py:176-196) and the label extension (allm.py:81-89). Row map per sample (bit-exact contract):

@@ -78,3 +78,29 @@ def test_fused_lora_in_llama_matches_hooks():
     a, b = run(False), run(True)
     assert O.rel_l2(b[0], a[0]) <= 3e-2                       # bf16 LLaMA both ways; different rounding points
     assert O.rel_l2(b[1], a[1]) <= 1e-1 and O.rel_l2(b[2], a[2]) <= 1e-1
+
+
+@pytest.mark.parametrize("in_dim,out_dim,rank,rows", [(3072, 1024, 64, 2014), (1024, 3072, 64, 517), (256, 512, 8, 77)])
+def test_lora_linear_backward(in_dim, out_dim, rank, rows):
+    """al_lora_linear_backward (dx, dA, dB) vs torch autograd of the oracle's hook formula in fp32."""
+    g = torch.Generator().manual_seed(in_dim * 7 + out_dim)
+    x = torch.randn(rows, in_dim, generator=g).bfloat16()
+    W = (torch.randn(out_dim, in_dim, generator=g) * 0.02).bfloat16()
+    A = (torch.randn(rank, in_dim, generator=g) * 0.05)
+    B = (torch.randn(out_dim, rank, generator=g) * 0.05)
+    dy = torch.randn(rows, out_dim, generator=g).bfloat16()
+    scaling = 16 / rank
+    xr = x.float().requires_grad_(True)
+    Ar = A.bfloat16().float().requires_grad_(True)      # the kernel's operands are the bf16 roundings
+    Br = B.clone().requires_grad_(True)
+    y = O.lora_linear(xr, W.float(), None, Ar, Br, scaling)
+    y.backward(dy.float())
+    xc, Wc = x.cuda(), W.cuda()
+    _, (a_pad, b_pad, t) = ops.lora_linear(xc, Wc, None, A.cuda(), B.cuda(), scaling, return_saved=True)
+    dx, dA, dB_raw = ops.lora_linear_backward(xc, dy.cuda(), Wc.t().contiguous(), a_pad, b_pad, t, rank)
+    assert O.rel_l2(dx.float().cpu(), xr.grad) <= 1e-2
+    assert O.rel_l2(dA.cpu(), Ar.grad) <= 2e-2
+    assert O.rel_l2((dB_raw * scaling).cpu(), Br.grad) <= 2e-2
+    # dx skipped when the input needs no gradient
+    dx2, dA2, _ = ops.lora_linear_backward(xc, dy.cuda(), None, a_pad, b_pad, t, rank, need_dx=False)
+    assert dx2 is None and O.rel_l2(dA2.cpu(), dA.cpu()) <= 1e-5      # (split-K reduce-add: not bit-reproducible)
