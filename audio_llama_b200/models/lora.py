@@ -63,6 +63,21 @@ def _frozen_weight_t(weight: torch.Tensor) -> torch.Tensor:
     return wt
 
 
+_PACK_CACHE = {}  # (id(A), id(B)) -> (A._version, B._version, scaling, packed operands): repacked after optimizer steps
+
+
+def _packed_operands(lora_A, lora_B, scaling):
+    from .. import ops
+    key = (id(lora_A), id(lora_B))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0] == lora_A._version and hit[1] == lora_B._version and hit[2] == scaling \
+            and hit[3][0].device == lora_A.device:
+        return hit[3]
+    packed = ops.pack_lora(lora_A, lora_B, scaling)
+    _PACK_CACHE[key] = (lora_A._version, lora_B._version, scaling, packed)
+    return packed
+
+
 class _FusedLoRALinearFn(torch.autograd.Function):
     """y = x W^T + b + s (x A^T) B^T through `al_lora_linear_forward` (the rank-r product rides in the frozen GEMM's
     TMEM accumulator). Backward keeps W frozen and is native too (`al_lora_linear_backward`): dx = dy W + s (dy B) A in
@@ -72,7 +87,7 @@ class _FusedLoRALinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, lora_A, lora_B, scaling):
         from .. import ops
         y, (a_pad, b_pad, t) = ops.lora_linear(x.contiguous(), weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype,
-                                              return_saved=True)
+                                              return_saved=True, packed=_packed_operands(lora_A, lora_B, scaling))
         ctx.save_for_backward(x, weight, a_pad, b_pad, t)
         ctx.scaling = scaling
         ctx.rank = lora_A.shape[0]

@@ -195,20 +195,30 @@ def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optiona
     return out, mask_out, labels_out
 
 
+def pack_lora(lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float):
+    """The kernel's operands: A zero-padded to a multiple of 8 rows, bf16 [r_pad, in]; scaling * B, bf16 [out, r_pad]."""
+    r, in_dim = lora_a.shape
+    out_dim = lora_b.shape[0]
+    r_pad = (r + 7) // 8 * 8
+    a = torch.zeros(r_pad, in_dim, dtype=torch.bfloat16, device=lora_a.device)
+    a[:r] = lora_a.detach().to(torch.bfloat16)
+    b = torch.zeros(out_dim, r_pad, dtype=torch.bfloat16, device=lora_b.device)
+    b[:, :r] = (lora_b.detach().float() * scaling).to(torch.bfloat16)
+    return a, b
+
+
 def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: torch.Tensor,
-                lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16, return_saved: bool = False):
+                lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16, return_saved: bool = False,
+                packed=None):
     """Frozen linear + LoRA (L1): x [..., in] bf16, w [out, in] bf16, lora_a [r, in], lora_b [out, r] (any float dtype).
     out = x w^T + bias + scaling * (x a^T) b^T with the rank-r product accumulated inside the frozen GEMM.
-    return_saved=True also returns (a_pad, b_scaled_pad, t) for lora_linear_backward."""
+    `packed` = pack_lora(lora_a, lora_b, scaling) when the caller keeps it across calls (the parameters only change at
+    optimizer steps); return_saved=True also returns (a_pad, b_scaled_pad, t) for lora_linear_backward."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
     out_dim, in_dim = w.shape
-    r = lora_a.shape[0]
-    r_pad = (r + 7) // 8 * 8
-    a = torch.zeros(r_pad, in_dim, dtype=torch.bfloat16, device=x.device)
-    a[:r] = lora_a.detach().to(torch.bfloat16)
-    b = torch.zeros(out_dim, r_pad, dtype=torch.bfloat16, device=x.device)
-    b[:, :r] = (lora_b.detach().float() * scaling).to(torch.bfloat16)
+    a, b = packed if packed is not None else pack_lora(lora_a, lora_b, scaling)
+    r_pad = a.shape[0]
     x2 = x.reshape(-1, in_dim)
     rows = x2.shape[0]
     t_ws = torch.empty(rows, r_pad, dtype=torch.bfloat16, device=x.device)
