@@ -7,6 +7,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#ifndef AL_WAIT_HINT_NS
+#define AL_WAIT_HINT_NS 2000
+#endif
+
 namespace al {
 
 // ----------------------------------------------------------------------------- error plumbing (host)
@@ -68,11 +72,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the thread may sleep in hardware for up to `ns` before the instruction returns
+// false, instead of coming back to spin (issue slots and power the working warps of the SM would rather have).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (the launch then returns an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, AL_WAIT_HINT_NS)) {
     if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
       printf("al: mbarrier wait timed out (block %d,%d,%d thread %d bar %p parity %u)\n", blockIdx.x, blockIdx.y,
              blockIdx.z, threadIdx.x, bar, parity);
