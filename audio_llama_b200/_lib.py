@@ -51,6 +51,14 @@ SIGNATURES = {
     "al_lora_linear_forward": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "al_lora_linear_backward_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "al_lora_linear_backward": (i32, [vp, vp, i32, i32, i32, i32] + [vp] * 9),
+    "al_rmsnorm_forward": (i32, [vp, vp, vp, vp, i32, i32, f32, vp]),
+    "al_rmsnorm_backward": (i32, [vp, vp, vp, vp, vp, i32, i32, vp]),
+    "al_swiglu_forward": (i32, [vp, vp, vp, i64, vp]),
+    "al_swiglu_backward": (i32, [vp, vp, vp, vp, vp, i64, vp]),
+    "al_rope": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
+    "al_cross_entropy_inplace": (i32, [vp, vp, i32, i32, i64, f32, vp, vp]),
+    "al_linear_ce_workspace_bytes": (sz, [i32, i32]),
+    "al_linear_ce": (i32, [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp]),
     "al_splice": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp]),
     "al_splice_ragged": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i64, i64, vp, vp, vp, vp, vp]),
 }

@@ -1008,6 +1008,77 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
   return 0;
 }
 
+// ----------------------------------------------------------------------------- LLaMA-side row kernels (§8f-1 slice)
+int al_rmsnorm_forward(const void* x, const void* weight, void* y, float* rstd, int rows, int d, float eps, al_stream_t stream) {
+  AL_REQUIRE(x && weight && y && rows >= 0, "al_rmsnorm_forward: NULL argument");
+  int rc = launch_rmsnorm(x, weight, y, rstd, nullptr, nullptr, rows, d, eps, false, (cudaStream_t)stream);
+  if (rc == 0 && rows > 0) g_launches += 1;
+  return rc;
+}
+int al_rmsnorm_backward(const void* x, const void* weight, const float* rstd, const void* dy, void* dx, int rows, int d,
+                        al_stream_t stream) {
+  AL_REQUIRE(x && weight && rstd && dy && dx && rows >= 0, "al_rmsnorm_backward: NULL argument");
+  int rc = launch_rmsnorm(x, weight, nullptr, const_cast<float*>(rstd), dy, dx, rows, d, 0.f, true, (cudaStream_t)stream);
+  if (rc == 0 && rows > 0) g_launches += 1;
+  return rc;
+}
+int al_swiglu_forward(const void* gate, const void* up, void* h, long long n, al_stream_t stream) {
+  AL_REQUIRE(gate && up && h && n >= 0, "al_swiglu_forward: NULL argument");
+  int rc = launch_swiglu(gate, up, nullptr, h, nullptr, n, false, num_sms(), (cudaStream_t)stream);
+  if (rc == 0 && n > 0) g_launches += 1;
+  return rc;
+}
+int al_swiglu_backward(const void* gate, const void* up, const void* dh, void* dgate, void* dup, long long n, al_stream_t stream) {
+  AL_REQUIRE(gate && up && dh && dgate && dup && n >= 0, "al_swiglu_backward: NULL argument");
+  int rc = launch_swiglu(gate, up, dh, dgate, dup, n, true, num_sms(), (cudaStream_t)stream);
+  if (rc == 0 && n > 0) g_launches += 1;
+  return rc;
+}
+int al_rope(const void* x, const void* cos, const void* sin, void* out, int B, int S, int H, int head_dim, int cos_batch,
+            int backward, al_stream_t stream) {
+  AL_REQUIRE(x && cos && sin && out, "al_rope: NULL argument");
+  int rc = launch_rope(x, cos, sin, out, B, S, H, head_dim, cos_batch, backward, num_sms(), (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+int al_cross_entropy_inplace(void* logits, const long long* labels, int rows, int vocab, long long ld, float grad_scale,
+                             float* loss_sum, al_stream_t stream) {
+  AL_REQUIRE(logits && labels && loss_sum && rows >= 0 && vocab > 0, "al_cross_entropy_inplace: bad argument");
+  int rc = launch_ce_inplace(logits, labels, rows, vocab, ld, grad_scale, loss_sum, (cudaStream_t)stream);
+  if (rc == 0 && rows > 0) g_launches += 1;
+  return rc;
+}
+
+size_t al_linear_ce_workspace_bytes(int chunk_rows, int vocab) {
+  const size_t ldv = ((size_t)vocab + 7) / 8 * 8;
+  return (size_t)chunk_rows * ldv * 2 + 1024;
+}
+// lm_head + cross-entropy without materialising the [rows][vocab] logits: per chunk of rows, logits = h W^T (bf16),
+// the cross-entropy overwrites them with (softmax - onehot) * grad_scale, and dh = dlogits W follows at once.
+int al_linear_ce(const void* h, const void* W, const void* W_T, const long long* labels, int rows, int d, int vocab,
+                 float grad_scale, int chunk_rows, void* workspace, float* loss_sum, void* dh, al_stream_t stream) {
+  AL_REQUIRE(h && W && labels && workspace && loss_sum, "al_linear_ce: NULL argument");
+  AL_REQUIRE(dh == nullptr || W_T != nullptr, "al_linear_ce: dh needs W_T ([d][round8(vocab)], lm_head transposed)");
+  AL_REQUIRE(rows >= 0 && d % 8 == 0 && vocab > 0 && chunk_rows > 0, "al_linear_ce: bad shape rows=%d d=%d vocab=%d", rows, d, vocab);
+  AL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "al_linear_ce: workspace must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long ldv = ((long long)vocab + 7) / 8 * 8;
+  AL_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(float), st));
+  int rc;
+  for (int r0 = 0; r0 < rows; r0 += chunk_rows) {
+    const int m = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+    const uint8_t* hc = (const uint8_t*)h + (size_t)r0 * d * 2;
+    if ((rc = gemm_plain(hc, d, m, W, d, vocab, d, nullptr, workspace, ldv, 0, nullptr, 0, 0, st))) return rc;
+    if ((rc = launch_ce_inplace(workspace, labels + r0, m, vocab, ldv, grad_scale, loss_sum, st))) return rc;
+    g_launches += 1;
+    if (dh != nullptr) {
+      uint8_t* dc = (uint8_t*)dh + (size_t)r0 * d * 2;
+      if ((rc = gemm_plain(workspace, ldv, m, W_T, ldv, d, vocab, nullptr, dc, d, 0, nullptr, 0, 0, st))) return rc;
+    }
+  }
+  return 0;
+}
+
 // ----------------------------------------------------------------------------- splice
 int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
               const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,

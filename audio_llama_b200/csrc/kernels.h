@@ -101,6 +101,16 @@ int launch_mel(const float* wave, const int* n_samples, int B, long long wave_st
                float* out, unsigned int* clip_max_bits, cudaStream_t stream);
 int launch_mel_finalize(float* out, const unsigned int* clip_max_bits, int B, int n_mels, cudaStream_t stream);
 
+// ------------------------------------------------------------------ LLaMA-side row kernels (llama_rows.cu)
+int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const void* dy, void* dx, int rows, int d, float eps,
+                   bool backward, cudaStream_t st);
+int launch_swiglu(const void* gate, const void* up, const void* dh, void* out0, void* out1, long long n, bool backward,
+                  int num_sms, cudaStream_t st);
+int launch_rope(const void* x, const void* cs, const void* sn, void* out, int B, int S, int H, int hd, int cos_batch,
+                int backward, int num_sms, cudaStream_t st);
+int launch_ce_inplace(void* logits, const long long* labels, int rows, int vocab, long long ld, float grad_scale,
+                      float* loss_sum, cudaStream_t st);
+
 // ------------------------------------------------------------------ ingest (ingest.cu)
 struct ResampleTable {
   const float* weights;   // [new_f][max_taps] non-zero run of each phase's filter (zero padded)

@@ -1,0 +1,202 @@
+"""LLaMA-side native ops (first slice): RMSNorm, SwiGLU, rotary embedding and the lm_head +
+cross-entropy tail of the HF LlamaForCausalLM that the reference drives (/root/reference/src/models/allm.py:99-104),
+as hand-written sm_100a kernels with their backward, wired in through torch.autograd.Function.
+
+`enable(audio_llm)` patches the LLaMA inside an AudioLLM in place (opt-in; the module API stays the reference's):
+  * every LlamaRMSNorm.forward          -> al_rmsnorm_forward / _backward         (weight frozen: dx only)
+  * every LlamaMLP.forward              -> gate / up / down linears unchanged (fused LoRA when enabled), the
+                                           `act_fn(gate) * up` between them -> al_swiglu_forward / _backward
+  * modeling_llama.apply_rotary_pos_emb -> al_rope (forward and transposed rotation for the gradient)
+  * the loss (labels given)             -> al_linear_ce: lm_head + cross-entropy per chunk of rows, never forming the
+                                           [tokens, vocab] logits (HF upcasts them to fp32: 8 GB at the README batch);
+                                           `outputs.logits` is None in that mode.
+Attention itself stays HF's (SDPA / cuDNN flash): library code, like the GEMMs HF calls.
+There is no CPU fallback: inputs that are not bf16 CUDA tensors go to the module's original forward.
+"""
+from __future__ import annotations
+
+import types
+
+import torch
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+def _ok(t: torch.Tensor) -> bool:
+    return t.is_cuda and t.dtype == torch.bfloat16
+
+
+# ----------------------------------------------------------------------------- RMSNorm
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        xc = x.contiguous()
+        d = xc.shape[-1]
+        rows = xc.numel() // d
+        y = torch.empty_like(xc)
+        rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        check(lib().al_rmsnorm_forward(ptr(xc), ptr(weight), ptr(y), ptr(rstd), rows, d, float(eps), stream_ptr()),
+              "al_rmsnorm_forward")
+        ctx.save_for_backward(xc, weight, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, weight, rstd = ctx.saved_tensors
+        d = xc.shape[-1]
+        dyc = dy.contiguous()
+        dx = torch.empty_like(xc)
+        check(lib().al_rmsnorm_backward(ptr(xc), ptr(weight), ptr(rstd), ptr(dyc), ptr(dx), xc.numel() // d, d, stream_ptr()),
+              "al_rmsnorm_backward")
+        return dx, None, None
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    return _RMSNormFn.apply(x, weight, eps)
+
+
+# ----------------------------------------------------------------------------- SwiGLU
+class _SwiGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        g, u = gate.contiguous(), up.contiguous()
+        h = torch.empty_like(g)
+        check(lib().al_swiglu_forward(ptr(g), ptr(u), ptr(h), g.numel(), stream_ptr()), "al_swiglu_forward")
+        ctx.save_for_backward(g, u)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        g, u = ctx.saved_tensors
+        dhc = dh.contiguous()
+        dg, du = torch.empty_like(g), torch.empty_like(u)
+        check(lib().al_swiglu_backward(ptr(g), ptr(u), ptr(dhc), ptr(dg), ptr(du), g.numel(), stream_ptr()), "al_swiglu_backward")
+        return dg, du
+
+
+def swiglu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    return _SwiGLUFn.apply(gate, up)
+
+
+# ----------------------------------------------------------------------------- rotary embedding
+class _RoPEFn(torch.autograd.Function):
+    """x [B, S, H, hd] contiguous; cos / sin [Bc, S, hd] contiguous (Bc = 1 or B)."""
+
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        B, S, H, hd = x.shape
+        out = torch.empty_like(x)
+        check(lib().al_rope(ptr(x), ptr(cos), ptr(sin), ptr(out), B, S, H, hd, cos.shape[0], 0, stream_ptr()), "al_rope")
+        ctx.save_for_backward(cos, sin)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        cos, sin = ctx.saved_tensors
+        dyc = dy.contiguous()
+        B, S, H, hd = dyc.shape
+        dx = torch.empty_like(dyc)
+        check(lib().al_rope(ptr(dyc), ptr(cos), ptr(sin), ptr(dx), B, S, H, hd, cos.shape[0], 1, stream_ptr()), "al_rope")
+        return dx, None, None
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, unsqueeze_dim=1):
+    """Drop-in for transformers.models.llama.modeling_llama.apply_rotary_pos_emb: q, k [B, H, S, hd] (views of the
+    [B, S, H, hd] projection outputs), cos / sin [B or 1, S, hd]."""
+    if not (_ok(q) and _ok(k) and _ok(cos) and unsqueeze_dim == 1 and q.shape[-1] % 16 == 0):
+        return _ORIG["rope"](q, k, cos, sin, unsqueeze_dim=unsqueeze_dim)
+    cc, ss = cos.contiguous(), sin.contiguous()
+    qo = _RoPEFn.apply(q.transpose(1, 2).contiguous(), cc, ss).transpose(1, 2)
+    ko = _RoPEFn.apply(k.transpose(1, 2).contiguous(), cc, ss).transpose(1, 2)
+    return qo, ko
+
+
+# ----------------------------------------------------------------------------- lm_head + cross-entropy
+_WT_PAD = {}   # frozen lm_head (data_ptr, shape) -> its transpose, row pitch padded to a multiple of 8
+
+
+def _lm_head_t(weight: torch.Tensor) -> torch.Tensor:
+    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
+    wt = _WT_PAD.get(key)
+    if wt is None:
+        V, d = weight.shape
+        ldv = (V + 7) // 8 * 8
+        wt = torch.zeros(d, ldv, dtype=weight.dtype, device=weight.device)
+        wt[:, :V] = weight.detach().t()
+        _WT_PAD[key] = wt
+    return wt
+
+
+class _LinearCEFn(torch.autograd.Function):
+    """loss = mean over labels != -100 of cross_entropy(h W^T, labels); W frozen. The gradient of h is produced in the
+    forward (chunk by chunk, right after the chunk's logits) and only scaled in the backward."""
+
+    @staticmethod
+    def forward(ctx, h, weight, labels, chunk_rows):
+        hc = h.contiguous()
+        rows, d = hc.shape
+        V = weight.shape[0]
+        lab = labels.contiguous()
+        n_valid = (lab != -100).sum().clamp(min=1).to(torch.float32)         # stays on the device: no host sync
+        nbytes = int(lib().al_linear_ce_workspace_bytes(chunk_rows, V))
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=hc.device)
+        off = (-ws.data_ptr()) % 1024
+        loss_sum = torch.empty(1, dtype=torch.float32, device=hc.device)
+        need_dh = ctx.needs_input_grad[0]
+        dh = torch.empty_like(hc) if need_dh else None
+        check(lib().al_linear_ce(ptr(hc), ptr(weight), ptr(_lm_head_t(weight)) if need_dh else None, ptr(lab), rows, d, V,
+                                 1.0, int(chunk_rows), ptr(ws[off:]), ptr(loss_sum), ptr(dh), stream_ptr()), "al_linear_ce")
+        if need_dh:
+            ctx.save_for_backward(dh, n_valid)
+        return (loss_sum / n_valid).squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        dh, n_valid = ctx.saved_tensors
+        return dh * (g / n_valid).to(dh.dtype), None, None, None
+
+
+def linear_cross_entropy(h: torch.Tensor, weight: torch.Tensor, shifted_labels: torch.Tensor, chunk_rows: int = 2048):
+    """h [tokens, d] bf16, weight [vocab, d] bf16 (frozen lm_head), shifted_labels [tokens] int64 (-100 = ignore)."""
+    return _LinearCEFn.apply(h, weight, shifted_labels, chunk_rows)
+
+
+def causal_lm_loss(h: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, chunk_rows: int = 2048):
+    """The loss of LlamaForCausalLM.forward (HF loss_utils.ForCausalLMLoss): position t predicts labels[t + 1]."""
+    shifted = torch.nn.functional.pad(labels, (0, 1), value=-100)[..., 1:]
+    return linear_cross_entropy(h.reshape(-1, h.shape[-1]), weight, shifted.reshape(-1), chunk_rows)
+
+
+# ----------------------------------------------------------------------------- wiring
+_ORIG = {}
+
+
+def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True):
+    """Patch the HF LLaMA inside `audio_llm` (an audio_llama_b200.models.allm.AudioLLM) to the native ops."""
+    from transformers.models.llama import modeling_llama as ML
+    llama = audio_llm.llama.model
+    for mod in llama.modules():
+        if rmsnorm_ and isinstance(mod, ML.LlamaRMSNorm):
+            def norm_fwd(m, hidden_states, _orig=type(mod).forward):
+                if _ok(hidden_states) and m.weight.dtype == torch.bfloat16 and hidden_states.shape[-1] % 8 == 0:
+                    return rmsnorm(hidden_states, m.weight, m.variance_epsilon)
+                return _orig(m, hidden_states)
+            mod.forward = types.MethodType(norm_fwd, mod)
+        if mlp and isinstance(mod, ML.LlamaMLP):
+            def mlp_fwd(m, x, _orig=type(mod).forward):
+                if _ok(x) and m.config.hidden_act == "silu":
+                    return m.down_proj(swiglu(m.gate_proj(x), m.up_proj(x)))
+                return _orig(m, x)
+            mod.forward = types.MethodType(mlp_fwd, mod)
+    if rope and "rope" not in _ORIG:
+        _ORIG["rope"] = ML.apply_rotary_pos_emb
+        ML.apply_rotary_pos_emb = apply_rotary_pos_emb
+    audio_llm.native_ce = bool(fused_ce)
+    audio_llm.native_llama = True
+    return audio_llm
+
+
+def disable_rope_patch():
+    from transformers.models.llama import modeling_llama as ML
+    if "rope" in _ORIG:
+        ML.apply_rotary_pos_emb = _ORIG.pop("rope")

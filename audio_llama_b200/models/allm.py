@@ -66,6 +66,12 @@ class AudioLLM(nn.Module):
         self.fused_lora = True
         return self
 
+    def enable_native_llama_ops(self, **which):
+        """RMSNorm / SwiGLU / rotary embedding / lm_head + cross-entropy of the HF LLaMA on hand-written kernels
+        (audio_llama_b200.llama_native). Opt-in: the reference's module API is unchanged."""
+        from .. import llama_native
+        return llama_native.enable(self, **which)
+
     # ------------------------------------------------------------------ forward (allm.py:47-106)
     def forward(self, input_ids=None, attention_mask=None, audio_features=None, labels=None, **kwargs):
         device = input_ids.device
@@ -80,6 +86,14 @@ class AudioLLM(nn.Module):
             combined_attention_mask = attention_mask
             adjusted_labels = labels
 
+        if getattr(self, "native_ce", False) and adjusted_labels is not None and combined_embeddings.dtype == torch.bfloat16:
+            # lm_head + cross-entropy fused per chunk of rows (no [tokens, vocab] logits; `logits` is None in this mode)
+            from transformers.modeling_outputs import CausalLMOutputWithPast
+            from .. import llama_native
+            hidden = self.llama.model.model(inputs_embeds=combined_embeddings, attention_mask=combined_attention_mask,
+                                            **kwargs).last_hidden_state
+            loss = llama_native.causal_lm_loss(hidden, self.llama.model.lm_head.weight, adjusted_labels)
+            return CausalLMOutputWithPast(loss=loss, logits=None)
         return self.llama.model(inputs_embeds=combined_embeddings, attention_mask=combined_attention_mask,
                                 labels=adjusted_labels, **kwargs)
 

@@ -176,6 +176,32 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
                             const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace,
                             void* dx, float* dA, float* dB_raw, al_stream_t stream);
 
+/* ---- LLaMA-side row kernels (first slice) -------------------------------------------------
+ * The elementwise / row work of the HF LlamaForCausalLM the reference drives (/root/reference/src/models/allm.py:99-104
+ * -> HF models/llama/modeling_llama.py), bf16 in / out, fp32 arithmetic, forward and backward:
+ *   al_rmsnorm_*      LlamaRMSNorm.forward: y = weight * bf16(x * rsqrt(mean(x^2) + eps)); rstd [rows] f32 saved for the
+ *                     backward (weight frozen: dx only)
+ *   al_swiglu_*       act_fn(gate_proj(x)) * up_proj(x) of LlamaMLP.forward (SiLU)
+ *   al_rope           apply_rotary_pos_emb on x [B][S][H][head_dim] with cos / sin [cos_batch][S][head_dim]
+ *                     (cos_batch 1 or B); backward = 1 applies the transposed rotation to a gradient
+ *   al_cross_entropy_inplace   rows of logits [rows][ld] bf16 -> loss_sum += lse - logit[label] (label -100 ignored),
+ *                     the row is overwritten with (softmax - onehot) * grad_scale
+ *   al_linear_ce      lm_head + the loss of LlamaForCausalLM.forward without materialising [rows][vocab] logits: per
+ *                     chunk_rows rows, logits = h W^T, cross-entropy in place, dh = dlogits W (W_T = W transposed,
+ *                     [d][round8(vocab)] bf16). labels are the SHIFTED labels (labels[t + 1], -100 at the end). */
+int al_rmsnorm_forward(const void* x, const void* weight, void* y, float* rstd, int rows, int d, float eps, al_stream_t stream);
+int al_rmsnorm_backward(const void* x, const void* weight, const float* rstd, const void* dy, void* dx, int rows, int d,
+                        al_stream_t stream);
+int al_swiglu_forward(const void* gate, const void* up, void* h, long long n, al_stream_t stream);
+int al_swiglu_backward(const void* gate, const void* up, const void* dh, void* dgate, void* dup, long long n, al_stream_t stream);
+int al_rope(const void* x, const void* cos, const void* sin, void* out, int B, int S, int H, int head_dim, int cos_batch,
+            int backward, al_stream_t stream);
+int al_cross_entropy_inplace(void* logits, const long long* labels, int rows, int vocab, long long ld, float grad_scale,
+                             float* loss_sum, al_stream_t stream);
+size_t al_linear_ce_workspace_bytes(int chunk_rows, int vocab);
+int al_linear_ce(const void* h, const void* W, const void* W_T, const long long* labels, int rows, int d, int vocab,
+                 float grad_scale, int chunk_rows, void* workspace, float* loss_sum, void* dh, al_stream_t stream);
+
 /* ---- S1 / S2: splice ------------------------------------------------------------------------------
  * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask
  * (allm.py:176-196) and the label extension (allm.py:81-89). Row map per sample (bit-exact contract):

@@ -1,0 +1,139 @@
+"""GPU parity of the LLaMA-side native ops (first slice) against the HF modules they replace
+(transformers LlamaRMSNorm / LlamaMLP's act*up / apply_rotary_pos_emb / ForCausalLMLoss), forward and backward.
+bf16 kernels vs an fp32 evaluation of the same formulas: rel-L2 <= 1e-2 (measured ~3e-3)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from audio_llama_b200 import llama_native as LN
+from oracle import encoder as O
+
+
+def rel(a, b):
+    return O.rel_l2(a.float().cpu(), b.float().cpu())
+
+
+@pytest.mark.parametrize("rows,d", [(517, 3072), (64, 2048), (33, 256), (5, 8192)])
+def test_rmsnorm(rows, d):
+    from transformers.models.llama.modeling_llama import LlamaRMSNorm
+    g = torch.Generator().manual_seed(d)
+    x = (torch.randn(rows, d, generator=g) * 2).bfloat16().cuda()
+    w = (1 + 0.1 * torch.randn(d, generator=g)).bfloat16().cuda()
+    dy = torch.randn(rows, d, generator=g).bfloat16().cuda()
+    m = LlamaRMSNorm(d, eps=1e-5).cuda().bfloat16()
+    with torch.no_grad():
+        m.weight.copy_(w)
+    y, yh = LN.rmsnorm(x, w, 1e-5), m(x)
+    # same rounding points as HF; only the summation order of mean(x^2) differs, which moves a few values by one bf16 ulp
+    assert (y != yh).float().mean() <= 0.02 and rel(y, yh) <= 2e-3
+    xr = x.float().requires_grad_(True)
+    yr = w.float() * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5))
+    yr.backward(dy.float())
+    xn = x.clone().requires_grad_(True)
+    LN.rmsnorm(xn.view(1, rows, d), w, 1e-5).backward(dy.view(1, rows, d))
+    assert rel(xn.grad, xr.grad) <= 1e-2
+
+
+def test_swiglu():
+    g = torch.Generator().manual_seed(1)
+    a = (torch.randn(300, 8192, generator=g) * 2).bfloat16().cuda()
+    b = torch.randn(300, 8192, generator=g).bfloat16().cuda()
+    dh = torch.randn(300, 8192, generator=g).bfloat16().cuda()
+    ar, br = a.float().requires_grad_(True), b.float().requires_grad_(True)
+    hr = torch.nn.functional.silu(ar) * br
+    hr.backward(dh.float())
+    an, bn = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    h = LN.swiglu(an, bn)
+    h.backward(dh)
+    assert rel(h, hr) <= 5e-3 and rel(an.grad, ar.grad) <= 1e-2 and rel(bn.grad, br.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,hd,cb", [(2, 300, 24, 8, 128, 1), (3, 65, 32, 8, 64, 3)])
+def test_rope(B, S, Hq, Hkv, hd, cb):
+    from transformers.models.llama import modeling_llama as ML
+    orig = LN._ORIG.get("rope", ML.apply_rotary_pos_emb)
+    g = torch.Generator().manual_seed(S)
+    q = torch.randn(B, S, Hq, hd, generator=g).bfloat16().cuda().transpose(1, 2)        # [B, H, S, hd] view, as in HF
+    k = torch.randn(B, S, Hkv, hd, generator=g).bfloat16().cuda().transpose(1, 2)
+    ang = torch.rand(cb, S, hd // 2, generator=g) * 6.28
+    cos = torch.cat([ang.cos(), ang.cos()], -1).bfloat16().cuda()
+    sin = torch.cat([ang.sin(), ang.sin()], -1).bfloat16().cuda()
+    dq = torch.randn(B, Hq, S, hd, generator=g).bfloat16().cuda()
+    qr, kr = q.float().requires_grad_(True), k.float().requires_grad_(True)
+    qe, ke = orig(qr, kr, cos.float(), sin.float())
+    (qe * dq.float()).sum().backward()
+    qn, kn = q.clone().requires_grad_(True), k.clone().requires_grad_(True)
+    qo, ko = LN.apply_rotary_pos_emb(qn, kn, cos, sin)
+    assert qo.shape == qe.shape and ko.shape == ke.shape
+    (qo.float() * dq.float()).sum().backward()
+    assert rel(qo, qe) <= 5e-3 and rel(ko, ke) <= 5e-3
+    assert rel(qn.grad, qr.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("rows,d,V,chunk", [(300, 256, 5003, 128), (64, 512, 128258, 64), (7, 64, 40, 16)])
+def test_linear_cross_entropy(rows, d, V, chunk):
+    g = torch.Generator().manual_seed(V)
+    h = torch.randn(rows, d, generator=g).bfloat16().cuda()
+    W = (torch.randn(V, d, generator=g) * 0.05).bfloat16().cuda()
+    labels = torch.randint(0, V, (rows,), generator=g)
+    labels[::5] = -100
+    labels = labels.cuda()
+    hr = h.float().requires_grad_(True)
+    logits = (hr @ W.float().t()).bfloat16().float()              # HF's lm_head output is bf16 before the fp32 upcast
+    ref = torch.nn.functional.cross_entropy(hr @ W.float().t(), labels, ignore_index=-100)
+    ref.backward()
+    hn = h.clone().requires_grad_(True)
+    loss = LN.linear_cross_entropy(hn, W, labels, chunk_rows=chunk)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 3e-3 * max(1.0, abs(float(ref)))
+    assert rel(hn.grad, hr.grad) <= 2e-2
+    # every label ignored: loss 0, gradient 0, no NaN
+    hz = h.clone().requires_grad_(True)
+    lz = LN.linear_cross_entropy(hz, W, torch.full_like(labels, -100), chunk_rows=chunk)
+    lz.backward()
+    assert float(lz) == 0.0 and float(hz.grad.abs().max()) == 0.0
+    del logits
+
+
+def test_native_llama_in_audio_llm_matches_hf():
+    """AudioLLM.enable_native_llama_ops(): loss and LoRA gradients of a bf16 LLaMA equal the stock HF path's."""
+    from unittest.mock import Mock, patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as B
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200 import synth
+
+    def fake(lp, wp):
+        torch.manual_seed(0)
+        lc = LlamaConfig(vocab_size=322, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2)
+        ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+        return (B.FrozenModelWrapper(LlamaForCausalLM(lc).to(torch.bfloat16)),
+                B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=2)))
+
+    def run(native):
+        with patch.object(B, "load_base_models", fake):
+            m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+        g = torch.Generator().manual_seed(3)
+        for l in m.lora_layers.values():
+            with torch.no_grad():
+                l.lora_A.copy_(torch.randn(l.lora_A.shape, generator=g) * 0.05)
+                l.lora_B.copy_(torch.randn(l.lora_B.shape, generator=g) * 0.05)
+        if native:
+            m.enable_native_llama_ops()
+        ids, mask, labels = (t.cuda() for t in synth.synth_text(2, 24, 320))
+        out = m(input_ids=ids, attention_mask=mask, labels=labels)
+        out.loss.backward()
+        l0 = m.lora_layers["model.layers.1.mlp.down_proj"]
+        l1 = m.lora_layers["model.layers.0.self_attn.q_proj"]
+        return float(out.loss), l0.lora_A.grad.float().cpu(), l1.lora_B.grad.float().cpu()
+
+    try:
+        a, b = run(False), run(True)
+    finally:
+        LN.disable_rope_patch()
+    assert abs(a[0] - b[0]) <= 2e-2 * abs(a[0])
+    assert O.rel_l2(b[1], a[1]) <= 1e-1 and O.rel_l2(b[2], a[2]) <= 1e-1

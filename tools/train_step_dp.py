@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--rank_lora", type=int, default=64)
     ap.add_argument("--fused-lora", action="store_true", help="AudioLLM.enable_fused_lora(): fused frozen+LoRA GEMM")
+    ap.add_argument("--native-llama", action="store_true", help="AudioLLM.enable_native_llama_ops(): RMSNorm / SwiGLU / RoPE / lm_head+CE kernels")
+    ap.add_argument("--profile", action="store_true", help="torch.profiler over the last step: GPU time by kernel (rank 0)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -65,6 +67,8 @@ def main():
     model = model.to(dev)
     if args.fused_lora:
         model.enable_fused_lora()
+    if args.native_llama:
+        model.enable_native_llama_ops()
     model.projector.to(torch.float32)
     for l in model.lora_layers.values():
         torch.nn.init.normal_(l.lora_A, std=0.01)
@@ -77,7 +81,11 @@ def main():
     fe = LogMelExtractor(ecfg.n_mels, device=dev)
     clips = [synth.synth_clip(rank * args.batch + i) for i in range(args.batch)]
     t_step, t_ar = [], []
+    prof = None
     for step in range(args.steps):
+        if args.profile and rank == 0 and step == args.steps - 1:
+            prof = torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA])
+            prof.__enter__()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -97,8 +105,15 @@ def main():
         t3 = time.perf_counter()
         t_step.append(t3 - t0)
         t_ar.append(t2 - t1)
+    if prof is not None:
+        prof.__exit__(None, None, None)
+        rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+        tot = sum(e.device_time_total for e in rows)
+        print(f"# GPU time of the profiled step: {tot / 1e3:.1f} ms", file=sys.stderr)
+        for e in rows[:40]:
+            print(f"# {e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}% x{e.count:<5d} {e.key[:110]}", file=sys.stderr)
     if rank == 0:
-        print(json.dumps({"world": world, "llama": args.llama, "encoder": args.encoder, "batch_per_gpu": args.batch, "fused_lora": bool(args.fused_lora),
+        print(json.dumps({"world": world, "llama": args.llama, "encoder": args.encoder, "batch_per_gpu": args.batch, "fused_lora": bool(args.fused_lora), "native_llama": bool(args.native_llama),
                           "trainable_params": bucket.numel, "bucket_mb": bucket.numel * 4 / 1e6,
                           "step_s": t_step, "allreduce_s": t_ar, "loss": float(out.loss.detach()),
                           "allreduce_bus_gbs": (2 * (world - 1) / world * bucket.numel * 4 / 1e9 / min(t_ar[1:] or t_ar)) if world > 1 else None}))
