@@ -7,6 +7,8 @@ as hand-written sm_100a kernels with their backward, wired in through torch.auto
   * every LlamaMLP.forward              -> gate / up / down linears unchanged (fused LoRA when enabled), the
                                            `act_fn(gate) * up` between them -> al_swiglu_forward / _backward
   * modeling_llama.apply_rotary_pos_emb -> al_rope (forward and transposed rotation for the gradient)
+  * right-padded attention masks        -> dropped (causal attention already hides the padding from every real token;
+                                           HF then takes SDPA's is_causal path instead of a dense additive bias)
   * the loss (labels given)             -> al_linear_ce: lm_head + cross-entropy per chunk of rows, never forming the
                                            [tokens, vocab] logits (HF upcasts them to fp32: 8 GB at the README batch);
                                            `outputs.logits` is None in that mode.
@@ -167,11 +169,23 @@ def causal_lm_loss(h: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, 
     return linear_cross_entropy(h.reshape(-1, h.shape[-1]), weight, shifted.reshape(-1), chunk_rows)
 
 
+def causal_only_mask(attention_mask):
+    """None when `attention_mask` only right-pads (ones then zeros in every row): under causal attention the padded keys
+    lie after every real query, so the real positions see exactly the same keys with or without the explicit mask, and
+    HF's SDPA path can then run `is_causal=True` (half the score tiles) instead of a dense [B, 1, S, S] bias. Rows that
+    are padded on the left or in the middle keep their mask. One tiny device->host read."""
+    if attention_mask is None:
+        return None
+    m = attention_mask
+    right_padded = bool((m[:, 1:] <= m[:, :-1]).all()) if m.shape[1] > 1 else True
+    return None if right_padded else attention_mask
+
+
 # ----------------------------------------------------------------------------- wiring
 _ORIG = {}
 
 
-def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True):
+def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True):
     """Patch the HF LLaMA inside `audio_llm` (an audio_llama_b200.models.allm.AudioLLM) to the native ops."""
     from transformers.models.llama import modeling_llama as ML
     llama = audio_llm.llama.model
@@ -192,6 +206,7 @@ def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True):
         _ORIG["rope"] = ML.apply_rotary_pos_emb
         ML.apply_rotary_pos_emb = apply_rotary_pos_emb
     audio_llm.native_ce = bool(fused_ce)
+    audio_llm.native_causal_only = bool(causal_only)
     audio_llm.native_llama = True
     return audio_llm
 

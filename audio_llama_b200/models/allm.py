@@ -86,10 +86,14 @@ class AudioLLM(nn.Module):
             combined_attention_mask = attention_mask
             adjusted_labels = labels
 
+        if getattr(self, "native_causal_only", False):
+            from .. import llama_native
+            combined_attention_mask = llama_native.causal_only_mask(combined_attention_mask)
         if getattr(self, "native_ce", False) and adjusted_labels is not None and combined_embeddings.dtype == torch.bfloat16:
             # lm_head + cross-entropy fused per chunk of rows (no [tokens, vocab] logits; `logits` is None in this mode)
             from transformers.modeling_outputs import CausalLMOutputWithPast
             from .. import llama_native
+            kwargs.setdefault("use_cache", False)      # a loss-only forward: no KV cache (HF's default builds and cats one)
             hidden = self.llama.model.model(inputs_embeds=combined_embeddings, attention_mask=combined_attention_mask,
                                             **kwargs).last_hidden_state
             loss = llama_native.causal_lm_loss(hidden, self.llama.model.lm_head.weight, adjusted_labels)

@@ -229,3 +229,14 @@ class _RefShapedProjector(nn.Module):
         super().__init__()
         h = (i + o) // 2
         self.layers = nn.Sequential(nn.Linear(i, h), nn.GELU(), nn.Linear(h, o), nn.LayerNorm(o))
+
+
+def test_causal_only_mask_rule():
+    """llama_native.causal_only_mask: only purely right-padded masks may be dropped in favour of causal attention."""
+    from audio_llama_b200.llama_native import causal_only_mask
+    right = torch.tensor([[1., 1., 1., 0., 0.], [1., 1., 1., 1., 1.]])
+    left = torch.tensor([[0., 1., 1., 1., 1.], [1., 1., 1., 1., 1.]])
+    hole = torch.tensor([[1., 0., 1., 1., 0.]])
+    assert causal_only_mask(right) is None and causal_only_mask(None) is None
+    assert causal_only_mask(left) is left and causal_only_mask(hole) is hole
+    assert causal_only_mask(torch.ones(3, 1)) is None
