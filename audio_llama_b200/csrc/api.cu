@@ -842,6 +842,41 @@ static int gemm_plain(const void* A, long long lda, int M, const void* W, long l
   return rc;
 }
 
+// out[M][N] (fp32) += A_src^T W_src with A_src [K][lda] (M valid columns) and W_src [K][ldw] (N valid columns), both
+// row-major over the contraction index (weight gradients: the contraction runs over the token rows). The operands are
+// staged MN-major (EPI_TN), so nothing is transposed in memory; split-K with TMA reduce-add into the zeroed output.
+static int gemm_tn(const void* A_src, long long lda, int M, const void* W_src, long long ldw, int N, int K, float* out,
+                   long long ldo, int want_items, cudaStream_t st) {
+  CUtensorMap ta, tb, to;
+  int rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)M, (uint64_t)K};
+    const uint64_t str[2] = {2, (uint64_t)lda * 2};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap(&ta, A_src, 2, 2, dims, str, box, true))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)K};
+    const uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap(&tb, W_src, 2, 2, dims, str, box, true))) return rc;
+  }
+  const int flags = EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD;
+  if ((rc = tmap_rows3d(&to, out, 4, N, M, 1, ldo, (uint64_t)M * ldo, gemm_out_box_cols(flags), 128))) return rc;
+  GemmParams p{};
+  p.m_per_batch = M; p.batch = 1; p.N = N; p.K = K;
+  const int out_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  const int num_kb = (K + 63) / 64;
+  int ks = (want_items + out_tiles - 1) / out_tiles;
+  if (ks > num_kb) ks = num_kb;
+  if (ks < 1) ks = 1;
+  const int per = (num_kb + ks - 1) / ks;
+  p.k_splits = (num_kb + per - 1) / per;
+  rc = launch_gemm(ta, tb, to, p, flags, num_sms(), st);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
 size_t al_projector_backward_workspace_bytes(int rows, int d_in, int hidden, int d_out) {
   const size_t rp = (size_t)(rows + 7) / 8 * 8;
   size_t b = 0;
@@ -869,12 +904,12 @@ int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_o
   uint8_t* w = (uint8_t*)workspace;
   auto take = [&](size_t n) { void* p = w; w += (n + 1023) / 1024 * 1024; return p; };
   void* dy = take((size_t)rows * d_out * 2);
-  void* dyT = take((size_t)rp * d_out * 2);
-  void* hT = take((size_t)rp * hidden * 2);
+  (void)take((size_t)rp * d_out * 2);   // (formerly dy^T / h^T: the weight-gradient GEMMs stage their operands MN-major now;
+  (void)take((size_t)rp * hidden * 2);  //  the workspace layout is kept so existing callers' sizes stay valid)
   void* W2T = take((size_t)hidden * d_out * 2);
   void* dh = take((size_t)rows * hidden * 2);
   void* da = take((size_t)rows * hidden * 2);
-  void* xT = take((size_t)rp * d_in * 2);
+  (void)take((size_t)rp * d_in * 2);
   AL_CHECK_CUDA(cudaMemsetAsync(dW1, 0, (size_t)hidden * d_in * 4, st));
   AL_CHECK_CUDA(cudaMemsetAsync(db1, 0, (size_t)hidden * 4, st));
   AL_CHECK_CUDA(cudaMemsetAsync(dW2, 0, (size_t)d_out * hidden * 4, st));
@@ -885,11 +920,8 @@ int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_o
 #define STEP(expr) do { rc = (expr); if (rc) return rc; g_launches += 1; } while (0)
   // 1. LayerNorm backward: dy (bf16), dgamma, dbeta, db2 = colsum(dy)
   STEP(launch_layernorm_bwd(y_saved, dout, gamma, dy, dgamma, dbeta, db2, rows, d_out, 1e-5f, st));
-  // 2. dW2 = dy^T h : both operands transposed to K-major, split-K reduce-add
-  STEP(launch_transpose_bf16(dy, dyT, rows, d_out, rp, st));
-  STEP(launch_transpose_bf16(h_saved, hT, rows, hidden, rp, st));
-  if ((rc = gemm_plain(dyT, rp, d_out, hT, rp, hidden, rp, nullptr, dW2, hidden, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
-                       2 * num_sms(), st))) return rc;
+  // 2. dW2 = dy^T h : contraction over the rows, operands staged MN-major (no transposes), split-K reduce-add
+  if ((rc = gemm_tn(dy, d_out, d_out, h_saved, hidden, hidden, rows, dW2, hidden, 2 * num_sms(), st))) return rc;
   // 3. dh = dy W2
   STEP(launch_transpose_bf16(W2, W2T, d_out, hidden, d_out, st));
   if ((rc = gemm_plain(dy, d_out, rows, W2T, d_out, hidden, d_out, nullptr, dh, hidden, 0, nullptr, 0, 0, st))) return rc;
@@ -897,10 +929,7 @@ int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_o
   if ((rc = gemm_plain(x, d_in, rows, W1, d_in, hidden, d_in, b1, da, hidden, EPI_GELU_GRAD, dh, hidden, 0, st))) return rc;
   // 5. db1 = colsum(da); dW1 = da^T x
   STEP(launch_colsum_bf16(da, db1, rows, hidden, st));
-  STEP(launch_transpose_bf16(da, hT, rows, hidden, rp, st));
-  STEP(launch_transpose_bf16(x, xT, rows, d_in, rp, st));
-  if ((rc = gemm_plain(hT, rp, hidden, xT, rp, d_in, rp, nullptr, dW1, d_in, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
-                       2 * num_sms(), st))) return rc;
+  if ((rc = gemm_tn(da, hidden, hidden, x, d_in, d_in, rows, dW1, d_in, 2 * num_sms(), st))) return rc;
 #undef STEP
   return 0;
 }
@@ -940,10 +969,7 @@ size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim
   add((size_t)rank * out_dim * 2);   // (sB)^T
   add((size_t)in_dim * rank * 2);    // A^T
   add((size_t)rows * rank * 2);      // U = dy (sB)
-  add(rp * rank * 2);                // U^T
-  add(rp * rank * 2);                // T^T
-  add(rp * in_dim * 2);              // x^T
-  add(rp * out_dim * 2);             // dy^T
+  (void)rp;
   return b;
 }
 
@@ -962,16 +988,12 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
              "al_lora_linear_backward: bad shape rows=%d in=%d out=%d rank=%d", rows, in_dim, out_dim, rank);
   AL_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "al_lora_linear_backward: workspace must be 1024-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const int rp = (rows + 7) / 8 * 8;
   uint8_t* w = (uint8_t*)workspace;
   auto take = [&](size_t n) { void* p = w; w += (n + 1023) / 1024 * 1024; return p; };
   void* sBT = take((size_t)rank * out_dim * 2);
   void* AT = take((size_t)in_dim * rank * 2);
   void* U = take((size_t)rows * rank * 2);
-  void* UT = take((size_t)rp * rank * 2);
-  void* TT = take((size_t)rp * rank * 2);
-  void* xT = take((size_t)rp * in_dim * 2);
-  void* dyT = take((size_t)rp * out_dim * 2);
+
   AL_CHECK_CUDA(cudaMemsetAsync(dA, 0, (size_t)rank * in_dim * 4, st));
   AL_CHECK_CUDA(cudaMemsetAsync(dB_raw, 0, (size_t)out_dim * rank * 4, st));
   int rc;
@@ -994,16 +1016,10 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
     if (rc) return rc;
     g_launches += 1;
   }
-  // 3. dA = U^T x  (contraction over the rows: both operands transposed to K-major, split-K)
-  STEP(launch_transpose_bf16(U, UT, rows, rank, rp, st));
-  STEP(launch_transpose_bf16(x, xT, rows, in_dim, rp, st));
-  if ((rc = gemm_plain(UT, rp, rank, xT, rp, in_dim, rp, nullptr, dA, in_dim, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
-                       2 * num_sms(), st))) return rc;
+  // 3. dA = U^T x  (contraction over the rows: operands staged MN-major, nothing transposed; split-K reduce-add)
+  if ((rc = gemm_tn(U, rank, rank, x, in_dim, in_dim, rows, dA, in_dim, 2 * num_sms(), st))) return rc;
   // 4. dB_raw = dy^T T
-  STEP(launch_transpose_bf16(dy, dyT, rows, out_dim, rp, st));
-  STEP(launch_transpose_bf16(t_saved, TT, rows, rank, rp, st));
-  if ((rc = gemm_plain(dyT, rp, out_dim, TT, rp, rank, rp, nullptr, dB_raw, rank, EPI_OUT_F32 | EPI_REDUCE_ADD, nullptr, 0,
-                       2 * num_sms(), st))) return rc;
+  if ((rc = gemm_tn(dy, out_dim, out_dim, t_saved, rank, rank, rows, dB_raw, rank, 2 * num_sms(), st))) return rc;
 #undef STEP
   return 0;
 }

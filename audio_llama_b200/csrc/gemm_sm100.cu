@@ -56,12 +56,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
   constexpr bool RESID = (FLAGS & EPI_RESIDUAL) != 0;
   constexpr bool GELU_GRAD = (FLAGS & EPI_GELU_GRAD) != 0;
+  constexpr bool TN = (FLAGS & EPI_TN) != 0;     // operands row-major over the contraction: staged MN-major
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_ROWS = CTA2 ? 128 : 256;       // weight rows staged by this CTA
   constexpr int B_BYTES = B_ROWS * BK * 2;
   constexpr int CH = OUT_F32 ? 32 : 64;          // output columns per staging chunk (128 B per row)
   constexpr int NCHUNK = BN / CH;
-  constexpr uint32_t IDESC = umma_idesc_bf16(CTA2 ? 256 : 128, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(CTA2 ? 256 : 128, BN, TN ? 1 : 0, TN ? 1 : 0);
   constexpr int TILE_M = CTA2 ? 256 : 128;       // rows per scheduled tile
 
   extern __shared__ uint8_t smem_raw[];
@@ -136,7 +137,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int k0 = (second ? kb - num_kb1 : kb) * BK;
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const CUtensorMap* mb = second ? &tmB2 : &tmB;
-          if constexpr (CTA2) {
+          if constexpr (TN) {
+            // MN-major staging: 64-wide column atoms of the row-major sources, [64 k rows][64 cols] = 8 KB each
+            if constexpr (CTA2) {
+              if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d_pair(sA + s * A_BYTES + i * 8192, ma, &full[s], m0 + 64 * i, k0);
+#pragma unroll
+              for (int i = 0; i < B_ROWS / 64; ++i) tma_load_2d_pair(sB + s * B_BYTES + i * 8192, mb, &full[s], n0 + 64 * i, k0);
+            } else {
+              mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i) tma_load_2d(sA + s * A_BYTES + i * 8192, ma, &full[s], m0 + 64 * i, k0);
+#pragma unroll
+              for (int i = 0; i < B_ROWS / 64; ++i) tma_load_2d(sB + s * B_BYTES + i * 8192, mb, &full[s], n0 + 64 * i, k0);
+            }
+          } else if constexpr (CTA2) {
             if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * (A_BYTES + B_BYTES));
             tma_load_3d_pair(sA + s * A_BYTES, ma, &full[s], k0, m0, b);
             tma_load_2d_pair(sB + s * B_BYTES, mb, &full[s], k0, n0);
@@ -164,12 +180,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (lane == 0) {
-          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), 16, 1024);
-          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), 16, 1024);
+          // K-major: +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field.
+          // MN-major (TN): atoms of 64 columns 8192 B apart (LBO), 8-row groups 1024 B apart (SBO); one UMMA_K = 16 rows
+          // = 2048 B = +128.
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + s * A_BYTES), TN ? 8192 : 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + s * B_BYTES), TN ? 8192 : 16, 1024);
+          constexpr int KSTEP = TN ? 128 : 2;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {  // +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field
-            if constexpr (CTA2) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
-            else umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            if constexpr (CTA2) umma_ss_pair(d_tmem, adesc + KSTEP * k, bdesc + KSTEP * k, IDESC, (kb | k) != 0);
+            else umma_ss(d_tmem, adesc + KSTEP * k, bdesc + KSTEP * k, IDESC, (kb | k) != 0);
           }
           if constexpr (CTA2) {
             umma_commit_pair(&empty[s]);
@@ -379,7 +399,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   return 0;
 }
 
-int gemm_out_box_cols(int flags) { return (flags & EPI_OUT_F32) ? 32 : 64; }
+int gemm_out_box_cols(int flags) { return (flags & EPI_OUT_F32) ? 32 : 64; }   // (EPI_TN does not change the output)
 
 int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, GemmParams p, int flags,
                 int num_sms, cudaStream_t stream) {
@@ -410,6 +430,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
       return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_GELU_GRAD:
       return launch_mode<EPI_GELU_GRAD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD:
+      return launch_mode<EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     default:
       set_error("launch_gemm: unsupported epilogue flags %d", flags);
       return -1;

@@ -15,6 +15,8 @@ enum GemmEpilogue : int {
   EPI_ROWAUX = 8,       // + aux[row_in_batch][col] (fp32; Whisper's position table)
   EPI_RESIDUAL = 16,    // + resid[batch][row][col] (fp32, may alias out: in-place residual add, no atomics)
   EPI_GELU_GRAD = 32,   // out = grad_in[row][col] * gelu'(acc + bias)  (backward of a Linear+GELU, recomputed)
+  EPI_TN = 64,          // operand layout, not an epilogue: out = A_src^T W_src with A_src [K][M], W_src [K][N] row-major
+                        // (contraction over the ROWS: weight gradients); both operands are staged MN-major
 };
 
 struct GemmParams {
