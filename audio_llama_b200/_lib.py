@@ -32,6 +32,7 @@ SIGNATURES = {
     "al_ingest_forward": (i32, [vp, i64, i64, i32, vp, i32, i32, i32, vp, i64, i32, vp, i32, vp]),
     "al_gemm_bf16": (i32, [vp, i64, i64, i32, i32, vp, i32, i32, vp, vp, i64, i64, i32, vp, i32, vp, vp]),
     "al_gemm_set_mode": (i32, [i32]),
+    "al_gemm_tn_accumulate": (i32, [vp, i64, i32, vp, i64, i32, i32, vp, i64, vp]),
     "al_layernorm": (i32, [vp, vp, vp, vp, i32, i32, f32, i32, i64, i32, i64, i64, vp]),
     "al_attention": (i32, [vp, vp, i32, i32, i32, vp]),
     "al_pack_mel": (i32, [vp, vp, i32, i32, i32, i32, vp]),

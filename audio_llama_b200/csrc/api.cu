@@ -877,6 +877,14 @@ static int gemm_tn(const void* A_src, long long lda, int M, const void* W_src, l
   return rc;
 }
 
+int al_gemm_tn_accumulate(const void* A_src, long long lda, int M, const void* W_src, long long ldw, int N, int K, float* out,
+                          long long ldo, al_stream_t stream) {
+  AL_REQUIRE(A_src && W_src && out, "al_gemm_tn_accumulate: NULL argument");
+  AL_REQUIRE(M > 0 && N > 0 && K > 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0 && lda >= M && ldw >= N && ldo >= N,
+             "al_gemm_tn_accumulate: bad shape M=%d N=%d K=%d lda=%lld ldw=%lld ldo=%lld", M, N, K, lda, ldw, ldo);
+  return gemm_tn(A_src, lda, M, W_src, ldw, N, K, out, ldo, 2 * num_sms(), (cudaStream_t)stream);
+}
+
 size_t al_projector_backward_workspace_bytes(int rows, int d_in, int hidden, int d_out) {
   const size_t rp = (size_t)(rows + 7) / 8 * 8;
   size_t b = 0;

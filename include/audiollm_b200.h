@@ -86,6 +86,13 @@ int al_gemm_bf16(const void* A, long long a_row_stride, long long a_batch_stride
                  long long o_batch_stride, int flags, const float* aux, int aux_ld, const float* resid,
                  al_stream_t stream);
 
+/* Weight-gradient form: out[M][N] (f32, row pitch ldo) += A_src^T W_src with A_src [K][lda] (M valid columns) and W_src
+ * [K][ldw] (N valid columns) bf16, both row-major over the contraction index (what autograd computes for nn.Linear's
+ * weight: grad_out^T x). The operands are staged MN-major (64-column swizzle atoms, a_major = b_major = 1 in the tcgen05
+ * instruction descriptor), nothing is transposed in memory; split-K with TMA reduce-add, so `out` must be initialised. */
+int al_gemm_tn_accumulate(const void* A_src, long long lda, int M, const void* W_src, long long ldw, int N, int K, float* out,
+                          long long ldo, al_stream_t stream);
+
 /* GEMM kernel form: 1 = CTA pair per 256x256 tile (tcgen05.mma.cta_group::2, default), 0 = one CTA per 128x256
  * tile. Same results; the environment variable AUDIOLLM_B200_GEMM=single|pair sets the default. */
 int al_gemm_set_mode(int pair);

@@ -87,3 +87,32 @@ def test_conv_as_strided_gemm(cin, cout, T, stride):
     ops.gemm_bf16_strided(xt.cuda(), stride * cin, (T + 2) * cin, To, B, wp.cuda(), b.cuda(), out, cout, To * cout,
                           flags=EPI_GELU)
     check(out, ref, True)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 3072, 16112), (3072, 64, 16112), (72, 200, 1000), (8, 256, 77), (300, 520, 4096)])
+@pytest.mark.parametrize("pair", [1, 0])
+def test_gemm_tn_accumulate(M, N, K, pair):
+    """Weight-gradient form (MN-major operand staging): out += A^T W for row-major A [K, M], W [K, N]; ragged M / N / K
+    tails go through TMA zero-fill. fp32 reference of the bf16 operands; the existing contents of `out` are kept."""
+    from audio_llama_b200._lib import check, lib, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M * 7 + N)
+    lda, ldw = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+    A = torch.zeros(K, lda).bfloat16()
+    W = torch.zeros(K, ldw).bfloat16()
+    A[:, :M] = torch.randn(K, M, generator=g).bfloat16()
+    W[:, :N] = torch.randn(K, N, generator=g).bfloat16()
+    out0 = torch.randn(M, N, generator=g)
+    ref = out0 + A[:, :M].float().t() @ W[:, :N].float()
+    ldo = (N + 3) // 4 * 4
+    out = torch.zeros(M, ldo)
+    out[:, :N] = out0
+    Ad, Wd, od = A.cuda(), W.cuda(), out.cuda()
+    lib().al_gemm_set_mode(pair)
+    try:
+        check(lib().al_gemm_tn_accumulate(ptr(Ad), lda, M, ptr(Wd), ldw, N, K, ptr(od), ldo, stream_ptr()), "al_gemm_tn_accumulate")
+    finally:
+        lib().al_gemm_set_mode(1)
+    got = od.cpu()[:, :N]
+    assert (got - ref).norm() / ref.norm() <= 2e-3
+    if ldo > N:
+        assert (od.cpu()[:, N:] == 0).all()
