@@ -9,6 +9,7 @@ as hand-written sm_100a kernels with their backward, wired in through torch.auto
   * modeling_llama.apply_rotary_pos_emb -> al_rope (forward and transposed rotation for the gradient)
   * right-padded attention masks        -> dropped (causal attention already hides the padding from every real token;
                                            HF then takes SDPA's is_causal path instead of a dense additive bias)
+  * nn.Linear without LoRA (o_proj, lm_head) -> the tcgen05 GEMM forward and dgrad (frozen weights)
   * the loss (labels given)             -> al_linear_ce: lm_head + cross-entropy per chunk of rows, never forming the
                                            [tokens, vocab] logits (HF upcasts them to fp32: 8 GB at the README batch);
                                            `outputs.logits` is None in that mode.
@@ -78,6 +79,63 @@ class _SwiGLUFn(torch.autograd.Function):
 
 def swiglu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
     return _SwiGLUFn.apply(gate, up)
+
+
+# ----------------------------------------------------------------------------- frozen linear (no LoRA on it)
+_WT_PLAIN = {}
+
+
+def _weight_t(weight: torch.Tensor) -> torch.Tensor:
+    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
+    wt = _WT_PLAIN.get(key)
+    if wt is None:
+        out_dim, in_dim = weight.shape
+        ld = (out_dim + 7) // 8 * 8
+        wt = torch.zeros(in_dim, ld, dtype=weight.dtype, device=weight.device)
+        wt[:, :out_dim] = weight.detach().t()
+        _WT_PLAIN[key] = wt
+    return wt
+
+
+class _FrozenLinearFn(torch.autograd.Function):
+    """y = x W^T (+ b) with W frozen: forward and dgrad on the tcgen05 GEMM (o_proj, lm_head: the linears the reference
+    puts no LoRA on). Ragged out_features (the reference's vocabulary of 128 258) go through TMA tails."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import ops
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        b = bias.detach().float().contiguous() if bias is not None else None
+        out_dim = weight.shape[0]
+        ld = (out_dim + 7) // 8 * 8
+        if ld == out_dim:
+            y = ops.gemm_bf16(x2, weight, b)
+        else:                                   # row pitch of the output must be a multiple of 16 bytes for TMA
+            ypad = torch.empty(x2.shape[0], ld, dtype=torch.bfloat16, device=x.device)
+            check(lib().al_gemm_bf16(ptr(x2), x2.shape[1], x2.numel(), x2.shape[0], 1, ptr(weight), out_dim, x2.shape[1],
+                                     ptr(b), ptr(ypad), ld, ypad.numel(), 0, None, 0, None, stream_ptr()), "al_gemm_bf16")
+            y = ypad[:, :out_dim]
+        ctx.save_for_backward(weight)
+        ctx.in_shape = x.shape
+        return y.reshape(*x.shape[:-1], out_dim)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (weight,) = ctx.saved_tensors
+        out_dim, in_dim = weight.shape
+        ld = (out_dim + 7) // 8 * 8
+        if ld != out_dim:
+            raise RuntimeError("frozen_linear: backward needs out_features % 8 == 0")
+        dy2 = dy.reshape(-1, out_dim).contiguous()
+        wt = _weight_t(weight)                  # [in, out]
+        dx = torch.empty(dy2.shape[0], in_dim, dtype=torch.bfloat16, device=dy.device)
+        check(lib().al_gemm_bf16(ptr(dy2), ld, dy2.numel(), dy2.shape[0], 1, ptr(wt), in_dim, out_dim, None, ptr(dx), in_dim,
+                                 dx.numel(), 0, None, 0, None, stream_ptr()), "al_gemm_bf16")
+        return dx.reshape(ctx.in_shape), None, None
+
+
+def frozen_linear(x, weight, bias=None):
+    return _FrozenLinearFn.apply(x, weight, bias)
 
 
 # ----------------------------------------------------------------------------- rotary embedding
@@ -185,10 +243,22 @@ def causal_only_mask(attention_mask):
 _ORIG = {}
 
 
-def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True):
+def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True, frozen_linears=True):
     """Patch the HF LLaMA inside `audio_llm` (an audio_llama_b200.models.allm.AudioLLM) to the native ops."""
     from transformers.models.llama import modeling_llama as ML
     llama = audio_llm.llama.model
+    if frozen_linears:
+        # the linears the reference puts no LoRA on (o_proj, lm_head): frozen GEMM + dgrad on the tcgen05 kernel
+        for name, mod in llama.named_modules():
+            if isinstance(mod, torch.nn.Linear) and name not in audio_llm.lora_layers and not mod.weight.requires_grad:
+                def lin_fwd(m, x, _orig=type(mod).forward):
+                    # (a ragged out_features — lm_head at the reference's vocabulary — is only taken without autograd: its
+                    #  dgrad would need a padded W^T pitch; training goes through al_linear_ce instead)
+                    if _ok(x) and m.weight.dtype == torch.bfloat16 and x.shape[-1] % 8 == 0 and \
+                            (m.weight.shape[0] % 8 == 0 or not (torch.is_grad_enabled() and x.requires_grad)):
+                        return frozen_linear(x, m.weight, m.bias)
+                    return _orig(m, x)
+                mod.forward = types.MethodType(lin_fwd, mod)
     for mod in llama.modules():
         if rmsnorm_ and isinstance(mod, ML.LlamaRMSNorm):
             def norm_fwd(m, hidden_states, _orig=type(mod).forward):

@@ -137,3 +137,54 @@ def test_native_llama_in_audio_llm_matches_hf():
         LN.disable_rope_patch()
     assert abs(a[0] - b[0]) <= 2e-2 * abs(a[0])
     assert O.rel_l2(b[1], a[1]) <= 1e-1 and O.rel_l2(b[2], a[2]) <= 1e-1
+
+
+def test_frozen_linear_and_inference_logits():
+    """o_proj / lm_head on the tcgen05 GEMM: forward (ragged vocabulary) and dgrad vs torch, and the no-grad logits of an
+    AudioLLM in native mode vs the stock HF path (the generate() prefill)."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 70, 256, generator=g).bfloat16().cuda()
+    W = (torch.randn(1003, 256, generator=g) * 0.05).bfloat16().cuda()        # 1003 % 8 != 0: forward only
+    with torch.no_grad():
+        y = LN.frozen_linear(x, W)
+    assert y.shape == (3, 70, 1003) and rel(y, x.float() @ W.float().t()) <= 5e-3
+    W2 = (torch.randn(512, 256, generator=g) * 0.05).bfloat16().cuda()
+    b2 = torch.randn(512, generator=g).bfloat16().cuda()
+    xr = x.float().requires_grad_(True)
+    (xr @ W2.float().t() + b2.float()).backward(torch.ones(3, 70, 512, device="cuda"))
+    xn = x.clone().requires_grad_(True)
+    yn = LN.frozen_linear(xn, W2, b2)
+    yn.backward(torch.ones_like(yn))
+    assert rel(yn, xr.detach() @ W2.float().t() + b2.float()) <= 5e-3 and rel(xn.grad, xr.grad) <= 1e-2
+
+    from unittest.mock import patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as B
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200 import synth
+
+    def fake(lp, wp):
+        torch.manual_seed(0)
+        lc = LlamaConfig(vocab_size=322, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2)
+        ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+        return (B.FrozenModelWrapper(LlamaForCausalLM(lc).to(torch.bfloat16)),
+                B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=2)))
+
+    def logits(native):
+        with patch.object(B, "load_base_models", fake):
+            m = AudioLLM("x", "y", lora_rank=8).to("cuda").eval()
+        if native:
+            m.enable_fused_lora()
+            m.enable_native_llama_ops()
+        ids, mask, _ = (t.cuda() for t in synth.synth_text(2, 24, 320))
+        with torch.no_grad():
+            return m(input_ids=ids, attention_mask=mask).logits.float().cpu(), mask.bool().cpu()
+
+    try:
+        (a, keep), (b, _) = logits(False), logits(True)
+    finally:
+        LN.disable_rope_patch()
+    assert O.rel_l2(b[keep], a[keep]) <= 3e-2           # real positions (padded ones see a different mask on purpose)
