@@ -82,19 +82,28 @@ def swiglu(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------- frozen linear (no LoRA on it)
-_WT_PLAIN = {}
-
-
 def _weight_t(weight: torch.Tensor) -> torch.Tensor:
-    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
-    wt = _WT_PLAIN.get(key)
-    if wt is None:
+    """[in, round8(out)] transpose of a frozen weight, built once per weight tensor."""
+    from . import ops
+
+    def build():
         out_dim, in_dim = weight.shape
         ld = (out_dim + 7) // 8 * 8
         wt = torch.zeros(in_dim, ld, dtype=weight.dtype, device=weight.device)
         wt[:, :out_dim] = weight.detach().t()
-        _WT_PLAIN[key] = wt
-    return wt
+        return wt
+    return _CACHE().get((weight,), build)
+
+
+_cache = None
+
+
+def _CACHE():
+    global _cache
+    if _cache is None:
+        from . import ops
+        _cache = ops.TensorDerivedCache()
+    return _cache
 
 
 class _FrozenLinearFn(torch.autograd.Function):
@@ -172,19 +181,8 @@ def apply_rotary_pos_emb(q, k, cos, sin, unsqueeze_dim=1):
 
 
 # ----------------------------------------------------------------------------- lm_head + cross-entropy
-_WT_PAD = {}   # frozen lm_head (data_ptr, shape) -> its transpose, row pitch padded to a multiple of 8
-
-
 def _lm_head_t(weight: torch.Tensor) -> torch.Tensor:
-    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
-    wt = _WT_PAD.get(key)
-    if wt is None:
-        V, d = weight.shape
-        ldv = (V + 7) // 8 * 8
-        wt = torch.zeros(d, ldv, dtype=weight.dtype, device=weight.device)
-        wt[:, :V] = weight.detach().t()
-        _WT_PAD[key] = wt
-    return wt
+    return _weight_t(weight)
 
 
 class _LinearCEFn(torch.autograd.Function):

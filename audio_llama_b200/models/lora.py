@@ -51,31 +51,26 @@ def lora_forward_hook(module, input, output, lora_layer):
 
 
 # ----------------------------------------------------------------------------- fused path (B200)
-_WT_CACHE = {}   # frozen weight (data_ptr, shape) -> its transpose [in, out], built once
-
-
 def _frozen_weight_t(weight: torch.Tensor) -> torch.Tensor:
-    key = (weight.data_ptr(), tuple(weight.shape), weight.device)
-    wt = _WT_CACHE.get(key)
-    if wt is None:
-        wt = weight.detach().t().contiguous()
-        _WT_CACHE[key] = wt
-    return wt
-
-
-_PACK_CACHE = {}  # (id(A), id(B)) -> (A._version, B._version, scaling, packed operands): repacked after optimizer steps
+    """The frozen weight transposed, [in, out], built once per weight tensor."""
+    from .. import ops
+    global _WTS
+    if _WTS is None:
+        _WTS = ops.TensorDerivedCache()
+    return _WTS.get((weight,), lambda: weight.detach().t().contiguous())
 
 
 def _packed_operands(lora_A, lora_B, scaling):
+    """pack_lora(A, B, scaling), repacked after optimizer steps (the parameters' version counters move)."""
     from .. import ops
-    key = (id(lora_A), id(lora_B))
-    hit = _PACK_CACHE.get(key)
-    if hit is not None and hit[0] == lora_A._version and hit[1] == lora_B._version and hit[2] == scaling \
-            and hit[3][0].device == lora_A.device:
-        return hit[3]
-    packed = ops.pack_lora(lora_A, lora_B, scaling)
-    _PACK_CACHE[key] = (lora_A._version, lora_B._version, scaling, packed)
-    return packed
+    global _PACKS
+    if _PACKS is None:
+        _PACKS = ops.TensorDerivedCache()
+    return _PACKS.get((lora_A, lora_B), lambda: ops.pack_lora(lora_A, lora_B, scaling), extra=scaling)
+
+
+_PACKS = None
+_WTS = None
 
 
 class _FusedLoRALinearFn(torch.autograd.Function):

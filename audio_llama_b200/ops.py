@@ -260,5 +260,27 @@ def lora_linear_backward(x: torch.Tensor, dy: torch.Tensor, w_t: Optional[torch.
     return (dx.view_as(x) if need_dx else None), dA[:rank], dB[:, :rank]
 
 
+class TensorDerivedCache:
+    """value = build(tensor), rebuilt when the tensor object, its storage address or its version counter changes (an
+    in-place optimizer step or load_state_dict bumps `_version`). Entries die with their tensor (weak references)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, tensors, build, extra=None):
+        import weakref
+        tensors = tuple(tensors)
+        key = tuple(id(t) for t in tensors)
+        stamp = tuple((t.data_ptr(), t._version, t.device) for t in tensors) + (extra,)
+        hit = self._d.get(key)
+        if hit is not None and hit[1] == stamp and all(r() is t for r, t in zip(hit[0], tensors)):
+            return hit[2]
+        if len(self._d) > 4096:                       # dead entries of freed models
+            self._d = {k: v for k, v in self._d.items() if all(r() is not None for r in v[0])}
+        val = build()
+        self._d[key] = (tuple(weakref.ref(t) for t in tensors), stamp, val)
+        return val
+
+
 def launch_count() -> int:
     return int(lib().al_launch_count())

@@ -240,3 +240,22 @@ def test_causal_only_mask_rule():
     assert causal_only_mask(right) is None and causal_only_mask(None) is None
     assert causal_only_mask(left) is left and causal_only_mask(hole) is hole
     assert causal_only_mask(torch.ones(3, 1)) is None
+
+
+def test_tensor_derived_cache_invalidation():
+    """Packed LoRA operands / transposed frozen weights are cached per tensor and rebuilt when the tensor is updated in
+    place (optimizer step) or replaced."""
+    from audio_llama_b200.ops import TensorDerivedCache
+    c = TensorDerivedCache()
+    w = torch.randn(4, 3)
+    calls = []
+
+    def build():
+        calls.append(1)
+        return w.t().contiguous()
+    a = c.get((w,), build)
+    assert c.get((w,), build) is a and len(calls) == 1
+    w.mul_(2.0)                                   # in-place update bumps the version counter
+    b = c.get((w,), build)
+    assert len(calls) == 2 and torch.equal(b, w.t())
+    assert c.get((w,), build, extra=0.5) is not b and len(calls) == 3      # a different scaling is a different entry
