@@ -198,7 +198,7 @@ def run_reference(args):
                          "sample": f"{n_clips} x 30 s clips per step, {kind}, torch threads = {cores}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- product arm
@@ -399,12 +399,32 @@ def run_product(args):
         "kernels": kernels,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner to fd 1 when
+    the communicator is created), so fd 1 points at stderr until the result line is printed."""
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
