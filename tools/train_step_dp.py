@@ -31,6 +31,9 @@ LLAMAS = {
 
 
 def main():
+    sys.stdout.flush()
+    real_stdout = os.dup(1)          # stdout carries only the JSON line (NCCL prints its banner to fd 1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--llama", default="1b")
     ap.add_argument("--encoder", default="turbo")
@@ -113,6 +116,8 @@ def main():
         for e in rows[:40]:
             print(f"# {e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}% x{e.count:<5d} {e.key[:110]}", file=sys.stderr)
     if rank == 0:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps({"world": world, "llama": args.llama, "encoder": args.encoder, "batch_per_gpu": args.batch, "fused_lora": bool(args.fused_lora), "native_llama": bool(args.native_llama),
                           "trainable_params": bucket.numel, "bucket_mb": bucket.numel * 4 / 1e6,
                           "step_s": t_step, "allreduce_s": t_ar, "loss": float(out.loss.detach()),
