@@ -8,6 +8,7 @@ pytestmark = pytest.mark.gpu
 
 from audio_llama_b200 import llama_native as LN
 from oracle import encoder as O
+from oracle import llama as OL
 
 
 def rel(a, b):
@@ -28,8 +29,9 @@ def test_rmsnorm(rows, d):
     # same rounding points as HF; only the summation order of mean(x^2) differs, which moves a few values by one bf16 ulp
     assert (y != yh).float().mean() <= 0.02 and rel(y, yh) <= 2e-3
     xr = x.float().requires_grad_(True)
-    yr = w.float() * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5))
+    yr = OL.rmsnorm(xr, w.float(), 1e-5)
     yr.backward(dy.float())
+    assert rel(y, yr) <= 5e-3
     xn = x.clone().requires_grad_(True)
     LN.rmsnorm(xn.view(1, rows, d), w, 1e-5).backward(dy.view(1, rows, d))
     assert rel(xn.grad, xr.grad) <= 1e-2
@@ -41,7 +43,7 @@ def test_swiglu():
     b = torch.randn(300, 8192, generator=g).bfloat16().cuda()
     dh = torch.randn(300, 8192, generator=g).bfloat16().cuda()
     ar, br = a.float().requires_grad_(True), b.float().requires_grad_(True)
-    hr = torch.nn.functional.silu(ar) * br
+    hr = OL.swiglu(ar, br)
     hr.backward(dh.float())
     an, bn = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
     h = LN.swiglu(an, bn)
@@ -61,7 +63,9 @@ def test_rope(B, S, Hq, Hkv, hd, cb):
     sin = torch.cat([ang.sin(), ang.sin()], -1).bfloat16().cuda()
     dq = torch.randn(B, Hq, S, hd, generator=g).bfloat16().cuda()
     qr, kr = q.float().requires_grad_(True), k.float().requires_grad_(True)
-    qe, ke = orig(qr, kr, cos.float(), sin.float())
+    qe, ke = OL.rope(qr, kr, cos.float(), sin.float())
+    qh, kh = orig(q.float(), k.float(), cos.float(), sin.float())               # the HF function itself
+    assert torch.equal(qe.detach(), qh) and torch.equal(ke.detach(), kh)
     (qe * dq.float()).sum().backward()
     qn, kn = q.clone().requires_grad_(True), k.clone().requires_grad_(True)
     qo, ko = LN.apply_rotary_pos_emb(qn, kn, cos, sin)
@@ -94,6 +98,19 @@ def test_linear_cross_entropy(rows, d, V, chunk):
     lz.backward()
     assert float(lz) == 0.0 and float(hz.grad.abs().max()) == 0.0
     del logits
+
+
+def test_causal_lm_loss_shift():
+    """llama_native.causal_lm_loss([B, S, d] hidden, lm_head, labels) == the oracle's ForCausalLMLoss restatement."""
+    g = torch.Generator().manual_seed(9)
+    h = torch.randn(3, 41, 128, generator=g).bfloat16().cuda()
+    W = (torch.randn(777, 128, generator=g) * 0.05).bfloat16().cuda()
+    labels = torch.randint(0, 777, (3, 41), generator=g)
+    labels[1, 30:] = -100
+    labels[:, :5] = -100
+    ref = OL.causal_lm_loss(h.float().cpu() @ W.float().cpu().t(), labels)
+    got = LN.causal_lm_loss(h, W, labels.cuda(), chunk_rows=32)
+    assert abs(float(got) - float(ref)) <= 3e-3 * abs(float(ref))
 
 
 def test_native_llama_in_audio_llm_matches_hf():

@@ -244,3 +244,31 @@ def test_ingest_orders():
     long = np.zeros((1, 16000 * 31), np.float32)
     assert R.ingest_inference(long, 16000).shape == (480000,)
     assert R.ingest_train(np.zeros((1, 48000 * 31), np.float32), 48000).shape == (160000,)   # truncated BEFORE resampling
+
+
+def test_llama_oracle_matches_hf():
+    """oracle/llama.py against the HF definitions it restates (the reference's third-party path), CPU fp32."""
+    from transformers import LlamaConfig
+    from transformers.models.llama import modeling_llama as ML
+    from transformers.loss.loss_utils import ForCausalLMLoss
+    from oracle import llama as OL
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 7, 64, generator=g)
+    norm = ML.LlamaRMSNorm(64, eps=1e-5)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(64, generator=g))
+    assert torch.equal(OL.rmsnorm(x, norm.weight.detach(), 1e-5), norm(x).detach())
+    mlp = ML.LlamaMLP(LlamaConfig(hidden_size=64, intermediate_size=96, num_hidden_layers=1, num_attention_heads=4, vocab_size=10))
+    with torch.no_grad():
+        ref = mlp(x)
+        mine = mlp.down_proj(OL.swiglu(mlp.gate_proj(x), mlp.up_proj(x)))
+    assert torch.equal(mine, ref)
+    q, k = torch.randn(2, 4, 9, 16, generator=g), torch.randn(2, 2, 9, 16, generator=g)
+    ang = torch.rand(1, 9, 8, generator=g)
+    cos, sin = torch.cat([ang.cos()] * 2, -1), torch.cat([ang.sin()] * 2, -1)
+    (a, b), (c, d) = OL.rope(q, k, cos, sin), ML.apply_rotary_pos_emb(q, k, cos, sin)
+    assert torch.equal(a, c) and torch.equal(b, d)
+    logits = torch.randn(2, 6, 11, generator=g)
+    labels = torch.randint(0, 11, (2, 6), generator=g)
+    labels[0, 3:] = -100
+    assert torch.allclose(OL.causal_lm_loss(logits, labels), ForCausalLMLoss(logits, labels, 11), rtol=0, atol=1e-6)
