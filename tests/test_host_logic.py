@@ -259,3 +259,31 @@ def test_tensor_derived_cache_invalidation():
     b = c.get((w,), build)
     assert len(calls) == 2 and torch.equal(b, w.t())
     assert c.get((w,), build, extra=0.5) is not b and len(calls) == 3      # a different scaling is a different entry
+
+
+def test_native_llama_wiring_falls_back_off_gpu():
+    """llama_native.enable() patches the HF modules; inputs that are not bf16 CUDA tensors must take the modules' own
+    forward (same results bit for bit), never a CPU re-implementation."""
+    import types
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from transformers.models.llama import modeling_llama as ML
+    from audio_llama_b200 import llama_native as LN
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(LlamaConfig(vocab_size=50, hidden_size=32, intermediate_size=64, num_hidden_layers=2,
+                                     num_attention_heads=4, num_key_value_heads=2)).eval()
+    for p in m.parameters():
+        p.requires_grad = False
+    ids = torch.randint(0, 50, (2, 9))
+    with torch.no_grad():
+        before = m(input_ids=ids).logits
+    fake = types.SimpleNamespace(llama=types.SimpleNamespace(model=m), lora_layers={})
+    orig_rope = ML.apply_rotary_pos_emb
+    try:
+        LN.enable(fake)
+        assert ML.apply_rotary_pos_emb is LN.apply_rotary_pos_emb and fake.native_ce and fake.native_causal_only
+        with torch.no_grad():
+            after = m(input_ids=ids).logits
+    finally:
+        LN.disable_rope_patch()
+    assert ML.apply_rotary_pos_emb is orig_rope
+    assert torch.equal(before, after)
