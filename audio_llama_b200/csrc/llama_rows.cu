@@ -29,7 +29,7 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // y = w * bf16(x * rsqrt(mean(x^2) + eps))   (HF rounds the normalised value to the input dtype before the weight)
 // One warp per row, the row kept in registers (MAXV 16-byte vectors per lane; d <= 256 * MAXV).
 template <int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MAXV <= 12) ? 4 : 2)
 rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, uint4* __restrict__ y, float* __restrict__ rstd_out,
                    int rows, int nvec, float inv_d, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -69,7 +69,7 @@ rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, uin
 
 // dx = rstd * (g - xhat * mean(g * xhat)), g = dy * w, xhat = x * rstd (the weight is frozen: no dw).
 template <int MAXV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MAXV <= 12) ? 3 : 2)
 rmsnorm_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ rstd_in,
                    const uint4* __restrict__ dy, uint4* __restrict__ dx, int rows, int nvec, float inv_d) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -133,6 +133,7 @@ int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const voi
   AL_REQUIRE(d % 8 == 0 && d <= 8192, "rmsnorm: d=%d must be a multiple of 8 and <= 8192", d);
   if (rows == 0) return 0;
   if (d <= 2048) return rmsnorm_launch<8>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
+  if (d <= 3072) return rmsnorm_launch<12>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);   // fewer registers: 4 CTAs / SM
   if (d <= 4096) return rmsnorm_launch<16>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
   return rmsnorm_launch<32>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
 }
