@@ -23,11 +23,12 @@
 //
 // One CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256) per 256 consecutive frames of a clip; each CTA
 // owns 128 frames (TMEM lane = frame) and keeps HALF of the twiddle rows (56 of 112 output bins per matrix, hi and
-// lo: 94 KB) resident in shared memory for the whole persistent kernel. Per CTA:
-//   warp 0      loader: 32-frame sample slots (ring of 5), one cp.async.bulk per 160-sample hop into rows of
-//               stride 164 floats (the 16-byte destination alignment of bulk copies allows no odd stride, so
-//               thread-per-frame scalar reads are 4-way bank conflicted); clip edges (reflect padding, zero padding
-//               past n_samples) are filled by the warp itself.
+// lo: 98 KB) resident in shared memory for the whole persistent kernel. Per CTA:
+//   warp 0      loader: 32-frame sample slots (ring of 5) laid out as 34 rows of 164 floats (one 160-sample hop + 4
+//               per row; the 16-byte destination alignment of TMA allows no odd pitch, so the thread-per-frame scalar
+//               reads are 4-way bank conflicted). An interior slot is ONE 3-D tensor copy of the overlapping-row view
+//               [clip][hop][164] of the wave buffer; slots at the clip edges (reflect padding, zero padding past
+//               n_samples) fall back to one bulk copy per in-range hop plus element-wise fills by the warp itself.
 //   warp 1      MMA issuer (leader CTA only): A from TMEM, B from shared memory (no-swizzle K-major).
 //   warp 2      TMEM allocator (all 512 columns: 4 accumulators x 112 + 2 A stages x 32).
 //   warps 4-11  operand builders, one thread per (frame, half of a 16-wide K chunk): fold, window, power-of-two
