@@ -29,8 +29,11 @@
 //               reads are 4-way bank conflicted). An interior slot is ONE 3-D tensor copy of the overlapping-row view
 //               [clip][hop][164] of the wave buffer; slots at the clip edges (reflect padding, zero padding past
 //               n_samples) fall back to one bulk copy per in-range hop plus element-wise fills by the warp itself.
-//   warp 1      MMA issuer (leader CTA only): A from TMEM, B from shared memory (no-swizzle K-major).
-//   warp 2      TMEM allocator (all 512 columns: 4 accumulators x 112 + 2 A stages x 32).
+//   warp 1      MMA issuer (leader CTA only): A from TMEM, B from shared memory (no-swizzle K-major). Even bins: 6 MMAs
+//               per K block behind a two-stage operand hand-off; odd bins: 42 MMAs back to back once the builders have
+//               stored all seven blocks and the mel warps have drained the even-bin accumulators.
+//   warp 2      TMEM allocator (all 512 columns: 2 accumulators x 112 used for the even and then the odd bins, the odd-bin
+//               operands of all 7 K blocks (7 x 32), and a ring of two even-bin operand stages (2 x 32)).
 //   warps 4-11  operand builders, one thread per (frame, half of a 16-wide K chunk): fold, window, power-of-two
 //               scale (per 32-frame slot, so any input amplitude fits fp16), hi/lo split, tcgen05.st.
 //   warps 12-15 one thread per frame: TMEM -> |X|^2 -> mel sums in registers (the bank is banded: every bin feeds
@@ -66,13 +69,15 @@ constexpr int TC_TILES_PER_CLIP = 12;                            // ceil(3000 / 
 constexpr int TC_THREADS = 512;
 constexpr int TC_CLIP = 480000, TC_FRAMES = 3000;
 // TMEM columns
-constexpr uint32_t TC_D_CE = 0, TC_D_SE = 112, TC_D_CO = 224, TC_D_SO = 336, TC_A_E = 448, TC_A_O = 480;
+// D (cos part | sin part) is used twice per tile: even bins first, odd bins after the mel warps have drained it.
+// A_O holds the odd-bin operands of ALL seven K blocks (32 columns each), A_E is a ring of two 32-column stages.
+constexpr uint32_t TC_D_C = 0, TC_D_S = 112, TC_A_O = 224, TC_A_E = 448;
 
 constexpr int TC_OFF_B = 0;
 constexpr int TC_OFF_SLOTS = TC_OFF_B + MEL_TC_B_BYTES;
 constexpr int TC_OFF_BAR = TC_OFF_SLOTS + TC_NSLOT * TC_SLOT_PITCH * 4;
 static_assert(TC_OFF_SLOTS % 128 == 0 && (TC_SLOT_PITCH * 4) % 128 == 0 && TC_SLOT_PITCH >= TC_SLOT_FLOATS, "slot alignment");
-constexpr int TC_NBAR = 2 * TC_NSLOT + 2 + 2 + 1 + 1 + 1;
+constexpr int TC_NBAR = 2 * TC_NSLOT + 2 + 2 + 2 + 2 + 2 + 1;
 constexpr int TC_OFF_MISC = TC_OFF_BAR + TC_NBAR * 8;
 constexpr int TC_SMEM = TC_OFF_MISC + 128 /*tmem ptr, slot max, scales*/ + 128 /*alignment slack*/;
 static_assert(TC_SMEM <= 232448, "mel_tc shared memory over the 227 KB limit");
@@ -190,8 +195,10 @@ struct MelTcArgs {
 // running pointers (x[i], x[200 + i] move up with j; x[400 - i], x[200 - i] move down); the 4-float pad between hops
 // shifts an address only when 400 - i < 320 or 200 - i < 160, which for a given HH depends on j for exactly one t.
 template <int HH>
-__device__ __forceinline__ void build_tile(uint32_t xb, float S, uint32_t t_lane, uint64_t* a_empty, uint64_t* a_full,
-                                           uint64_t* slot_done, uint32_t n_use0, uint32_t rank, int lane) {
+__device__ __forceinline__ void build_tile(uint32_t xb, float S, uint32_t t_lane, uint64_t* e_empty, uint64_t* e_full,
+                                           uint64_t* o_empty, uint64_t* o_full, uint64_t* slot_done, uint32_t tile_it,
+                                           uint32_t rank, int lane) {
+  const uint32_t n_use0 = tile_it * 7u;
 #pragma unroll 1
   for (int j = 0; j < 7; ++j) {
     const int base = j + 56 * HH;
@@ -236,23 +243,30 @@ __device__ __forceinline__ void build_tile(uint32_t xb, float S, uint32_t t_lane
       tmem_st_32x4(t_hi + 4 * HH, h[0], h[1], h[2], h[3]);
       tmem_st_32x4(t_hi + 8 + 4 * HH, l[0], l[1], l[2], l[3]);
     };
-    const uint32_t n_use = n_use0 + j;
-    mbar_wait(&a_empty[0], (n_use & 1) ^ 1);
+    // even-bin operands: ring of two stages, one hand-off per K block
+    const uint32_t n_use = n_use0 + j;               // running K-block count of this CTA
+    const uint32_t es = n_use & 1;
+    mbar_wait(&e_empty[es], ((n_use >> 1) & 1) ^ 1);
     tc_fence_after();
-    split_store(ce, t_lane + TC_A_E);
-    split_store(se, t_lane + TC_A_E + 16);
+    split_store(ce, t_lane + TC_A_E + 32 * es);
+    split_store(se, t_lane + TC_A_E + 32 * es + 16);
     tmem_st_wait();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) arrive_on_leader(&a_full[0], rank);
-    mbar_wait(&a_empty[1], (n_use & 1) ^ 1);
-    tc_fence_after();
-    split_store(co, t_lane + TC_A_O);
-    split_store(so, t_lane + TC_A_O + 16);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) arrive_on_leader(&a_full[1], rank);
+    if (lane == 0) arrive_on_leader(&e_full[es], rank);
+    // odd-bin operands: block j of the tile-wide buffer, handed over once per tile
+    if (j == 0) {
+      mbar_wait(o_empty, (tile_it & 1) ^ 1);         // the previous tile's odd pass has read the buffer
+      tc_fence_after();
+    }
+    split_store(co, t_lane + TC_A_O + 32 * j);
+    split_store(so, t_lane + TC_A_O + 32 * j + 16);
+    if (j == 6) {
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_on_leader(o_full, rank);
+    }
   }
 }
 
@@ -278,11 +292,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
   uint64_t* slot_full = bars;                     // [NSLOT] loader -> builders (tx bytes + 1 arrival)
   uint64_t* slot_empty = bars + TC_NSLOT;         // [NSLOT] 2 builder warps -> loader
-  uint64_t* a_full = bars + 2 * TC_NSLOT;         // [2] (leader's are used) 16 builder warps of the pair -> MMA
-  uint64_t* a_empty = a_full + 2;                 // [2] MMA commit (multicast) -> builders
-  uint64_t* d_full = a_empty + 2;                 // MMA commit (multicast) -> mel warps
-  uint64_t* d_empty = d_full + 1;                 // (leader's) 8 mel warps of the pair -> MMA
-  uint64_t* b_full = d_empty + 1;                 // twiddle image landed
+  uint64_t* e_full = bars + 2 * TC_NSLOT;         // [2] (leader's are used) 16 builder warps of the pair -> MMA, per K block
+  uint64_t* e_empty = e_full + 2;                 // [2] MMA commit (multicast) -> builders
+  uint64_t* o_full = e_empty + 2;                 // (leader's) 16 builder warps -> MMA, once per tile: all 7 odd-bin blocks stored
+  uint64_t* o_empty = o_full + 1;                 // MMA commit (multicast) -> builders: the odd pass has read them
+  uint64_t* d_full = o_empty + 1;                 // [2] MMA commit (multicast) -> mel warps: even / odd accumulators complete
+  uint64_t* d_drained = d_full + 2;               // [2] (leader's) 8 mel warps of the pair -> MMA: D may be overwritten
+  uint64_t* b_full = d_drained + 2;               // twiddle image landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + TC_OFF_MISC);
   float* s_red = reinterpret_cast<float*>(smem + TC_OFF_MISC + 16);      // [2 parity][4 quarter][2 half]
   float* s_inv2 = s_red + 16;                                            // [2 parity][4 quarter]
@@ -300,12 +316,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
       mbar_init(&slot_full[s], 1);
       mbar_init(&slot_empty[s], 2);
     }
-    mbar_init(&a_full[0], 16);
-    mbar_init(&a_full[1], 16);
-    mbar_init(&a_empty[0], 1);
-    mbar_init(&a_empty[1], 1);
-    mbar_init(d_full, 1);
-    mbar_init(d_empty, 8);
+    mbar_init(&e_full[0], 16);
+    mbar_init(&e_full[1], 16);
+    mbar_init(&e_empty[0], 1);
+    mbar_init(&e_empty[1], 1);
+    mbar_init(o_full, 16);
+    mbar_init(o_empty, 1);
+    mbar_init(&d_full[0], 1);
+    mbar_init(&d_full[1], 1);
+    mbar_init(&d_drained[0], 8);
+    mbar_init(&d_drained[1], 8);
     mbar_init(b_full, 1);
     fence_barrier_init();
   }
@@ -411,36 +431,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
       const uint32_t b_addr = smem_u32(sB);
       int it = 0;
       uint32_t n_use = 0;
+      // the three products of one (matrix, K block): the two small ones first, the large one last
+      auto products = [&](uint32_t d, uint32_t a_hi, int mat, int j) {
+        const uint64_t b_hi = umma_desc_noswz(b_addr + (2 * mat) * MEL_TC_MAT_BYTES + 2 * j * MEL_TC_KCHUNK_BYTES,
+                                              MEL_TC_KCHUNK_BYTES, 128);
+        const uint64_t b_lo = umma_desc_noswz(b_addr + (2 * mat + 1) * MEL_TC_MAT_BYTES + 2 * j * MEL_TC_KCHUNK_BYTES,
+                                              MEL_TC_KCHUNK_BYTES, 128);
+        umma_ts_pair(d, a_hi + 8, b_hi, IDESC, j != 0);
+        umma_ts_pair(d, a_hi, b_lo, IDESC, 1);
+        umma_ts_pair(d, a_hi, b_hi, IDESC, 1);
+      };
       for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
-        mbar_wait(d_empty, (it & 1) ^ 1);
+        // even bins: one hand-off per K block (ring of two operand stages)
+        mbar_wait(&d_drained[1], (it & 1) ^ 1);     // the previous tile's odd-bin accumulators have been read
         tc_fence_after();
         for (int j = 0; j < 7; ++j, ++n_use) {
-#pragma unroll
-          for (int ph = 0; ph < 2; ++ph) {         // ph 0: even bins (ce, se); ph 1: odd bins (co, so)
-            mbar_wait(&a_full[ph], n_use & 1);
-            tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a0 = tmem_base + (ph ? TC_A_O : TC_A_E);
-#pragma unroll
-              for (int g = 0; g < 2; ++g) {        // g 0: cos part, g 1: sin part
-                const uint32_t d = tmem_base + (ph ? (g ? TC_D_SO : TC_D_CO) : (g ? TC_D_SE : TC_D_CE));
-                const int mat = ph * 2 + g;
-                const uint64_t b_hi = umma_desc_noswz(b_addr + (2 * mat) * MEL_TC_MAT_BYTES + 2 * j * MEL_TC_KCHUNK_BYTES,
-                                                      MEL_TC_KCHUNK_BYTES, 128);
-                const uint64_t b_lo = umma_desc_noswz(b_addr + (2 * mat + 1) * MEL_TC_MAT_BYTES + 2 * j * MEL_TC_KCHUNK_BYTES,
-                                                      MEL_TC_KCHUNK_BYTES, 128);
-                const uint32_t a_hi = a0 + g * 16, a_lo = a0 + g * 16 + 8;
-                // the two small products first, the large one last: one truncating add of a large term per block
-                umma_ts_pair(d, a_lo, b_hi, IDESC, j != 0);
-                umma_ts_pair(d, a_hi, b_lo, IDESC, 1);
-                umma_ts_pair(d, a_hi, b_hi, IDESC, 1);
-              }
-              umma_commit_pair(&a_empty[ph]);
-              if (j == 6 && ph == 1) umma_commit_pair(d_full);
-            }
-            __syncwarp();
+          const uint32_t es = n_use & 1;
+          mbar_wait(&e_full[es], (n_use >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a0 = tmem_base + TC_A_E + 32 * es;
+            products(tmem_base + TC_D_C, a0, 0, j);
+            products(tmem_base + TC_D_S, a0 + 16, 1, j);
+            umma_commit_pair(&e_empty[es]);
+            if (j == 6) umma_commit_pair(&d_full[0]);
           }
+          __syncwarp();
         }
+        // odd bins: all seven K blocks are already in TMEM, 42 MMAs back to back
+        mbar_wait(o_full, it & 1);
+        mbar_wait(&d_drained[0], it & 1);           // the even-bin accumulators have been read
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll 1
+          for (int j = 0; j < 7; ++j) {
+            const uint32_t a0 = tmem_base + TC_A_O + 32 * j;
+            products(tmem_base + TC_D_C, a0, 2, j);
+            products(tmem_base + TC_D_S, a0 + 16, 3, j);
+          }
+          umma_commit_pair(o_empty);
+          umma_commit_pair(&d_full[1]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp < 12) {
@@ -479,8 +511,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
       if (hh == 0 && lane == 0) s_inv2[(it & 1) * 4 + q] = __uint_as_float(static_cast<uint32_t>(127 - 2 * sh) << 23);
 
       const uint32_t xb = smem_u32(sl + lane * TC_SEG_STRIDE);   // this thread's frame: sample n at xb + 4 tc_off(n)
-      if (hh == 0) build_tile<0>(xb, S, t_lane, a_empty, a_full, &slot_empty[slot], static_cast<uint32_t>(it) * 7u, rank, lane);
-      else build_tile<1>(xb, S, t_lane, a_empty, a_full, &slot_empty[slot], static_cast<uint32_t>(it) * 7u, rank, lane);
+      if (hh == 0) build_tile<0>(xb, S, t_lane, e_empty, e_full, o_empty, o_full, &slot_empty[slot], static_cast<uint32_t>(it), rank, lane);
+      else build_tile<1>(xb, S, t_lane, e_empty, e_full, o_empty, o_full, &slot_empty[slot], static_cast<uint32_t>(it), rank, lane);
     }
   } else {
     // ------------------------------------------------------------------ power, mel, log, store
@@ -496,37 +528,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
       float mel[128];
 #pragma unroll
       for (int m = 0; m < 128; ++m) mel[m] = 0.f;
-      mbar_wait(d_full, it & 1);
-      tc_fence_after();
-      const float inv_s2 = s_inv2[(it & 1) * 4 + q];
-      static_for<0, 7>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        {
+      // two passes over the same accumulator columns: even bins, then (after the MMAs of the odd pass) odd bins. Each
+      // pass releases D as soon as its last column has been read.
+      static_for<0, 2>([&](auto pp) {
+        constexpr int PAR = decltype(pp)::value;
+        mbar_wait(&d_full[PAR], it & 1);
+        tc_fence_after();
+        static_for<0, 7>([&](auto cc) {
+          constexpr int c = decltype(cc)::value;
           uint32_t rr[16], ri[16];
-          tmem_ld_32x16(t_lane + TC_D_CE + 16 * c, rr);
-          tmem_ld_32x16(t_lane + TC_D_SE + 16 * c, ri);
+          tmem_ld_32x16(t_lane + TC_D_C + 16 * c, rr);
+          tmem_ld_32x16(t_lane + TC_D_S + 16 * c, ri);
           tmem_ld_wait();
-          static_for<0, 16>([&](auto jj) {
-            constexpr int k = 2 * (16 * c + decltype(jj)::value);
-            if constexpr (k <= 200) mel_bin<BANK, k>(mel, __uint_as_float(rr[decltype(jj)::value]), __uint_as_float(ri[decltype(jj)::value]));
-          });
-        }
-        {
-          uint32_t rr[16], ri[16];
-          tmem_ld_32x16(t_lane + TC_D_CO + 16 * c, rr);
-          tmem_ld_32x16(t_lane + TC_D_SO + 16 * c, ri);
-          tmem_ld_wait();
-          if constexpr (c == 6) {                    // accumulators drained: the next tile's MMAs may start
+          if constexpr (c == 6) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_on_leader(d_empty, rank);
+            if (lane == 0) arrive_on_leader(&d_drained[PAR], rank);
           }
           static_for<0, 16>([&](auto jj) {
-            constexpr int k = 2 * (16 * c + decltype(jj)::value) + 1;
-            if constexpr (k <= 199) mel_bin<BANK, k>(mel, __uint_as_float(rr[decltype(jj)::value]), __uint_as_float(ri[decltype(jj)::value]));
+            constexpr int k = 2 * (16 * c + decltype(jj)::value) + PAR;
+            if constexpr (k <= (PAR ? 199 : 200))
+              mel_bin<BANK, k>(mel, __uint_as_float(rr[decltype(jj)::value]), __uint_as_float(ri[decltype(jj)::value]));
           });
-        }
+        });
       });
+      const float inv_s2 = s_inv2[(it & 1) * 4 + q];     // (written by this tile's builders before their first hand-off)
       float lmax = -INFINITY;
 #pragma unroll
       for (int m = 0; m < N_MELS; ++m) {
