@@ -4,14 +4,15 @@ as four ~100x100 products, operands split into fp16 hi + lo, three products (hi*
 fp32, then the streaming banded mel projection. Run it to see the error of this arithmetic against the float64 value
 of the reference formula (oracle.mel) before spending GPU time; it also documents the operand layout the kernel uses.
 
-Not product code and not imported by the package: a design check that lives next to the other tools."""
+Not product code and not imported by the package: a design check that lives with the tests (it uses the oracle as its
+checker); tests/test_mel_tc_design.py runs a reduced version on CPU."""
 import os
 import sys
 
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import mel as M  # noqa: E402  (tools/ may use the oracle as a checker)
+from oracle import mel as M  # noqa: E402
 
 KP = 112     # padded contraction length (K index i = 0..100 used)
 NP = 112     # padded output count per parity (even k: 101 used, odd k: 100 used)
@@ -173,7 +174,7 @@ def mel_tc(wave, n_mels=128, mode=0, split=split_f16_trunc, frames_sel=None):
 
 
 if __name__ == "__main__":
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     from golden_signals import kat_signals
     sig = kat_signals()
     sel = np.arange(0, 3000, 7)
