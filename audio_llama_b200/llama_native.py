@@ -173,7 +173,11 @@ def apply_rotary_pos_emb(q, k, cos, sin, unsqueeze_dim=1):
     """Drop-in for transformers.models.llama.modeling_llama.apply_rotary_pos_emb: q, k [B, H, S, hd] (views of the
     [B, S, H, hd] projection outputs), cos / sin [B or 1, S, hd]."""
     if not (_ok(q) and _ok(k) and _ok(cos) and unsqueeze_dim == 1 and q.shape[-1] % 16 == 0):
-        return _ORIG["rope"](q, k, cos, sin, unsqueeze_dim=unsqueeze_dim)
+        hf = _ORIG.get("rope")
+        if hf is None:                       # called directly, without enable(): HF's own function is still in place
+            from transformers.models.llama import modeling_llama as ML
+            hf = ML.apply_rotary_pos_emb
+        return hf(q, k, cos, sin, unsqueeze_dim=unsqueeze_dim)
     cc, ss = cos.contiguous(), sin.contiguous()
     qo = _RoPEFn.apply(q.transpose(1, 2).contiguous(), cc, ss).transpose(1, 2)
     ko = _RoPEFn.apply(k.transpose(1, 2).contiguous(), cc, ss).transpose(1, 2)
