@@ -205,3 +205,53 @@ def test_frozen_linear_and_inference_logits():
     finally:
         LN.disable_rope_patch()
     assert O.rel_l2(b[keep], a[keep]) <= 3e-2           # real positions (padded ones see a different mask on purpose)
+
+
+def test_generate_in_native_mode():
+    """AudioLLM.generate() with the native LLaMA ops and the fused LoRA linears: HF's KV-cache decode loop runs on the
+    patched modules (RMSNorm / RoPE at one token per step, lm_head on the tcgen05 GEMM) and stays deterministic."""
+    from unittest.mock import Mock, patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as B
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200.features import LogMelExtractor
+    from audio_llama_b200 import synth
+
+    def fake(lp, wp):
+        torch.manual_seed(0)
+        lc = LlamaConfig(vocab_size=322, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2)
+        ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+        return (B.FrozenModelWrapper(LlamaForCausalLM(lc).to(torch.bfloat16)),
+                B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=1, out_dtype=torch.bfloat16)))
+
+    with patch.object(B, "load_base_models", fake):
+        m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+    m.projector.to(torch.bfloat16)
+    tok = Mock()
+    tok.convert_tokens_to_ids = lambda t: {"<audio>": 320, "</audio>": 321}[t]
+    tok.pad_token_id, tok.bos_token_id, tok.eos_token_id = 0, 1, None
+    tok.decode = lambda t, skip_special_tokens=True: " ".join(str(int(x)) for x in t)
+    m.tokenizer = tok
+    m.enable_fused_lora()
+    m.enable_native_llama_ops()
+    ids, mask, _ = (t.cuda() for t in synth.synth_text(1, 8, 320))
+    feats = LogMelExtractor(80)([synth.synth_clip(0)], sampling_rate=16000).input_features.unsqueeze(1)
+    try:
+        a = m.generate(input_ids=ids, attention_mask=mask, audio_features=feats, max_new_tokens=6, do_sample=False,
+                       temperature=None, top_p=None)
+        b = m.generate(input_ids=ids, attention_mask=mask, audio_features=feats, max_new_tokens=6, do_sample=False,
+                       temperature=None, top_p=None)
+        # the decode loop itself: 6 new tokens from the conditioned embeddings, identical on a second run
+        with torch.no_grad():
+            emb, amask, _ = m._conditioned_inputs(ids, mask, feats, None)
+            kw = dict(inputs_embeds=emb, attention_mask=amask, max_new_tokens=6, do_sample=False, temperature=None,
+                      top_p=None, pad_token_id=0)
+            t1 = m.llama.model.generate(**kw)
+            t2 = m.llama.model.generate(**kw)
+    finally:
+        LN.disable_rope_patch()
+    assert isinstance(a, str) and a == b          # (the reference slices `outputs[0, input_length:]`, allm.py:333-346)
+    assert t1.shape == (1, 6) and torch.equal(t1, t2)
