@@ -287,3 +287,19 @@ def test_native_llama_wiring_falls_back_off_gpu():
         LN.disable_rope_patch()
     assert ML.apply_rotary_pos_emb is orig_rope
     assert torch.equal(before, after)
+
+
+def test_pack_lora_operands():
+    """ops.pack_lora: A zero-padded to a multiple of 8 rows, scaling folded into B, both bf16 (pure torch: CPU-checkable)."""
+    from audio_llama_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    A, Bm = torch.randn(5, 16, generator=g), torch.randn(24, 5, generator=g)
+    a, b = ops.pack_lora(A, Bm, 0.25)
+    assert a.shape == (8, 16) and b.shape == (24, 8) and a.dtype == b.dtype == torch.bfloat16
+    assert torch.equal(a[:5], A.bfloat16()) and (a[5:] == 0).all()
+    assert torch.equal(b[:, :5], (Bm * 0.25).bfloat16()) and (b[:, 5:] == 0).all()
+    # the packed operands reproduce the hook's update: (x a^T)(s b)^T == scaling * x (B A)^T
+    x = torch.randn(7, 16, generator=g)
+    ref = (x @ (Bm @ A).T) * 0.25
+    got = (x @ a.float().T) @ b.float().T
+    assert torch.allclose(got, ref, rtol=0, atol=0.15)          # bf16 operand rounding
