@@ -36,6 +36,9 @@ constexpr int ATT_SMEM = (1 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 25
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float ATT_TAU = 8.0f;   // lazy-rescale threshold, log2 units
 constexpr int POLY_PAIRS = 1;     // of every 4 pairs, how many use the FMA-pipe exp2
+// softmax warps -> MMA warp hand-offs are named barriers (128 arrive + 32 sync); id 0 is __syncthreads
+constexpr int ATT_BAR_P_FULL = 1;
+constexpr int ATT_BAR_S_EMPTY = 2;
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -79,10 +82,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
   uint64_t* k_empty = k_full + ATT_K_STAGES;
   uint64_t* v_full = k_empty + ATT_K_STAGES;
   uint64_t* v_empty = v_full + ATT_V_STAGES;
-  uint64_t* s_full = v_empty + ATT_V_STAGES;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_empty + 1;
-  uint64_t* o_full = p_full + 1;
+  uint64_t* s_full = v_empty + ATT_V_STAGES;            // "S drained" and "P stored" are named barriers (see below)
+  uint64_t* o_full = s_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -105,8 +106,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_empty, 128);
-    mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -182,14 +181,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
           mbar_wait(&k_full[ks], kph);
-          mbar_wait(s_empty, j & 1);
+          named_bar_sync(ATT_BAR_S_EMPTY, 160);        // blocks in hardware: no polling next to the softmax warps
           tc_fence_after();
           if (lane == 0) issue_s(ks);
           __syncwarp();
           if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
         }
         mbar_wait(&v_full[vs], vph);
-        mbar_wait(p_full, j & 1);
+        named_bar_sync(ATT_BAR_P_FULL, 160);
         tc_fence_after();
         if (lane == 0) issue_o(vs, j == 0);
         __syncwarp();
@@ -225,7 +224,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
         tmem_ld_wait();
       }
       tc_fence_before();
-      mbar_arrive(s_empty);                        // S is in registers: Q K_{j+1}^T may overwrite it now
+      if (j + 1 < nkv) named_bar_arrive(ATT_BAR_S_EMPTY, 160);   // S is in registers: Q K_{j+1}^T may overwrite it now
       if (j == nkv - 1) {                          // kv tail: columns >= kv_valid are zero-filled K rows
         const int kv_valid = T - j * ATT_BKV;
         if (kv_valid < ATT_BKV) {
@@ -302,7 +301,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      named_bar_arrive(ATT_BAR_P_FULL, 160);
     }
     // normalise and store
     mbar_wait(o_full, (nkv - 1) & 1);

@@ -88,6 +88,11 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 // Bounded wait: a protocol bug must trap (the launch then returns an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  // short waits poll without the watchdog arithmetic (3 instructions per poll instead of ~10: the polling warp shares
+  // its scheduler with working warps)
+#pragma unroll 1
+  for (int i = 0; i < 128; ++i)
+    if (mbar_try_wait_hint(bar, parity, AL_WAIT_HINT_NS)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_hint(bar, parity, AL_WAIT_HINT_NS)) {
     if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
@@ -103,6 +108,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ----------------------------------------------------------------------------- TMA
