@@ -108,6 +108,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
     mbar_init(s_full, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    // the first loads need nothing but their barriers: they start before the TMEM allocation and the CTA-wide sync
+    mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+    tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
+    mbar_arrive_expect_tx(&k_full[0], ATT_TILE_BYTES);
+    tma_load_3d(sK, &tmQKV, &k_full[0], d + h * ATT_HD, 0, b);
   }
   if (warp == 2) tmem_alloc<256>(tmem_ptr);
   tc_fence_before();
@@ -126,10 +131,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-        tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
+        // (Q and K_0 were requested by this same thread before the CTA-wide sync)
         // K runs ahead of V: K_{j+1} is requested before V_j so that Q K_{j+1}^T is never starved
-        int ks = 0, vs = 0;
+        int ks = 1, vs = 0;
         uint32_t kph = 0, vph = 0;
         auto load_k = [&](int j) {
           mbar_wait(&k_empty[ks], kph ^ 1);
@@ -137,7 +141,6 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
           tma_load_3d(sK + ks * ATT_TILE_BYTES, &tmQKV, &k_full[ks], d + h * ATT_HD, j * ATT_BKV, b);
           if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
         };
-        load_k(0);
         for (int j = 0; j < nkv; ++j) {
           if (j + 1 < nkv) load_k(j + 1);
           mbar_wait(&v_empty[vs], vph ^ 1);
