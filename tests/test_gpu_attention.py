@@ -17,7 +17,8 @@ def ref_attention(qkv, H):
 
 
 @pytest.mark.parametrize("B,T,H,qs", [(1, 128, 1, 1.0), (1, 256, 2, 1.0), (2, 300, 3, 2.0), (1, 1500, 6, 1.0),
-                                      (2, 1500, 20, 3.0), (1, 92, 1, 1.0), (1, 1000, 2, 0.2)])
+                                      (2, 1500, 20, 3.0), (1, 92, 1, 1.0), (1, 1000, 2, 0.2),
+                                      (6, 700, 20, 1.0), (3, 100, 120, 1.0)])   # many CTAs per SM slot, many heads
 def test_attention(B, T, H, qs):
     g = torch.Generator().manual_seed(B * 1000 + T + H)
     qkv = torch.randn(B, T, 3 * H * 64, generator=g)
