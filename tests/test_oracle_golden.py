@@ -272,3 +272,62 @@ def test_llama_oracle_matches_hf():
     labels = torch.randint(0, 11, (2, 6), generator=g)
     labels[0, 3:] = -100
     assert torch.allclose(OL.causal_lm_loss(logits, labels), ForCausalLMLoss(logits, labels, 11), rtol=0, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- properties of the index contracts
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.lists(st.integers(1, 1500), min_size=1, max_size=4), min_size=1, max_size=5), st.integers(0, 40))
+def test_ragged_layout_properties(rows, t_txt):
+    """Extension row (config 5): the exclusive prefix sum over (a_i + 2) — spans tile the prefix without gaps or
+    overlap, text starts right after the last </audio>, S_max is the longest sample."""
+    span_off, text_off, total, s_max = O.ragged_layout(rows, t_txt)
+    assert s_max == max(total)
+    for b, r in enumerate(rows):
+        assert span_off[b][0] == 0
+        for i, a in enumerate(r):
+            end = span_off[b][i] + a + 2
+            assert end == (span_off[b][i + 1] if i + 1 < len(r) else text_off[b])
+        assert text_off[b] == sum(a + 2 for a in r)
+        assert total[b] == text_off[b] + t_txt
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.lists(st.lists(st.integers(1, 9), min_size=1, max_size=3), min_size=1, max_size=4), st.integers(1, 6),
+       st.integers(0, 2 ** 31 - 1))
+def test_combine_ragged_properties(rows, t_txt, seed):
+    """Every output row is exactly one of: a delimiter row, a projected row, a text row or a zero pad row; the mask
+    counts the real rows; labels are -100 everywhere but under the text."""
+    g = torch.Generator().manual_seed(seed)
+    B, d, vocab = len(rows), 4, 20
+    E = torch.randn(vocab, d, generator=g)
+    ids = torch.randint(0, vocab - 2, (B, t_txt), generator=g)
+    am = torch.ones(B, t_txt, dtype=torch.long)
+    labels = torch.randint(0, vocab - 2, (B, t_txt), generator=g)
+    proj = [[torch.randn(a, d, generator=g) for a in r] for r in rows]
+    out, mask, lab = O.combine_ragged(E, ids, am, labels, proj, vocab - 2, vocab - 1)
+    span_off, text_off, total, s_max = O.ragged_layout(rows, t_txt)
+    assert out.shape == (B, s_max, d) and mask.shape == (B, s_max) and lab.shape == (B, s_max)
+    for b in range(B):
+        assert mask[b].sum().item() == total[b]
+        assert (out[b, total[b]:] == 0).all() and (mask[b, total[b]:] == 0).all()
+        assert (lab[b, :text_off[b]] == -100).all() and (lab[b, total[b]:] == -100).all()
+        assert (lab[b, text_off[b]:total[b]] == labels[b]).all()
+        assert (out[b, text_off[b]:total[b]] == E[ids[b]]).all()
+        for i, p in enumerate(proj[b]):
+            o = span_off[b][i]
+            assert (out[b, o] == E[vocab - 2]).all() and (out[b, o + 1 + p.shape[0]] == E[vocab - 1]).all()
+            assert (out[b, o + 1:o + 1 + p.shape[0]] == p).all()
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 64), st.integers(1, 1500))
+def test_splice_index_map_is_a_bijection_onto_sources(t_txt, n_audio):
+    """S1 index contract (allm.py:165-170): row 0 <- <audio>, 1..A <- projected, A+1 <- </audio>, A+2+j <- text j."""
+    m = O.splice_index_map(t_txt, n_audio)
+    assert len(m) == n_audio + 2 + t_txt and len(np.unique(m)) == len(m)      # every source row used exactly once
+    assert m[0] == -1 and m[n_audio + 1] == -2
+    assert (m[1:1 + n_audio] - (1 << 40) == np.arange(n_audio)).all()
+    assert (m[n_audio + 2:] == np.arange(t_txt)).all()
