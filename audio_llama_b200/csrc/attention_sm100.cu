@@ -40,6 +40,46 @@ constexpr int POLY_PAIRS = 1;     // of every 4 pairs, how many use the FMA-pipe
 constexpr int ATT_BAR_P_FULL = 1;
 constexpr int ATT_BAR_S_EMPTY = 2;
 
+#ifdef ATT_TRACE
+// Development-only event timeline (tools/att_lab): lane 0 of each role of a few CTAs records (tag, kv tile, %clock).
+constexpr int TR_SLOTS = 32, TR_EVENTS = 256;
+__device__ uint32_t g_att_trace[TR_SLOTS][3][TR_EVENTS][2];
+__device__ uint32_t g_att_trace_n[TR_SLOTS][3];
+__device__ uint32_t g_att_trace_sm[TR_SLOTS];
+struct Tracer {
+  int slot, role, n;
+  __device__ Tracer(int role_, int lane) : role(role_), n(0) {
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    slot = lin < 16 ? lin : (lin >= 148 && lin < 164 ? lin - 132 : -1);
+    if (lane != 0) slot = -1;
+  }
+  __device__ __forceinline__ void ev(int tag, int j) {
+    if (slot >= 0 && n < TR_EVENTS) {
+      uint32_t c;
+      asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+      g_att_trace[slot][role][n][0] = (tag << 16) | j;
+      g_att_trace[slot][role][n][1] = c;
+      ++n;
+    }
+  }
+  __device__ void done() {
+    if (slot >= 0) {
+      g_att_trace_n[slot][role] = n;
+      uint32_t sm;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+      g_att_trace_sm[slot] = sm;
+    }
+  }
+};
+#define TR_DECL(role) Tracer tr(role, lane)
+#define TR(tag, j) tr.ev(tag, j)
+#define TR_DONE() tr.done()
+#else
+#define TR_DECL(role)
+#define TR(tag, j)
+#define TR_DONE()
+#endif
+
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -94,7 +134,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
   const int q0 = blockIdx.x * ATT_BQ;
   const int nkv = (T + ATT_BKV - 1) / ATT_BKV;
 
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int s = 0; s < ATT_K_STAGES; ++s) {
@@ -130,13 +170,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
     setmaxnreg_dec<48>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
-      if (lane == 0) {
+      TR_DECL(0);
+      if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows ONE thread issues and emits no per-lane waterfall loop around the uniform-datapath instructions
         // (Q and K_0 were requested by this same thread before the CTA-wide sync)
         // K runs ahead of V: K_{j+1} is requested before V_j so that Q K_{j+1}^T is never starved
         int ks = 1, vs = 0;
         uint32_t kph = 0, vph = 0;
         auto load_k = [&](int j) {
           mbar_wait(&k_empty[ks], kph ^ 1);
+          TR(1, j);
           mbar_arrive_expect_tx(&k_full[ks], ATT_TILE_BYTES);
           tma_load_3d(sK + ks * ATT_TILE_BYTES, &tmQKV, &k_full[ks], d + h * ATT_HD, j * ATT_BKV, b);
           if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
@@ -144,11 +186,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
         for (int j = 0; j < nkv; ++j) {
           if (j + 1 < nkv) load_k(j + 1);
           mbar_wait(&v_empty[vs], vph ^ 1);
+          TR(2, j);
           mbar_arrive_expect_tx(&v_full[vs], ATT_TILE_BYTES);
           tma_load_3d(sV + vs * ATT_TILE_BYTES, &tmQKV, &v_full[vs], 2 * d + h * ATT_HD, j * ATT_BKV, b);
           if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
         }
       }
+      TR_DONE();
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
@@ -174,29 +218,40 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
         umma_commit(&v_empty[stage]);
         umma_commit(o_full);
       };
+      TR_DECL(1);
+      TR(10, 0);
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      if (lane == 0) issue_s(0);
+      TR(11, 0);
+      if (elect_one()) issue_s(0);
       __syncwarp();
+      TR(12, 0);
       int ks = 1, vs = 0;                            // next K stage to consume, current V stage
       uint32_t kph = 0, vph = 0;
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
           mbar_wait(&k_full[ks], kph);
+          TR(13, j + 1);
           named_bar_sync(ATT_BAR_S_EMPTY, 160);        // blocks in hardware: no polling next to the softmax warps
           tc_fence_after();
-          if (lane == 0) issue_s(ks);
+          TR(11, j + 1);
+          if (elect_one()) issue_s(ks);
           __syncwarp();
+          TR(12, j + 1);
           if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
         }
         mbar_wait(&v_full[vs], vph);
+        TR(14, j);
         named_bar_sync(ATT_BAR_P_FULL, 160);
         tc_fence_after();
-        if (lane == 0) issue_o(vs, j == 0);
+        TR(15, j);
+        if (elect_one()) issue_o(vs, j == 0);
         __syncwarp();
+        TR(16, j);
         if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
       }
+      TR_DONE();
     }
   } else {
     // ------------------------------------------------------------------ softmax warpgroup
@@ -210,10 +265,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
     float m_ref = -INFINITY;                       // reference max, log2 units (score * log2 e)
     unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);   // row-sum accumulators (4 partial sums)
     const unsigned long long LOG2E2 = pk2(LOG2E, LOG2E);
+    TR_DECL(2);
+#ifdef ATT_TRACE
+    if (warp != 4) tr.slot = -1;
+#endif
 
     for (int j = 0; j < nkv; ++j) {
+      TR(20, j);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      TR(21, j);
       uint32_t s[128];
       {
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
@@ -227,6 +288,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
         tmem_ld_wait();
       }
       tc_fence_before();
+      TR(22, j);
       if (j + 1 < nkv) named_bar_arrive(ATT_BAR_S_EMPTY, 160);   // S is in registers: Q K_{j+1}^T may overwrite it now
       if (j == nkv - 1) {                          // kv tail: columns >= kv_valid are zero-filled K rows
         const int kv_valid = T - j * ATT_BKV;
@@ -297,18 +359,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
           pk[k >> 1] = pack_bf16(p0, p1);
         }
         if (c == 0 && !o_ready) {                  // P is still being read by the previous tile's P V until then
+          TR(23, j);
           mbar_wait(o_full, (j - 1) & 1);
           tc_fence_after();
+          TR(24, j);
         }
         tmem_st_32x16(tPi + c * 16, pk);
       }
+      TR(25, j);
       tmem_st_wait();
       tc_fence_before();
+      TR(26, j);
       named_bar_arrive(ATT_BAR_P_FULL, 160);
     }
     // normalise and store
     mbar_wait(o_full, (nkv - 1) & 1);
     tc_fence_after();
+    TR(27, nkv);
     float la, lb, lc, ld;
     unpk2(l2a, la, lb);
     unpk2(l2b, lc, ld);
@@ -332,12 +399,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
         }
       }
     }
+    TR(28, nkv);
+    TR_DONE();
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<256>(tmem_base);
 }
+
+#ifdef ATT_TRACE
+void att_trace_reset() {
+  static uint32_t zeros[TR_SLOTS][3];
+  memset(zeros, 0, sizeof(zeros));
+  cudaMemcpyToSymbol(g_att_trace_n, zeros, sizeof(zeros));
+}
+void att_trace_dump() {
+  static uint32_t ev[TR_SLOTS][3][TR_EVENTS][2];
+  static uint32_t n[TR_SLOTS][3], sm[TR_SLOTS];
+  cudaMemcpyFromSymbol(ev, g_att_trace, sizeof(ev));
+  cudaMemcpyFromSymbol(n, g_att_trace_n, sizeof(n));
+  cudaMemcpyFromSymbol(sm, g_att_trace_sm, sizeof(sm));
+  for (int s = 0; s < TR_SLOTS; ++s)
+    for (int r = 0; r < 3; ++r)
+      for (uint32_t i = 0; i < n[s][r]; ++i)
+        printf("TRACE slot %d sm %u role %d tag %u j %u clk %u\n", s, sm[s], r, ev[s][r][i][0] >> 16, ev[s][r][i][0] & 0xffff,
+               ev[s][r][i][1]);
+}
+#endif
 
 int launch_attention(const CUtensorMap& tm_qkv, void* out, int B, int T, int H, cudaStream_t stream) {
   static bool attr_set = false;
