@@ -32,13 +32,23 @@ constexpr int ATT_HD = 64;
 constexpr int ATT_K_STAGES = 3;
 constexpr int ATT_V_STAGES = 2;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;   // 16 KB: any of Q / K / V tile
-constexpr int ATT_SMEM = (1 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 256 + 1024;
+constexpr int ATT_THREADS = 384;                 // warps 0-3 control (TMA, MMA, TMEM allocator, idle), warps 4-11 softmax
+constexpr int ATT_CTRL_REGS = 32;
+constexpr int ATT_SOFTMAX_REGS = 104;
+constexpr int ATT_SMEM = (1 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 5 * 2 * 128 * 4 + 256 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
-constexpr float ATT_TAU = 8.0f;   // lazy-rescale threshold, log2 units
-constexpr int POLY_PAIRS = 1;     // of every 4 pairs, how many use the FMA-pipe exp2
-// softmax warps -> MMA warp hand-offs are named barriers (128 arrive + 32 sync); id 0 is __syncthreads
+constexpr int ATT_TAU_LOG2 = 40;          // the reference follows a tile whose probabilities summed to more than 2^40
+constexpr float ATT_RISK_SUM = 1.2676506e30f;   // 2^100: a tile sum this large sends the CTA's rows to the exact path
+#ifndef ATT_POLY_NUM
+#define ATT_POLY_NUM 1
+#define ATT_POLY_DEN 4
+#endif
+constexpr int POLY_NUM = ATT_POLY_NUM, POLY_DEN = ATT_POLY_DEN;   // of every DEN element pairs, NUM take exp2 on the FMA pipe
+// softmax warps -> MMA warp hand-offs are named barriers (256 arrive + 32 sync); id 0 is __syncthreads
 constexpr int ATT_BAR_P_FULL = 1;
 constexpr int ATT_BAR_S_EMPTY = 2;
+constexpr int ATT_BAR_SOFTMAX = 3;        // the 256 softmax threads among themselves
+constexpr int ATT_BAR_COUNT = 256 + 32;
 
 #ifdef ATT_TRACE
 // Development-only event timeline (tools/att_lab): lane 0 of each role of a few CTAs records (tag, kv tile, %clock).
@@ -109,86 +119,145 @@ __device__ __forceinline__ void poly_exp2_pair(unsigned long long x2, float& o0,
   o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
-__global__ void __launch_bounds__(256, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* __restrict__ out, int T, int H) {
+// Exact attention for ONE query row by one warp (plain loads, online softmax in fp32). Only used for the rows of a CTA in
+// which the fast path flagged a possible overflow of its lagged softmax reference (see the softmax warps below): a
+// score that outgrows the reference by more than 2^100 within two kv tiles. Slow, exact, practically never taken.
+__device__ __noinline__ void attention_row_exact(const __nv_bfloat16* __restrict__ qkv_b, __nv_bfloat16* __restrict__ out_row,
+                                                 int q, int T, int d, int h, int lane) {
+  const size_t ld = static_cast<size_t>(3) * d;
+  const uint4* qp = reinterpret_cast<const uint4*>(qkv_b + static_cast<size_t>(q) * ld + h * ATT_HD);
+  uint4 qv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qv[i] = __ldg(qp + i);
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int base = 0; base < T; base += 32) {
+    const int kv = base + lane;
+    float sc = -INFINITY;
+    if (kv < T) {
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv_b + static_cast<size_t>(kv) * ld + d + h * ATT_HD);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 kk = __ldg(kp + i);
+        const uint32_t qa[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+        const uint32_t ka[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc = fmaf(__uint_as_float(qa[e] << 16), __uint_as_float(ka[e] << 16), acc);
+          acc = fmaf(__uint_as_float(qa[e] & 0xffff0000u), __uint_as_float(ka[e] & 0xffff0000u), acc);
+        }
+      }
+      sc = acc * LOG2E;
+    }
+    const float m_new = fmaxf(m, warp_max(sc));
+    const float scale = exp2f(m - m_new);          // 0 on the first chunk
+    m = m_new;
+    const float p = exp2f(sc - m);                 // 0 for kv >= T
+    l = l * scale + p;
+    o0 *= scale;
+    o1 *= scale;
+    const int n = min(32, T - base);
+    for (int i = 0; i < n; ++i) {
+      const float pi = __shfl_sync(0xffffffffu, p, i);
+      const uint32_t vv = __ldg(reinterpret_cast<const uint32_t*>(qkv_b + static_cast<size_t>(base + i) * ld + 2 * d + h * ATT_HD) + lane);
+      o0 = fmaf(pi, __uint_as_float(vv << 16), o0);
+      o1 = fmaf(pi, __uint_as_float(vv & 0xffff0000u), o1);
+    }
+  }
+  l = warp_sum(l);
+  const float inv = 1.0f / l;
+  reinterpret_cast<uint32_t*>(out_row)[lane] = pack_bf16(o0 * inv, o1 * inv);
+}
+
+#ifdef ATT_CYCLES
+__device__ unsigned long long g_att_cycles[2];   // [0] sum over CTAs of (last - first clock), [1] CTAs
+#endif
+
+// Shared memory, as byte offsets from the 1024-aligned base (every address in the kernel is base + constant)
+constexpr uint32_t ATT_OFF_Q = 0;
+constexpr uint32_t ATT_OFF_K = ATT_TILE_BYTES;
+constexpr uint32_t ATT_OFF_V = ATT_OFF_K + ATT_K_STAGES * ATT_TILE_BYTES;
+constexpr uint32_t ATT_OFF_PART = ATT_OFF_V + ATT_V_STAGES * ATT_TILE_BYTES;   // [4 tiles + final][2 halves][128 rows] f32 sums
+constexpr uint32_t ATT_OFF_BARS = ATT_OFF_PART + 5 * 2 * ATT_BQ * 4;
+constexpr uint32_t ATT_BAR_Q_FULL = ATT_OFF_BARS;
+constexpr uint32_t ATT_BAR_K_FULL = ATT_BAR_Q_FULL + 8;
+constexpr uint32_t ATT_BAR_K_EMPTY = ATT_BAR_K_FULL + 8 * ATT_K_STAGES;
+constexpr uint32_t ATT_BAR_V_FULL = ATT_BAR_K_EMPTY + 8 * ATT_K_STAGES;
+constexpr uint32_t ATT_BAR_V_EMPTY = ATT_BAR_V_FULL + 8 * ATT_V_STAGES;
+constexpr uint32_t ATT_BAR_S_FULL = ATT_BAR_V_EMPTY + 8 * ATT_V_STAGES;         // "S drained" / "P stored" are named barriers
+constexpr uint32_t ATT_BAR_O_FULL = ATT_BAR_S_FULL + 8;
+constexpr uint32_t ATT_OFF_TMEM_PTR = ATT_BAR_O_FULL + 8;
+constexpr uint32_t ATT_OFF_EXACT = ATT_OFF_TMEM_PTR + 4;                        // "a row of this tile needs the exact path"
+static_assert(ATT_OFF_EXACT + 4 + 1024 <= ATT_SMEM, "shared-memory carve-up exceeds ATT_SMEM");
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ qkv,
+                     __nv_bfloat16* __restrict__ out, int T, int H) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // 1 tile
-  uint8_t* sK = smem + ATT_TILE_BYTES;                  // K ring
-  uint8_t* sV = sK + ATT_K_STAGES * ATT_TILE_BYTES;     // V ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_V_STAGES * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;                              // 1
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + ATT_K_STAGES;
-  uint64_t* v_full = k_empty + ATT_K_STAGES;
-  uint64_t* v_empty = v_full + ATT_V_STAGES;
-  uint64_t* s_full = v_empty + ATT_V_STAGES;            // "S drained" and "P stored" are named barriers (see below)
-  uint64_t* o_full = s_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 1);
+  const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);   // the one base register
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int d = H * ATT_HD;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int q0 = blockIdx.x * ATT_BQ;
+#ifdef ATT_CYCLES
+  const long long cyc0 = clock64();
+#endif
   const int nkv = (T + ATT_BKV - 1) / ATT_BKV;
 
+  // elect.sync, not threadIdx.x == 0: ptxas then knows ONE thread runs the branch and emits no per-lane "waterfall"
+  // loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) around every uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR) --
+  // with lane == 0 each MMA cost ~110 cycles to issue and the issue itself was the critical path of the kernel.
   if (warp == 0 && elect_one()) {
+    const int d = H * ATT_HD, h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * ATT_BQ;
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < ATT_K_STAGES; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-    }
-    for (int s = 0; s < ATT_V_STAGES; ++s) {
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(o_full, 1);
+    for (uint32_t a = ATT_BAR_Q_FULL; a <= ATT_BAR_O_FULL; a += 8) mbar_init_a(sb + a, 1);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(sb + ATT_OFF_EXACT), "r"(0u) : "memory");
     fence_barrier_init();
     // the first loads need nothing but their barriers: they start before the TMEM allocation and the CTA-wide sync
-    mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-    tma_load_3d(sQ, &tmQKV, q_full, h * ATT_HD, q0, b);
-    mbar_arrive_expect_tx(&k_full[0], ATT_TILE_BYTES);
-    tma_load_3d(sK, &tmQKV, &k_full[0], d + h * ATT_HD, 0, b);
+    mbar_arrive_expect_tx_a(sb + ATT_BAR_Q_FULL, ATT_TILE_BYTES);
+    tma_load_3d_a(sb + ATT_OFF_Q, &tmQKV, sb + ATT_BAR_Q_FULL, h * ATT_HD, q0, b);
+    mbar_arrive_expect_tx_a(sb + ATT_BAR_K_FULL, ATT_TILE_BYTES);
+    tma_load_3d_a(sb + ATT_OFF_K, &tmQKV, sb + ATT_BAR_K_FULL, d + h * ATT_HD, 0, b);
   }
-  if (warp == 2) tmem_alloc<256>(tmem_ptr);
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + ATT_OFF_TMEM_PTR), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tS = tmem_base;            // 128 columns
-  const uint32_t tO = tmem_base + 128;      // 64 columns
-  const uint32_t tP = tmem_base + 192;      // 64 columns (bf16 pairs: 128 kv -> 64 columns)
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + ATT_OFF_TMEM_PTR) : "memory");
+  // TMEM columns: S 0..127 | O 128..191 | P 192..255 (bf16 pairs: 128 kv -> 64 columns)
 
-  // Register budget: launched with 128 regs x 256 threads (2 CTAs / SM). The 4 control warps drop to 48, which
-  // frees 80 x 128 = 10240 registers; the 4 softmax warps grow to 208, which takes 80 x 128 = 10240. (Asking for
-  // more than was freed makes setmaxnreg.inc wait forever.)
+  // Register budget: launched with 80 regs x 384 threads (2 CTAs / SM). The control warpgroup drops to 32, which frees
+  // 48 x 128 = 6144 registers; the 8 softmax warps grow to 104, which takes 24 x 256 = 6144. (Asking for more than was
+  // freed makes setmaxnreg.inc wait forever.)
   if (warp < 4) {
-    setmaxnreg_dec<48>();
+    setmaxnreg_dec<ATT_CTRL_REGS>();
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       TR_DECL(0);
-      if (elect_one()) {   // elect.sync, not lane == 0: ptxas then knows ONE thread issues and emits no per-lane waterfall loop around the uniform-datapath instructions
+      if (elect_one()) {
+        const int d = H * ATT_HD, h = blockIdx.y, b = blockIdx.z;
         // (Q and K_0 were requested by this same thread before the CTA-wide sync)
         // K runs ahead of V: K_{j+1} is requested before V_j so that Q K_{j+1}^T is never starved
         int ks = 1, vs = 0;
         uint32_t kph = 0, vph = 0;
-        auto load_k = [&](int j) {
-          mbar_wait(&k_empty[ks], kph ^ 1);
-          TR(1, j);
-          mbar_arrive_expect_tx(&k_full[ks], ATT_TILE_BYTES);
-          tma_load_3d(sK + ks * ATT_TILE_BYTES, &tmQKV, &k_full[ks], d + h * ATT_HD, j * ATT_BKV, b);
-          if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
-        };
+#pragma unroll 1
         for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) load_k(j + 1);
-          mbar_wait(&v_empty[vs], vph ^ 1);
+          if (j + 1 < nkv) {
+            mbar_wait_a(sb + ATT_BAR_K_EMPTY + 8 * ks, kph ^ 1);
+            TR(1, j + 1);
+            mbar_arrive_expect_tx_a(sb + ATT_BAR_K_FULL + 8 * ks, ATT_TILE_BYTES);
+            tma_load_3d_a(sb + ATT_OFF_K + ks * ATT_TILE_BYTES, &tmQKV, sb + ATT_BAR_K_FULL + 8 * ks, d + h * ATT_HD,
+                          (j + 1) * ATT_BKV, b);
+            if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
+          }
+          mbar_wait_a(sb + ATT_BAR_V_EMPTY + 8 * vs, vph ^ 1);
           TR(2, j);
-          mbar_arrive_expect_tx(&v_full[vs], ATT_TILE_BYTES);
-          tma_load_3d(sV + vs * ATT_TILE_BYTES, &tmQKV, &v_full[vs], 2 * d + h * ATT_HD, j * ATT_BKV, b);
+          mbar_arrive_expect_tx_a(sb + ATT_BAR_V_FULL + 8 * vs, ATT_TILE_BYTES);
+          tma_load_3d_a(sb + ATT_OFF_V + vs * ATT_TILE_BYTES, &tmQKV, sb + ATT_BAR_V_FULL + 8 * vs, 2 * d + h * ATT_HD,
+                        j * ATT_BKV, b);
           if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
         }
       }
@@ -197,31 +266,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
       constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t k_addr = smem_u32(sK);
-      const uint32_t v_addr = smem_u32(sV);
+      const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
       auto issue_s = [&](int stage) {
-        const uint64_t qd = umma_desc_sw128(q_addr, 16, 1024);
-        const uint64_t kd = umma_desc_sw128(k_addr + stage * ATT_TILE_BYTES, 16, 1024);
+        const uint64_t qd = umma_desc_sw128(sb + ATT_OFF_Q, 16, 1024);
+        const uint64_t kd = umma_desc_sw128(sb + ATT_OFF_K + stage * ATT_TILE_BYTES, 16, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
-        umma_commit(&k_empty[stage]);          // the K stage is free once these MMAs have run
-        umma_commit(s_full);
+        umma_commit_a(sb + ATT_BAR_K_EMPTY + 8 * stage);   // the K stage is free once these MMAs have run
+        umma_commit_a(sb + ATT_BAR_S_FULL);
       };
       auto issue_o = [&](int stage, bool first_tile) {
         // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B
         // = +128 in the descriptor's (>>4) start-address field.
-        const uint64_t vd = umma_desc_sw128(v_addr + stage * ATT_TILE_BYTES, 1024, 1024);
+        const uint64_t vd = umma_desc_sw128(sb + ATT_OFF_V + stage * ATT_TILE_BYTES, 1024, 1024);
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
           umma_ts(tO, tP + k * 8, vd + 128 * k, IDESC_O, (k != 0) || !first_tile);
-        umma_commit(&v_empty[stage]);
-        umma_commit(o_full);
+        umma_commit_a(sb + ATT_BAR_V_EMPTY + 8 * stage);
+        umma_commit_a(sb + ATT_BAR_O_FULL);
       };
       TR_DECL(1);
       TR(10, 0);
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      mbar_wait_a(sb + ATT_BAR_Q_FULL, 0);
+      mbar_wait_a(sb + ATT_BAR_K_FULL, 0);
       tc_fence_after();
       TR(11, 0);
       if (elect_one()) issue_s(0);
@@ -229,11 +296,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       TR(12, 0);
       int ks = 1, vs = 0;                            // next K stage to consume, current V stage
       uint32_t kph = 0, vph = 0;
+#pragma unroll 1
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
-          mbar_wait(&k_full[ks], kph);
+          mbar_wait_a(sb + ATT_BAR_K_FULL + 8 * ks, kph);
           TR(13, j + 1);
-          named_bar_sync(ATT_BAR_S_EMPTY, 160);        // blocks in hardware: no polling next to the softmax warps
+          named_bar_sync(ATT_BAR_S_EMPTY, ATT_BAR_COUNT);   // blocks in hardware: no polling next to the softmax warps
           tc_fence_after();
           TR(11, j + 1);
           if (elect_one()) issue_s(ks);
@@ -241,9 +309,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
           TR(12, j + 1);
           if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
         }
-        mbar_wait(&v_full[vs], vph);
+        mbar_wait_a(sb + ATT_BAR_V_FULL + 8 * vs, vph);
         TR(14, j);
-        named_bar_sync(ATT_BAR_P_FULL, 160);
+        named_bar_sync(ATT_BAR_P_FULL, ATT_BAR_COUNT);
         tc_fence_after();
         TR(15, j);
         if (elect_one()) issue_o(vs, j == 0);
@@ -254,138 +322,172 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
       TR_DONE();
     }
   } else {
-    // ------------------------------------------------------------------ softmax warpgroup
-    setmaxnreg_inc<208>();
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tSi = tS + lane_off;
-    const uint32_t tOi = tO + lane_off;
-    const uint32_t tPi = tP + lane_off;
-    float m_ref = -INFINITY;                       // reference max, log2 units (score * log2 e)
-    unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);   // row-sum accumulators (4 partial sums)
-    const unsigned long long LOG2E2 = pk2(LOG2E, LOG2E);
+    // ------------------------------------------------------------------ softmax: 8 warps, TWO threads per query row
+    // Warps 4-7 take kv columns 0..63 of every 128-wide score tile, warps 8-11 columns 64..127 (a warp may only touch the
+    // TMEM lane quarter warp % 4). Four softmax warps per scheduler (two CTAs per SM) instead of two hide the
+    // fixed-latency stalls of the exp chains; 64 scores per thread fit 104 registers.
+    //
+    // No row maximum. The two threads of a row would have to exchange it before the first exp; instead the exponent
+    // reference r = r0 + K (log2 units) is LAGGED: r0 is the row's first score, and K is raised at the start of tile j
+    // from the sum of tile j-2's probabilities (both halves, through shared memory -- visible by then without an extra
+    // barrier: each half publishes its sum before it arrives on "P stored", and the other half has since waited for the
+    // commit of the P V product that arrival released). sum <= 128 max, so floor(log2 sum) stands for the maximum to
+    // within 7 binary orders, which is all a reference needs: it only keeps the numbers inside fp32 / bf16 range; the
+    // result O / l is exact for any reference. K moves by integers (exact power-of-two rescale of O and l) and only
+    // when the tile outgrew the reference by 2^40.
+    // What a lagged reference cannot rule out is a score more than 2^100 above it (a jump of ~69 in the natural-log
+    // domain inside two kv tiles, or over the row's first score): such a row's sums reach 2^100 / inf, the thread raises
+    // a flag, and the CTA recomputes its rows with attention_row_exact after the fast path. Never seen on real
+    // attention scores; tests/test_gpu_attention.py forces it.
+    setmaxnreg_inc<ATT_SOFTMAX_REGS>();
+    const int half = (warp - 4) >> 2;
+    const uint32_t row = (warp & 3) * 32 + lane;
+    // per-thread TMEM base (lane quarter in bits 16+): S at tSi (this half's 64 columns), O at tOP + 128, P at tOP + 192
+    const uint32_t tOP = opaque_u32(tmem_base + ((row & ~31u) << 16) + half * 32);
+    const uint32_t tSi = opaque_u32(tOP + half * 32);
+    // tile sums: slot * 1024 + half * 512 + row * 4
+    const uint32_t my_part = opaque_u32(sb + ATT_OFF_PART + half * (ATT_BQ * 4) + row * 4);
+    const uint32_t other_part = my_part ^ (ATT_BQ * 4);      // (ATT_OFF_PART is a multiple of 1024)
     TR_DECL(2);
 #ifdef ATT_TRACE
     if (warp != 4) tr.slot = -1;
 #endif
+    // reference base r0: the row's first score (column 0 of tile 0), the same for both halves, log2 units
+    float neg_r0;
+    {
+      mbar_wait_a(sb + ATT_BAR_S_FULL, 0);
+      tc_fence_after();
+      uint32_t s_first[1];
+      tmem_ld_32x1(tSi - half * 64, s_first);
+      tmem_ld_wait();
+      neg_r0 = -__uint_as_float(s_first[0]) * LOG2E;
+    }
+    int k_m1 = 0, k_m2 = 0;                        // integer reference offsets of tiles j-1 and j-2
+    unsigned long long l2 = pk2(0.f, 0.f);         // this half's row sum (two partial sums), relative to r0 + k_m1
+    float biggest = 0.f;                           // largest tile sum seen (inf sticks): the overflow sentinel
+    const unsigned long long LOG2E2 = pk2(LOG2E, LOG2E);
 
+    // 16 scores -> 8 packed bf16 pairs of probabilities; KB = first column (decides which pairs take the FMA-pipe exp2)
+#define ATT_EXPS16(sv, pv, KB)                                                                                        \
+  _Pragma("unroll") for (int k = (KB); k < (KB) + 16; k += 2) {                                                        \
+    const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), LOG2E2, nm2);         \
+    float p0, p1;                                                                                                      \
+    if (((k >> 1) % POLY_DEN) < POLY_NUM) {                                                                            \
+      poly_exp2_pair(x2, p0, p1);                                                                                      \
+    } else {                                                                                                           \
+      float x0, x1;                                                                                                    \
+      unpk2(x2, x0, x1);                                                                                               \
+      p0 = fast_exp2(x0);                                                                                              \
+      p1 = fast_exp2(x1);                                                                                              \
+    }                                                                                                                  \
+    if ((k >> 1) & 1) t2b = fadd2(t2b, pk2(p0, p1));                                                                   \
+    else t2a = fadd2(t2a, pk2(p0, p1));                                                                                \
+    pv[k >> 1] = pack_bf16(p0, p1);                                                                                    \
+  }
+
+#pragma unroll 1
     for (int j = 0; j < nkv; ++j) {
       TR(20, j);
-      mbar_wait(s_full, j & 1);
+      mbar_wait_a(sb + ATT_BAR_S_FULL, j & 1);
       tc_fence_after();
       TR(21, j);
-      uint32_t s[128];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-        tmem_ld_32x32(tSi, s0);
-        tmem_ld_32x32(tSi + 32, s1);
-        tmem_ld_32x32(tSi + 64, s2);
-        tmem_ld_32x32(tSi + 96, s3);
-        tmem_ld_wait();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32(tSi, s0);
+      // reference offset of this tile, from the sums of tile j-2 (under the TMEM load)
+      int k_cur = k_m1;
+      if (j >= 2) {
+        const uint32_t slot = ((j + 2) & 3) * 1024;
+        const float tsum = lds_f32(my_part + slot) + lds_f32(other_part + slot);                 // both halves, relative to k_m2
+        const int mag = k_m2 + static_cast<int>((__float_as_uint(tsum) >> 23) & 0xff) - 127;     // ~ log2 of the largest p
+        if (mag > k_m1 + ATT_TAU_LOG2) k_cur = mag - 4;
       }
+      const int dk = k_cur - k_m1;                                           // 0, or >= ATT_TAU_LOG2 - 3
+      k_m2 = k_m1;
+      k_m1 = k_cur;
+      const float nm = neg_r0 - static_cast<float>(k_cur);
+      const unsigned long long nm2 = pk2(nm, nm);
+      const int kv_valid = T - j * ATT_BKV - half * 64;                      // < 64 only in the last tile: zero-filled K rows
+      tmem_ld_wait_regs(s0);
+      if (kv_valid < 32) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          if (k >= kv_valid) s0[k] = 0xff800000u;  // -inf
+      }
+      // p = 2^(s*log2e - r); P -> TMEM as bf16 (columns kk/2), tile sums in fp32
+      unsigned long long t2a = pk2(0.f, 0.f), t2b = pk2(0.f, 0.f);
+      uint32_t pa[16], pb[16];
+      ATT_EXPS16(s0, pa, 0);
+      tmem_ld_32x32(tSi + 32, s1);                 // the other 32 scores land under the second quarter's exps
+      ATT_EXPS16(s0, pa, 16);
+      tmem_ld_wait_regs(s1);
       tc_fence_before();
       TR(22, j);
-      if (j + 1 < nkv) named_bar_arrive(ATT_BAR_S_EMPTY, 160);   // S is in registers: Q K_{j+1}^T may overwrite it now
-      if (j == nkv - 1) {                          // kv tail: columns >= kv_valid are zero-filled K rows
-        const int kv_valid = T - j * ATT_BKV;
-        if (kv_valid < ATT_BKV) {
+      if (j + 1 < nkv) named_bar_arrive(ATT_BAR_S_EMPTY, ATT_BAR_COUNT);   // S is in registers: Q K_{j+1}^T may overwrite it
+      if (kv_valid < 64) {
 #pragma unroll
-          for (int k = 0; k < 128; ++k)
-            if (k >= kv_valid) s[k] = 0xff800000u;  // -inf
+        for (int k = 0; k < 32; ++k)
+          if (k + 32 >= kv_valid) s1[k] = 0xff800000u;
+      }
+      ATT_EXPS16(s1, pb, 0);
+      ATT_EXPS16(s1, pb, 16);
+      const bool rescale = __any_sync(0xffffffffu, dk != 0);
+      float down = 1.0f;
+      if (rescale) {                                                         // rare
+        if (dk != 0) down = dk < 127 ? __int_as_float((127 - dk) << 23) : 0.f;   // 2^-dk, exact
+        l2 = fmul2(l2, pk2(down, down));
+      }
+      {
+        const unsigned long long t2 = fadd2(t2a, t2b);
+        l2 = fadd2(l2, t2);
+        float ta, tb;
+        unpk2(t2, ta, tb);
+        const float tsum = ta + tb;
+        sts_f32(my_part + (j & 3) * 1024, tsum);
+        biggest = fmaxf(biggest, tsum);
+      }
+      if (j > 0) {                                 // P is still being read by the previous tile's P V until then
+        TR(23, j);
+        mbar_wait_a(sb + ATT_BAR_O_FULL, (j - 1) & 1);
+        tc_fence_after();
+        TR(24, j);
+        if (rescale) {                             // rare: O (this half's 32 columns) follows the reference
+          uint32_t r[32];
+          tmem_ld_32x32(tOP + 128, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * down);
+          tmem_st_32x32(tOP + 128, r);
         }
       }
-      // row max: 4 independent FMNMX3 chains
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int k = 4; k < 128; k += 8) {
-        mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-        mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-        if (k + 4 < 128) {
-          mx2 = fmax3(mx2, __uint_as_float(s[k + 4]), __uint_as_float(s[k + 5]));
-          mx3 = fmax3(mx3, __uint_as_float(s[k + 6]), __uint_as_float(s[k + 7]));
-        }
-      }
-      const float mx_s = fmaxf(fmax3(mx0, mx1, mx2), mx3) * LOG2E;
-      bool o_ready = (j == 0);
-      if (__any_sync(0xffffffffu, mx_s > m_ref + ATT_TAU)) {
-        // advance the reference (whole warp, so the TMEM ld/st below stay warp-uniform) and rescale l and O
-        const float new_ref = fmaxf(m_ref, mx_s);
-        const float scale = fast_exp2(m_ref - new_ref);        // 0 on the first tile (m_ref = -inf)
-        m_ref = new_ref;
-        const unsigned long long sc2 = pk2(scale, scale);
-        l2a = fmul2(l2a, sc2);
-        l2b = fmul2(l2b, sc2);
-        if (j > 0) {
-          mbar_wait(o_full, (j - 1) & 1);                      // P V of the previous tile has landed in O
-          tc_fence_after();
-          o_ready = true;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tOi + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * scale);
-            tmem_st_32x32(tOi + c * 32, r);
-          }
-          tmem_st_wait();
-        }
-      }
-      const float nm = -m_ref;
-      const unsigned long long nm2 = pk2(nm, nm);
-      // p = 2^(s*log2e - m_ref); P -> TMEM as bf16 (columns kk/2), row sums in fp32
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const int idx = c * 32 + k;
-          const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[idx]), __uint_as_float(s[idx + 1])), LOG2E2, nm2);
-          float p0, p1;
-          if (((k >> 1) & 3) < POLY_PAIRS) {
-            poly_exp2_pair(x2, p0, p1);
-          } else {
-            float x0, x1;
-            unpk2(x2, x0, x1);
-            p0 = fast_exp2(x0);
-            p1 = fast_exp2(x1);
-          }
-          if ((k >> 1) & 1) l2b = fadd2(l2b, pk2(p0, p1));
-          else l2a = fadd2(l2a, pk2(p0, p1));
-          pk[k >> 1] = pack_bf16(p0, p1);
-        }
-        if (c == 0 && !o_ready) {                  // P is still being read by the previous tile's P V until then
-          TR(23, j);
-          mbar_wait(o_full, (j - 1) & 1);
-          tc_fence_after();
-          TR(24, j);
-        }
-        tmem_st_32x16(tPi + c * 16, pk);
-      }
+      tmem_st_32x16(tOP + 192, pa);
+      tmem_st_32x16(tOP + 192 + 16, pb);
       TR(25, j);
       tmem_st_wait();
       tc_fence_before();
       TR(26, j);
-      named_bar_arrive(ATT_BAR_P_FULL, 160);
+      named_bar_arrive(ATT_BAR_P_FULL, ATT_BAR_COUNT);
     }
-    // normalise and store
-    mbar_wait(o_full, (nkv - 1) & 1);
+    // the two halves of a row: total l, and whether any row of the tile needs the exact path
+    {
+      float la, lb;
+      unpk2(l2, la, lb);
+      sts_f32(my_part + 4 * 1024, la + lb);      // slot 4: the tile-sum slots may still be read by the other half
+      if (!(biggest < ATT_RISK_SUM)) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sb + ATT_OFF_EXACT), "r"(1u) : "memory");
+    }
+    named_bar_sync(ATT_BAR_SOFTMAX, 256);
+    const float inv_l = 1.0f / (lds_f32(my_part + 4 * 1024) + lds_f32(other_part + 4 * 1024));
+    uint32_t exact;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(exact) : "r"(sb + ATT_OFF_EXACT) : "memory");
+    // normalise and store this half's 32 columns
+    mbar_wait_a(sb + ATT_BAR_O_FULL, (nkv - 1) & 1);
     tc_fence_after();
     TR(27, nkv);
-    float la, lb, lc, ld;
-    unpk2(l2a, la, lb);
-    unpk2(l2b, lc, ld);
-    const float inv_l = 1.0f / ((la + lb) + (lc + ld));
-    const int q = q0 + row;
-    uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q) * d + h * ATT_HD);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    const int d = H * ATT_HD, h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * ATT_BQ;
+    {
+      const int q = q0 + row;
+      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q) * d + h * ATT_HD + half * 32);
       uint32_t r[32];
-      tmem_ld_32x32(tOi + c * 32, r);
+      tmem_ld_32x32(tOP + 128, r);
       tmem_ld_wait();
       if (q < T) {
 #pragma unroll
@@ -395,19 +497,40 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, __nv_bfloat16* _
           v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * inv_l, __uint_as_float(r[8 * u + 3]) * inv_l);
           v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * inv_l, __uint_as_float(r[8 * u + 5]) * inv_l);
           v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * inv_l, __uint_as_float(r[8 * u + 7]) * inv_l);
-          dst[c * 4 + u] = v;
+          dst[u] = v;
         }
       }
     }
     TR(28, nkv);
     TR_DONE();
+    if (exact) {
+      named_bar_sync(ATT_BAR_SOFTMAX, 256);        // every fast-path store of the tile is out before it is overwritten
+      const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * T * 3 * d;
+      for (int r = warp - 4; r < ATT_BQ && q0 + r < T; r += 8)
+        attention_row_exact(qkv_b, out + (static_cast<size_t>(b) * T + q0 + r) * d + h * ATT_HD, q0 + r, T, d, h, lane);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<256>(tmem_base);
+#ifdef ATT_CYCLES
+  if (threadIdx.x == 0) {
+    atomicAdd(&g_att_cycles[0], static_cast<unsigned long long>(clock64() - cyc0));
+    atomicAdd(&g_att_cycles[1], 1ull);
+  }
+#endif
 }
 
+#ifdef ATT_CYCLES
+void att_cycles_read(unsigned long long* out2, bool reset) {
+  cudaMemcpyFromSymbol(out2, g_att_cycles, 16);
+  if (reset) {
+    unsigned long long z[2] = {0, 0};
+    cudaMemcpyToSymbol(g_att_cycles, z, 16);
+  }
+}
+#endif
 #ifdef ATT_TRACE
 void att_trace_reset() {
   static uint32_t zeros[TR_SLOTS][3];
@@ -428,14 +551,15 @@ void att_trace_dump() {
 }
 #endif
 
-int launch_attention(const CUtensorMap& tm_qkv, void* out, int B, int T, int H, cudaStream_t stream) {
+int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
-  attention_fwd_kernel<<<grid, 256, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<__nv_bfloat16*>(out), T, H);
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), T, H);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -119,7 +119,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one per CTA)
-    if (lane == 0) {
+    // elect.sync (not lane == 0): ptxas then knows a single thread runs this and emits no per-lane "waterfall" loop
+    // (ELECT / R2UR.BROADCAST / BRA.U.ANY) around every uniform-datapath instruction (UTMALDG, UTCHMMA, UTCBAR)
+    if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
       for (int t = worker; t < num_tiles; t += n_workers) {
@@ -179,7 +181,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           // K-major: +32 B per UMMA_K inside the 128 B swizzle atom = +2 in the >>4 field.
           // MN-major (TN): atoms of 64 columns 8192 B apart (LBO), 8-row groups 1024 B apart (SBO); one UMMA_K = 16 rows
           // = 2048 B = +128.
@@ -316,7 +318,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // stage into 128B-swizzled smem (row = 128 B; 16 B unit u of row r lives at u ^ (r & 7))
-        if (etid == 0) tma_wait_group_read<0>();   // this warpgroup's previous store has drained the buffer
+        // (bulk async-groups belong to the issuing thread: elect.sync with the full mask always elects the same lane)
+        if (etid < 32 && elect_one()) tma_wait_group_read<0>();   // this warpgroup's previous store has drained the buffer
         named_bar_sync(1 + 2 * wg, 128);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -332,7 +335,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         fence_proxy_async_smem();
         named_bar_sync(2 + 2 * wg, 128);
-        if (etid == 0 && m0 < p.m_per_batch) {     // (pair: the peer's rows may lie wholly past the end)
+        if (etid < 32 && m0 < p.m_per_batch && elect_one()) {     // (pair: the peer's rows may lie wholly past the end)
           if constexpr (REDUCE) tma_reduce_add_3d(&tmO, stg, col0, m0, b);
           else tma_store_3d(&tmO, stg, col0, m0, b);
           tma_commit_group();
@@ -343,7 +346,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
-    if (etid == 0) tma_wait_group<0>();
+    if (etid < 32 && elect_one()) tma_wait_group<0>();
   }
 
   tc_fence_before();

@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
     setmaxnreg_dec<48>();
     if (warp == 0) {
       // ---------------------------------------------------------------- loader
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(b_full, MEL_TC_B_BYTES);
         bulk_g2s(sB, p.b_image + static_cast<size_t>(rank) * MEL_TC_B_BYTES, MEL_TC_B_BYTES, b_full);
       }
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
           // copy; its 34 x 164 box is exactly the slot image (the 4 "pad" floats of a row are the next row's first
           // samples). Everything it reads must be real audio: the scale scan looks at the whole slot.
           if (p.use_tmap && s_first >= 0 && s_first + TC_NSEG * TC_SEG + 4 <= nv) {
-            if (lane == 0) {
+            if (elect_one()) {
               mbar_arrive_expect_tx(&slot_full[slot], TC_SLOT_FLOATS * 4);
               tma_load_3d(dst, &tm_wave, &slot_full[slot], 0, f0 - 2, b);
             }
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
           const uint32_t es = n_use & 1;
           mbar_wait(&e_full[es], (n_use >> 1) & 1);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {   // elect.sync: a single-thread branch ptxas can see (no waterfall loop around each UTCHMMA)
             const uint32_t a0 = tmem_base + TC_A_E + 32 * es;
             products(tmem_base + TC_D_C, a0, 0, j);
             products(tmem_base + TC_D_S, a0 + 16, 1, j);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
         mbar_wait(o_full, it & 1);
         mbar_wait(&d_drained[0], it & 1);           // the even-bin accumulators have been read
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
 #pragma unroll 1
           for (int j = 0; j < 7; ++j) {
             const uint32_t a0 = tmem_base + TC_A_O + 32 * j;

@@ -15,6 +15,14 @@
 #define ATT_SRC "../../audio_llama_b200/csrc/attention_sm100.cu"
 #endif
 #include ATT_SRC
+#ifndef ATT_LAB_CTAS_PER_SM
+#define ATT_LAB_CTAS_PER_SM 2
+#endif
+#ifdef ATT_LAB_OLDSIG
+#define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, o, B, T, H, 0)
+#else
+#define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, q, o, B, T, H, 0)
+#endif
 
 namespace al {
 static char g_err[512];
@@ -109,7 +117,7 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
     printf("tmap: %s\n", al::g_err);
     return 1;
   }
-  int rc = al::launch_attention(tm, dout, B, T, H, 0);
+  int rc = ATT_LAUNCH(tm, dq, dout, B, T, H);
   if (rc) {
     printf("launch failed: %s\n", al::g_err);
     return 1;
@@ -165,9 +173,14 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) al::launch_attention(tm, dout, B, T, H, 0);
+    for (int i = 0; i < 3; ++i) ATT_LAUNCH(tm, dq, dout, B, T, H);
+#ifdef ATT_CYCLES
+    unsigned long long cy[2];
+    CK(cudaDeviceSynchronize());
+    al::att_cycles_read(cy, true);
+#endif
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < iters; ++i) al::launch_attention(tm, dout, B, T, H, 0);
+    for (int i = 0; i < iters; ++i) ATT_LAUNCH(tm, dq, dout, B, T, H);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms;
@@ -175,6 +188,20 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
     ms /= iters;
     const double fl = 4.0 * T * T * H * 64 * B;
     printf("time B=%d T=%d H=%d: %.4f ms  %.1f TFLOP/s\n", B, T, H, ms, fl / ms / 1e9);
+#ifdef ATT_CYCLES
+    {
+      al::att_cycles_read(cy, true);
+      int nsm = 0, occ = 0;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+      // CTA-cycles summed over CTAs / (resident CTAs per SM * SMs) ~ kernel cycles when the grid keeps every slot busy
+      const double cta_cyc = (double)cy[0] / (double)cy[1];
+      const double tiles_per_cta = (T + 127) / 128;
+      const double kcyc = (double)cy[0] / iters / (ATT_LAB_CTAS_PER_SM * nsm);
+      printf("cycles: %.0f per CTA (%.0f per kv tile), ~%.0f kernel cycles -> %.0f MHz effective, %.0f cycles per 128x128 tile per SM\n",
+             cta_cyc, cta_cyc / tiles_per_cta, kcyc, kcyc / (ms * 1e3), cta_cyc / tiles_per_cta / ATT_LAB_CTAS_PER_SM);
+      (void)occ;
+    }
+#endif
   }
   cudaFree(dq);
   cudaFree(dout);
@@ -184,6 +211,10 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
 int main(int argc, char** argv) {
   const char* name = argc > 1 ? argv[1] : "variant";
   printf("== %s\n", name);
+  if (argc > 2 && !strcmp(argv[2], "prof")) {   // one short case for ncu
+    run_case(argc > 3 ? atoi(argv[3]) : 8, 1500, 20, 1.0f, 1, false);
+    return 0;
+  }
   int fails = 0;
   const int cases[][3] = {{1, 128, 1}, {1, 256, 2}, {2, 300, 3}, {1, 1500, 6}, {1, 92, 1}, {1, 1000, 2}, {3, 100, 40}, {2, 1500, 20}};
   const float qs[] = {1.0f, 1.0f, 2.0f, 1.0f, 1.0f, 0.2f, 1.0f, 3.0f};
@@ -195,7 +226,7 @@ int main(int argc, char** argv) {
   run_case(4, 1500, 20, 1.0f, 0, false);
   al::att_trace_dump();
 #endif
-  run_case(32, 1500, 20, 1.0f, 20, false);
+  run_case(32, 1500, 20, 1.0f, argc > 2 ? atoi(argv[2]) : 20, false);
   printf("== %s: %s\n", name, fails ? "FAILED" : "all checks ok");
   return fails ? 1 : 0;
 }
