@@ -559,7 +559,7 @@ int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t st
   const uint64_t d3 = (uint64_t)3 * H * 64;
   int rc = tmap_rows3d(&tm, qkv, 2, d3, T, B, d3, d3 * T, 64, 128);
   if (rc) return rc;
-  rc = launch_attention(tm, qkv, out, B, T, H, (cudaStream_t)stream);
+  rc = launch_attention(tm, qkv, out, B, T, H, 0, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -734,7 +734,7 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
       p.m_per_batch = rows; p.batch = 1; p.N = 3 * d; p.K = d; p.bias = w.bqkv;
       RUN(AL_K_QKV, launch_gemm(e->tm_xn_A, w.tm_wqkv, e->tm_qkv_O, p, 0, nsm, st));
     }
-    RUN(AL_K_ATTN, launch_attention(e->tm_qkv_att, e->qkv, e->attn, B, 1500, e->H, st));
+    RUN(AL_K_ATTN, launch_attention(e->tm_qkv_att, e->qkv, e->attn, B, 1500, e->H, 0, st));
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = d; p.bias = w.bo;

@@ -38,6 +38,7 @@ constexpr int ATT_SOFTMAX_REGS = 104;
 constexpr int ATT_SMEM = (1 + ATT_K_STAGES + ATT_V_STAGES) * ATT_TILE_BYTES + 5 * 2 * 128 * 4 + 256 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int ATT_TAU_LOG2 = 40;          // the reference follows a tile whose probabilities summed to more than 2^40
+constexpr float ATT_RAW_LIMIT = 40.0f;    // QLOG2 fast form only while every first score of the warp's rows is within 2^+-40
 constexpr float ATT_RISK_SUM = 1.2676506e30f;   // 2^100: a tile sum this large sends the CTA's rows to the exact path
 #ifndef ATT_POLY_NUM
 #define ATT_POLY_NUM 1
@@ -53,8 +54,8 @@ constexpr int ATT_BAR_COUNT = 256 + 32;
 #ifdef ATT_TRACE
 // Development-only event timeline (tools/att_lab): lane 0 of each role of a few CTAs records (tag, kv tile, %clock).
 constexpr int TR_SLOTS = 32, TR_EVENTS = 256;
-__device__ uint32_t g_att_trace[TR_SLOTS][3][TR_EVENTS][2];
-__device__ uint32_t g_att_trace_n[TR_SLOTS][3];
+__device__ uint32_t g_att_trace[TR_SLOTS][4][TR_EVENTS][2];
+__device__ uint32_t g_att_trace_n[TR_SLOTS][4];
 __device__ uint32_t g_att_trace_sm[TR_SLOTS];
 struct Tracer {
   int slot, role, n;
@@ -123,7 +124,7 @@ __device__ __forceinline__ void poly_exp2_pair(unsigned long long x2, float& o0,
 // which the fast path flagged a possible overflow of its lagged softmax reference (see the softmax warps below): a
 // score that outgrows the reference by more than 2^100 within two kv tiles. Slow, exact, practically never taken.
 __device__ __noinline__ void attention_row_exact(const __nv_bfloat16* __restrict__ qkv_b, __nv_bfloat16* __restrict__ out_row,
-                                                 int q, int T, int d, int h, int lane) {
+                                                 int q, int T, int d, int h, int lane, float to_log2) {
   const size_t ld = static_cast<size_t>(3) * d;
   const uint4* qp = reinterpret_cast<const uint4*>(qkv_b + static_cast<size_t>(q) * ld + h * ATT_HD);
   uint4 qv[8];
@@ -147,7 +148,7 @@ __device__ __noinline__ void attention_row_exact(const __nv_bfloat16* __restrict
           acc = fmaf(__uint_as_float(qa[e] & 0xffff0000u), __uint_as_float(ka[e] & 0xffff0000u), acc);
         }
       }
-      sc = acc * LOG2E;
+      sc = acc * to_log2;
     }
     const float m_new = fmaxf(m, warp_max(sc));
     const float scale = exp2f(m - m_new);          // 0 on the first chunk
@@ -190,6 +191,10 @@ constexpr uint32_t ATT_OFF_TMEM_PTR = ATT_BAR_O_FULL + 8;
 constexpr uint32_t ATT_OFF_EXACT = ATT_OFF_TMEM_PTR + 4;                        // "a row of this tile needs the exact path"
 static_assert(ATT_OFF_EXACT + 4 + 1024 <= ATT_SMEM, "shared-memory carve-up exceeds ATT_SMEM");
 
+// QLOG2: the caller folded log2(e) into q as well (the scores arrive in log2 units). Then, while a warp's rows need no
+// reference (first scores within 2^+-ATT_RAW_LIMIT and no reference move yet -- the normal case), exp2 is taken
+// straight from the accumulator values: the scale-and-subtract FFMA2 of every element pair disappears.
+template <bool QLOG2>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ qkv,
                      __nv_bfloat16* __restrict__ out, int T, int H) {
@@ -263,58 +268,60 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
       }
       TR_DONE();
     } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
+      // ---------------------------------------------------------------- MMA issuer 1: S = Q K_j^T
+      // Two issuing warps (this one and warp 3 for O += P V_j): their loops only meet in the tensor pipe's queue, so a
+      // P V product is issued the moment its P is stored, not after the issue (and queueing) of the next Q K^T.
       constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BQ, ATT_BKV);             // Q K^T: both K-major
-      constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
-      const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
-      auto issue_s = [&](int stage) {
-        const uint64_t qd = umma_desc_sw128(sb + ATT_OFF_Q, 16, 1024);
-        const uint64_t kd = umma_desc_sw128(sb + ATT_OFF_K + stage * ATT_TILE_BYTES, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
-        umma_commit_a(sb + ATT_BAR_K_EMPTY + 8 * stage);   // the K stage is free once these MMAs have run
-        umma_commit_a(sb + ATT_BAR_S_FULL);
-      };
-      auto issue_o = [&](int stage, bool first_tile) {
-        // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B
-        // = +128 in the descriptor's (>>4) start-address field.
-        const uint64_t vd = umma_desc_sw128(sb + ATT_OFF_V + stage * ATT_TILE_BYTES, 1024, 1024);
-#pragma unroll
-        for (int k = 0; k < ATT_BKV / 16; ++k)
-          umma_ts(tO, tP + k * 8, vd + 128 * k, IDESC_O, (k != 0) || !first_tile);
-        umma_commit_a(sb + ATT_BAR_V_EMPTY + 8 * stage);
-        umma_commit_a(sb + ATT_BAR_O_FULL);
-      };
       TR_DECL(1);
       TR(10, 0);
       mbar_wait_a(sb + ATT_BAR_Q_FULL, 0);
-      mbar_wait_a(sb + ATT_BAR_K_FULL, 0);
-      tc_fence_after();
-      TR(11, 0);
-      if (elect_one()) issue_s(0);
-      __syncwarp();
-      TR(12, 0);
-      int ks = 1, vs = 0;                            // next K stage to consume, current V stage
-      uint32_t kph = 0, vph = 0;
+      int ks = 0;
+      uint32_t kph = 0;
 #pragma unroll 1
       for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {                           // scores of the next kv tile as soon as S is drained
-          mbar_wait_a(sb + ATT_BAR_K_FULL + 8 * ks, kph);
-          TR(13, j + 1);
-          named_bar_sync(ATT_BAR_S_EMPTY, ATT_BAR_COUNT);   // blocks in hardware: no polling next to the softmax warps
-          tc_fence_after();
-          TR(11, j + 1);
-          if (elect_one()) issue_s(ks);
-          __syncwarp();
-          TR(12, j + 1);
-          if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
+        mbar_wait_a(sb + ATT_BAR_K_FULL + 8 * ks, kph);
+        TR(13, j);
+        if (j > 0) named_bar_sync(ATT_BAR_S_EMPTY, ATT_BAR_COUNT);   // S drained; blocks in hardware, no polling
+        tc_fence_after();
+        TR(11, j);
+        if (elect_one()) {
+          const uint32_t tS = opaque_u32(tmem_base);                 // (opaque: nothing hoisted out of the loop and spilled)
+          const uint64_t qd = umma_desc_sw128(sb + ATT_OFF_Q, 16, 1024);
+          const uint64_t kd = umma_desc_sw128(sb + ATT_OFF_K + ks * ATT_TILE_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, qd + 2 * k, kd + 2 * k, IDESC_S, k != 0);
+          umma_commit_a(sb + ATT_BAR_K_EMPTY + 8 * ks);   // the K stage is free once these MMAs have run
+          umma_commit_a(sb + ATT_BAR_S_FULL);
         }
+        __syncwarp();
+        TR(12, j);
+        if (++ks == ATT_K_STAGES) { ks = 0; kph ^= 1; }
+      }
+      TR_DONE();
+    } else if (warp == 3) {
+      // ---------------------------------------------------------------- MMA issuer 2: O += P V_j
+      constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);        // P V: V is MN-major
+      TR_DECL(3);
+      int vs = 0;
+      uint32_t vph = 0;
+#pragma unroll 1
+      for (int j = 0; j < nkv; ++j) {
         mbar_wait_a(sb + ATT_BAR_V_FULL + 8 * vs, vph);
         TR(14, j);
         named_bar_sync(ATT_BAR_P_FULL, ATT_BAR_COUNT);
         tc_fence_after();
         TR(15, j);
-        if (elect_one()) issue_o(vs, j == 0);
+        if (elect_one()) {
+          // V tile: [kv 128 rows][64 d] bf16, 128 B rows, SW128 -> MN-major B operand. One UMMA_K = 16 kv rows = 2048 B
+          // = +128 in the descriptor's (>>4) start-address field.
+          const uint32_t tb = opaque_u32(tmem_base);
+          const uint64_t vd = umma_desc_sw128(sb + ATT_OFF_V + vs * ATT_TILE_BYTES, 1024, 1024);
+#pragma unroll
+          for (int k = 0; k < ATT_BKV / 16; ++k)
+            umma_ts(tb + 128, tb + 192 + k * 8, vd + 128 * k, IDESC_O, (k != 0) || (j != 0));
+          umma_commit_a(sb + ATT_BAR_V_EMPTY + 8 * vs);
+          umma_commit_a(sb + ATT_BAR_O_FULL);
+        }
         __syncwarp();
         TR(16, j);
         if (++vs == ATT_V_STAGES) { vs = 0; vph ^= 1; }
@@ -353,24 +360,32 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
     if (warp != 4) tr.slot = -1;
 #endif
     // reference base r0: the row's first score (column 0 of tile 0), the same for both halves, log2 units
+    constexpr float SCALE = QLOG2 ? 1.0f : LOG2E;
     float neg_r0;
+    bool raw = false;                              // warp-uniform: exponent = accumulator value (no reference at all)
     {
       mbar_wait_a(sb + ATT_BAR_S_FULL, 0);
       tc_fence_after();
       uint32_t s_first[1];
       tmem_ld_32x1(tSi - half * 64, s_first);
       tmem_ld_wait();
-      neg_r0 = -__uint_as_float(s_first[0]) * LOG2E;
+      neg_r0 = -__uint_as_float(s_first[0]) * SCALE;
+      if (QLOG2) {
+        // both halves of a row sit in warps that hold the same 32 rows: they take the same decision
+        raw = __all_sync(0xffffffffu, fabsf(neg_r0) < ATT_RAW_LIMIT);
+        if (raw) neg_r0 = 0.f;
+      }
     }
     int k_m1 = 0, k_m2 = 0;                        // integer reference offsets of tiles j-1 and j-2
     unsigned long long l2 = pk2(0.f, 0.f);         // this half's row sum (two partial sums), relative to r0 + k_m1
     float biggest = 0.f;                           // largest tile sum seen (inf sticks): the overflow sentinel
-    const unsigned long long LOG2E2 = pk2(LOG2E, LOG2E);
+    const unsigned long long SCALE2 = pk2(SCALE, SCALE);
 
     // 16 scores -> 8 packed bf16 pairs of probabilities; KB = first column (decides which pairs take the FMA-pipe exp2)
-#define ATT_EXPS16(sv, pv, KB)                                                                                        \
+#define ATT_EXPS16(sv, pv, KB, RAW)                                                                                   \
   _Pragma("unroll") for (int k = (KB); k < (KB) + 16; k += 2) {                                                        \
-    const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), LOG2E2, nm2);         \
+    const unsigned long long s2 = pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1]));                             \
+    const unsigned long long x2 = (RAW) ? s2 : ffma2(s2, SCALE2, nm2);                                                 \
     float p0, p1;                                                                                                      \
     if (((k >> 1) % POLY_DEN) < POLY_NUM) {                                                                            \
       poly_exp2_pair(x2, p0, p1);                                                                                      \
@@ -402,6 +417,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
         if (mag > k_m1 + ATT_TAU_LOG2) k_cur = mag - 4;
       }
       const int dk = k_cur - k_m1;                                           // 0, or >= ATT_TAU_LOG2 - 3
+      const bool rescale = __any_sync(0xffffffffu, dk != 0);
+      if (rescale) raw = false;                                              // (rare) from now on the general form
       k_m2 = k_m1;
       k_m1 = k_cur;
       const float nm = neg_r0 - static_cast<float>(k_cur);
@@ -416,9 +433,17 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
       // p = 2^(s*log2e - r); P -> TMEM as bf16 (columns kk/2), tile sums in fp32
       unsigned long long t2a = pk2(0.f, 0.f), t2b = pk2(0.f, 0.f);
       uint32_t pa[16], pb[16];
-      ATT_EXPS16(s0, pa, 0);
+      if (QLOG2 && raw) {
+        ATT_EXPS16(s0, pa, 0, true);
+      } else {
+        ATT_EXPS16(s0, pa, 0, false);
+      }
       tmem_ld_32x32(tSi + 32, s1);                 // the other 32 scores land under the second quarter's exps
-      ATT_EXPS16(s0, pa, 16);
+      if (QLOG2 && raw) {
+        ATT_EXPS16(s0, pa, 16, true);
+      } else {
+        ATT_EXPS16(s0, pa, 16, false);
+      }
       tmem_ld_wait_regs(s1);
       tc_fence_before();
       TR(22, j);
@@ -428,9 +453,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
         for (int k = 0; k < 32; ++k)
           if (k + 32 >= kv_valid) s1[k] = 0xff800000u;
       }
-      ATT_EXPS16(s1, pb, 0);
-      ATT_EXPS16(s1, pb, 16);
-      const bool rescale = __any_sync(0xffffffffu, dk != 0);
+      if (QLOG2 && raw) {
+        ATT_EXPS16(s1, pb, 0, true);
+        ATT_EXPS16(s1, pb, 16, true);
+      } else {
+        ATT_EXPS16(s1, pb, 0, false);
+        ATT_EXPS16(s1, pb, 16, false);
+      }
       float down = 1.0f;
       if (rescale) {                                                         // rare
         if (dk != 0) down = dk < 127 ? __int_as_float((127 - dk) << 23) : 0.f;   // 2^-dk, exact
@@ -507,7 +536,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
       named_bar_sync(ATT_BAR_SOFTMAX, 256);        // every fast-path store of the tile is out before it is overwritten
       const __nv_bfloat16* qkv_b = qkv + static_cast<size_t>(b) * T * 3 * d;
       for (int r = warp - 4; r < ATT_BQ && q0 + r < T; r += 8)
-        attention_row_exact(qkv_b, out + (static_cast<size_t>(b) * T + q0 + r) * d + h * ATT_HD, q0 + r, T, d, h, lane);
+        attention_row_exact(qkv_b, out + (static_cast<size_t>(b) * T + q0 + r) * d + h * ATT_HD, q0 + r, T, d, h, lane, SCALE);
     }
   }
 
@@ -533,33 +562,38 @@ void att_cycles_read(unsigned long long* out2, bool reset) {
 #endif
 #ifdef ATT_TRACE
 void att_trace_reset() {
-  static uint32_t zeros[TR_SLOTS][3];
+  static uint32_t zeros[TR_SLOTS][4];
   memset(zeros, 0, sizeof(zeros));
   cudaMemcpyToSymbol(g_att_trace_n, zeros, sizeof(zeros));
 }
 void att_trace_dump() {
-  static uint32_t ev[TR_SLOTS][3][TR_EVENTS][2];
-  static uint32_t n[TR_SLOTS][3], sm[TR_SLOTS];
+  static uint32_t ev[TR_SLOTS][4][TR_EVENTS][2];
+  static uint32_t n[TR_SLOTS][4], sm[TR_SLOTS];
   cudaMemcpyFromSymbol(ev, g_att_trace, sizeof(ev));
   cudaMemcpyFromSymbol(n, g_att_trace_n, sizeof(n));
   cudaMemcpyFromSymbol(sm, g_att_trace_sm, sizeof(sm));
   for (int s = 0; s < TR_SLOTS; ++s)
-    for (int r = 0; r < 3; ++r)
+    for (int r = 0; r < 4; ++r)
       for (uint32_t i = 0; i < n[s][r]; ++i)
         printf("TRACE slot %d sm %u role %d tag %u j %u clk %u\n", s, sm[s], r, ev[s][r][i][0] >> 16, ev[s][r][i][0] & 0xffff,
                ev[s][r][i][1]);
 }
 #endif
 
-int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, cudaStream_t stream) {
+int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, int q_log2, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                reinterpret_cast<__nv_bfloat16*>(out), T, H);
+  if (q_log2)
+    attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                        reinterpret_cast<__nv_bfloat16*>(out), T, H);
+  else
+    attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                         reinterpret_cast<__nv_bfloat16*>(out), T, H);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -48,7 +48,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
 
 // ------------------------------------------------------------------ attention (attention_sm100.cu)
 // qkv: [B][T][3*H*64] bf16 (q pre-scaled), out: [B][T][H*64] bf16. tm_qkv: 3-D map, box {64,128,1}, SW128.
-int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, cudaStream_t stream);
+// q_log2 != 0: q carries log2(e) as well as head_dim^-1/2 (scores in log2 units; the encoder folds both into Wq).
+int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, int q_log2, cudaStream_t stream);
 
 // ------------------------------------------------------------------ row kernels (rowwise.cu)
 // LayerNorm over the last dim of fp32 rows. out_dtype 0 = bf16, 1 = fp32. Output row of input row r is

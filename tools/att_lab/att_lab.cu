@@ -15,13 +15,24 @@
 #define ATT_SRC "../../audio_llama_b200/csrc/attention_sm100.cu"
 #endif
 #include ATT_SRC
+#ifdef ATT_LAB_QLOG2
+#define ATT_LAB_QMUL 1.4426950408889634f
+#define ATT_LAB_EXPMUL 0.6931471805599453
+#else
+#define ATT_LAB_QMUL 1.0f
+#define ATT_LAB_EXPMUL 1.0
+#endif
 #ifndef ATT_LAB_CTAS_PER_SM
 #define ATT_LAB_CTAS_PER_SM 2
 #endif
 #ifdef ATT_LAB_OLDSIG
 #define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, o, B, T, H, 0)
 #else
-#define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, q, o, B, T, H, 0)
+#ifdef ATT_LAB_QLOG2
+#define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, q, o, B, T, H, 1, 0)
+#else
+#define ATT_LAUNCH(tm, q, o, B, T, H) al::launch_attention(tm, q, o, B, T, H, 0, 0)
+#endif
 #endif
 
 namespace al {
@@ -101,7 +112,7 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
   for (size_t i = 0; i < h.size(); ++i) {
     const size_t c = i % d3;
     float v = frand();
-    if (c < d) v *= qscale * 0.125f * 3.0f;
+    if (c < d) v *= qscale * 0.125f * 3.0f * ATT_LAB_QMUL;
     h[i] = f2bf(v);
   }
   uint16_t *dq, *dout;
@@ -148,7 +159,7 @@ static int run_case(int B, int T, int H, float qscale, int iters, bool check) {
       }
       double l = 0;
       for (int j = 0; j < T; ++j) {
-        sc[j] = exp(sc[j] - mx);
+        sc[j] = exp((sc[j] - mx) * ATT_LAB_EXPMUL);
         l += sc[j];
       }
       for (int c = 0; c < 64; ++c) {
