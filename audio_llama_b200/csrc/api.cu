@@ -368,6 +368,7 @@ struct LayerW {
 
 struct al_encoder {
   int d, L, H, ffn, n_mels, c_pad, max_batch;
+  int att_flags = 0;   // AL_ATT_* for the attention launches (al_encoder_set_options)
   static constexpr int T_MEL = 3000, T = 1500;
   // workspace
   uint8_t* ws;
@@ -554,12 +555,17 @@ int al_layernorm(const float* x, const float* gamma, const float* beta, void* ou
 }
 
 int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t stream) {
+  return al_attention_ex(qkv, out, B, T, H, 0, stream);
+}
+
+int al_attention_ex(const void* qkv, void* out, int B, int T, int H, int flags, al_stream_t stream) {
   AL_REQUIRE(B > 0 && T > 0 && H > 0, "al_attention: bad shape B=%d T=%d H=%d", B, T, H);
+  AL_REQUIRE((flags & ~AL_ATT_Q_LOG2) == 0, "al_attention_ex: unknown flags 0x%x", flags);
   CUtensorMap tm;
   const uint64_t d3 = (uint64_t)3 * H * 64;
   int rc = tmap_rows3d(&tm, qkv, 2, d3, T, B, d3, d3 * T, 64, 128);
   if (rc) return rc;
-  rc = launch_attention(tm, qkv, out, B, T, H, 0, (cudaStream_t)stream);
+  rc = launch_attention(tm, qkv, out, B, T, H, (flags & AL_ATT_Q_LOG2) ? 1 : 0, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -734,7 +740,7 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
       p.m_per_batch = rows; p.batch = 1; p.N = 3 * d; p.K = d; p.bias = w.bqkv;
       RUN(AL_K_QKV, launch_gemm(e->tm_xn_A, w.tm_wqkv, e->tm_qkv_O, p, 0, nsm, st));
     }
-    RUN(AL_K_ATTN, launch_attention(e->tm_qkv_att, e->qkv, e->attn, B, 1500, e->H, 0, st));
+    RUN(AL_K_ATTN, launch_attention(e->tm_qkv_att, e->qkv, e->attn, B, 1500, e->H, (e->att_flags & AL_ATT_Q_LOG2) ? 1 : 0, st));
     {
       GemmParams p{};
       p.m_per_batch = rows; p.batch = 1; p.N = d; p.K = d; p.bias = w.bo;
@@ -759,6 +765,13 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
 }
 
 float* al_encoder_hidden(al_encoder* e) { return e ? e->x : nullptr; }
+
+int al_encoder_set_options(al_encoder* e, int attention_flags) {
+  AL_REQUIRE(e != nullptr, "al_encoder_set_options: NULL plan");
+  AL_REQUIRE((attention_flags & ~AL_ATT_Q_LOG2) == 0, "al_encoder_set_options: unknown attention flags 0x%x", attention_flags);
+  e->att_flags = attention_flags;
+  return 0;
+}
 
 int al_encoder_set_profiling(al_encoder* e, int on) {
   AL_REQUIRE(e != nullptr, "al_encoder_set_profiling: NULL plan");

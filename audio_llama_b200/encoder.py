@@ -43,6 +43,7 @@ class WhisperEncoderB200:
         check(L.al_encoder_create(C.byref(h), cfg.d_model, cfg.n_layers, cfg.n_heads, cfg.ffn_dim, cfg.n_mels,
                                   self.max_batch, ptr(self._ws), nbytes), "al_encoder_create")
         self._h = h
+        check(L.al_encoder_set_options(h, 1), "al_encoder_set_options")   # AL_ATT_Q_LOG2: see _pack
         w = self._w
         check(L.al_encoder_set_stem(h, ptr(w["conv1_w"]), ptr(w["conv1_b"]), ptr(w["conv2_w"]), ptr(w["conv2_b"]),
                                     ptr(w["pos"]), ptr(w["lnf_g"]), ptr(w["lnf_b"])), "al_encoder_set_stem")
@@ -71,7 +72,10 @@ class WhisperEncoderB200:
             "lnf_g": f("layer_norm.weight").contiguous(), "lnf_b": f("layer_norm.bias").contiguous(),
             "layers": [],
         }
-        scale = hd ** -0.5        # 0.125 for head_dim 64: q is scaled together with its bias (HF :310)
+        # q is scaled together with its bias (HF :310): hd^-0.5 (0.125 for head_dim 64), and log2(e) rides along so
+        # that the attention kernel's scores arrive in log2 units (AL_ATT_Q_LOG2: exp2 straight from the accumulator).
+        # The product is formed in fp32 before the one bf16 rounding of the packed weight.
+        scale = hd ** -0.5 * 1.4426950408889634
         for l in range(cfg.n_layers):
             p = f"layers.{l}."
             wq, bq = f(p + "self_attn.q_proj.weight") * scale, f(p + "self_attn.q_proj.bias") * scale

@@ -135,14 +135,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def attention(qkv: torch.Tensor, n_heads: int) -> torch.Tensor:
-    """qkv [B, T, 3*H*64] bf16 (q pre-scaled) -> [B, T, H*64] bf16."""
+def attention(qkv: torch.Tensor, n_heads: int, q_log2: bool = False) -> torch.Tensor:
+    """qkv [B, T, 3*H*64] bf16 (q pre-scaled by head_dim^-1/2; q_log2: and by log2 e) -> [B, T, H*64] bf16."""
     _req(qkv, torch.bfloat16, "qkv")
     B, T, d3 = qkv.shape
     if d3 != 3 * n_heads * 64:
         raise ValueError("attention kernel is head_dim 64 only")
     out = torch.empty(B, T, n_heads * 64, dtype=torch.bfloat16, device=qkv.device)
-    check(lib().al_attention(ptr(qkv), ptr(out), B, T, n_heads, stream_ptr()), "al_attention")
+    check(lib().al_attention_ex(ptr(qkv), ptr(out), B, T, n_heads, 1 if q_log2 else 0, stream_ptr()), "al_attention_ex")
     return out
 
 

@@ -104,8 +104,12 @@ int al_layernorm(const float* x, const float* gamma, const float* beta, void* ou
                  long long out_row_offset, al_stream_t stream);
 
 /* softmax(Q K^T) V, no mask, head_dim 64, q pre-scaled. qkv [B][T][3*H*64] bf16 -> out [B][T][H*64] bf16.
- * Replaces WhisperAttention's attention_interface call (modeling_whisper.py:339-349). */
+ * Replaces WhisperAttention's attention_interface call (modeling_whisper.py:339-349).
+ * al_attention_ex flags: AL_ATT_Q_LOG2 = q carries log2(e) as well as head_dim^-1/2 (scores arrive in log2 units:
+ * the kernel then takes exp2 straight from the accumulator; same result). al_attention = flags 0. */
+enum { AL_ATT_Q_LOG2 = 1 };
 int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t stream);
+int al_attention_ex(const void* qkv, void* out, int B, int T, int H, int flags, al_stream_t stream);
 
 int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream);
 int al_f32_to_bf16(const float* x, void* out_bf16, long long n, al_stream_t stream);
@@ -125,6 +129,9 @@ int al_encoder_set_stem(al_encoder* e, const void* conv1_w, const float* conv1_b
 int al_encoder_set_layer(al_encoder* e, int layer, const float* ln1_g, const float* ln1_b, const void* wqkv,
                          const float* bqkv, const void* wo, const float* bo, const float* ln2_g,
                          const float* ln2_b, const void* w1, const float* b1, const void* w2, const float* b2);
+/* attention_flags: AL_ATT_* the plan passes to its attention launches (AL_ATT_Q_LOG2 when the host packed
+ * wqkv's q rows and bias with hd^-0.5 * log2(e), as audio_llama_b200/encoder.py does). Default 0. */
+int al_encoder_set_options(al_encoder* e, int attention_flags);
 /* mel [B][n_mels][3000] f32 -> out [B][1500][d] (out_dtype 0 bf16 / 1 f32). n_layers_run < 0 = all. */
 int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
                        al_stream_t stream);
