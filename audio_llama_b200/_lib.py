@@ -26,6 +26,9 @@ SIGNATURES = {
     "al_last_error": (C.c_char_p, []),
     "al_launch_count": (i64, []),
     "al_mel_forward": (i32, [vp, vp, i32, i64, i32, i32, vp, vp, vp]),
+    "al_mel_forward_ex": (i32, [vp, vp, i32, i64, i32, i32, i32, vp, vp, vp]),
+    "al_pack_mel_ex": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "al_encoder_forward_ex": (i32, [vp, vp, vp, i32, vp, i32, i32, vp]),
     "al_mel_filterbank_host": (i32, [i32, i32, vp]),
     "al_mel_set_filterbank_host": (i32, [i32, i32, vp]),
     "al_mel_set_mode": (i32, [i32]),
@@ -62,8 +65,8 @@ SIGNATURES = {
     "al_cross_entropy_inplace": (i32, [vp, vp, i32, i32, i64, f32, vp, vp]),
     "al_linear_ce_workspace_bytes": (sz, [i32, i32]),
     "al_linear_ce": (i32, [vp, vp, vp, vp, i32, i32, i32, f32, i32, vp, vp, vp, vp]),
-    "al_splice": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, vp]),
-    "al_splice_ragged": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i64, i64, vp, vp, vp, vp, vp]),
+    "al_splice": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, i64, i64, vp, vp, vp, vp, i64, vp, vp]),
+    "al_splice_ragged": (i32, [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, i64, i64, vp, vp, vp, vp, i64, vp, vp]),
 }
 
 

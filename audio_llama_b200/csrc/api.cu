@@ -441,6 +441,12 @@ int al_mel_set_mode(int tc) {
 
 int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels, int mode,
                    float* out, unsigned int* clip_max_ws, al_stream_t stream) {
+  return al_mel_forward_ex(wave, n_samples, n_clips, wave_stride, n_mels, mode, 0, out, clip_max_ws, stream);
+}
+
+int al_mel_forward_ex(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels, int mode,
+                      int flags, float* out, unsigned int* clip_max_ws, al_stream_t stream) {
+  AL_REQUIRE((flags & ~AL_MEL_RAW) == 0, "al_mel_forward_ex: unknown flags 0x%x", flags);
   AL_REQUIRE(n_clips >= 0 && n_mels > 0 && n_mels <= 256, "al_mel_forward: bad n_clips=%d / n_mels=%d", n_clips, n_mels);
   AL_REQUIRE(mode == 0 || mode == 1, "al_mel_forward: mode must be 0 (whisper) or 1 (train), got %d", mode);
   AL_REQUIRE(n_samples != nullptr || wave_stride >= 480000,
@@ -455,7 +461,7 @@ int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long lo
   else rc = launch_mel(wave, n_samples, n_clips, wave_stride, tb, mode, out, clip_max_ws, st);
   if (rc) return rc;
   g_launches += 1;
-  if (mode == 0) {
+  if (mode == 0 && !(flags & AL_MEL_RAW)) {
     rc = launch_mel_finalize(out, clip_max_ws, n_clips, n_mels, st);
     if (rc) return rc;
     g_launches += 1;
@@ -571,8 +577,13 @@ int al_attention_ex(const void* qkv, void* out, int B, int T, int H, int flags, 
 }
 
 int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream) {
+  return al_pack_mel_ex(mel, nullptr, out_bf16, B, n_mels, T, c_pad, stream);
+}
+
+int al_pack_mel_ex(const float* mel, const unsigned int* clip_max_ws, void* out_bf16, int B, int n_mels, int T, int c_pad,
+                   al_stream_t stream) {
   AL_REQUIRE(c_pad >= n_mels, "al_pack_mel: c_pad=%d < n_mels=%d", c_pad, n_mels);
-  int rc = launch_pack_mel(mel, out_bf16, B, n_mels, T, c_pad, (cudaStream_t)stream);
+  int rc = launch_pack_mel(mel, out_bf16, B, n_mels, T, c_pad, clip_max_ws, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -702,6 +713,11 @@ static int encoder_maps(al_encoder* e, int B) {
 
 int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
                        al_stream_t stream) {
+  return al_encoder_forward_ex(e, mel, nullptr, B, out, out_dtype, n_layers_run, stream);
+}
+
+int al_encoder_forward_ex(al_encoder* e, const float* mel, const unsigned int* clip_max_ws, int B, void* out, int out_dtype,
+                          int n_layers_run, al_stream_t stream) {
   AL_REQUIRE(e && mel && out, "al_encoder_forward: NULL argument");
   AL_REQUIRE(B > 0 && B <= e->max_batch, "al_encoder_forward: B=%d outside 1..max_batch=%d", B, e->max_batch);
   AL_REQUIRE(e->conv1_w != nullptr, "al_encoder_forward: stem weights not set");
@@ -721,7 +737,7 @@ int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int ou
     if (_e1) cudaEventRecord(_e1, st);                                    \
     g_launches += 1;                                                      \
   } while (0)
-  RUN(AL_K_PACK, launch_pack_mel(mel, e->melT, B, e->n_mels, 3000, e->c_pad, st));
+  RUN(AL_K_PACK, launch_pack_mel(mel, e->melT, B, e->n_mels, 3000, e->c_pad, clip_max_ws, st));
   {  // conv1 + GELU (modeling_whisper.py:619)
     GemmParams p{};
     p.m_per_batch = 3000; p.batch = B; p.N = d; p.K = 3 * e->c_pad; p.bias = e->conv1_b;
@@ -1119,13 +1135,16 @@ int al_linear_ce(const void* h, const void* W, const void* W_T, const long long*
 // ----------------------------------------------------------------------------- splice
 int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
               const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
-              const void* audio_rows, void* out, float* mask_out, long long* labels_out, al_stream_t stream) {
+              const void* audio_rows, void* out, float* mask_out, long long* labels_out, long long vocab,
+              int* bad_id_flag, al_stream_t stream) {
   AL_REQUIRE(table && input_ids && out, "al_splice: NULL argument");
+  AL_REQUIRE(vocab > 0, "al_splice: vocab must be positive (rows of the embedding table)");
+  AL_REQUIRE(start_id < vocab && end_id < vocab, "Token IDs %lld, %lld are outside vocabulary size %lld", start_id, end_id, vocab);
   AL_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "al_splice: elem_bytes must be 2 or 4");
   AL_REQUIRE(B >= 0 && t_txt >= 0 && n_audio >= 0, "al_splice: negative size");
   AL_REQUIRE(start_id >= 0 && end_id >= 0, "al_splice: negative delimiter id");
   int rc = launch_splice(table, elem_bytes, d, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id, end_id,
-                         audio_rows, out, mask_out, labels_out, (cudaStream_t)stream);
+                         audio_rows, out, mask_out, labels_out, vocab, bad_id_flag, (cudaStream_t)stream);
   if (rc == 0 && B > 0) g_launches += 1;
   return rc;
 }
@@ -1134,13 +1153,16 @@ int al_splice_ragged(const void* table, int elem_bytes, int d, const long long* 
                      const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
                      const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
                      const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
-                     long long* labels_out, int* span_start_out, al_stream_t stream) {
+                     long long* labels_out, int* span_start_out, long long vocab, int* bad_id_flag,
+                     al_stream_t stream) {
   AL_REQUIRE(table && input_ids && out && span_rows && span_src_row && n_spans && audio_rows,
              "al_splice_ragged: NULL argument");
+  AL_REQUIRE(vocab > 0 && start_id >= 0 && end_id >= 0 && start_id < vocab && end_id < vocab,
+             "Token IDs %lld, %lld are outside vocabulary size %lld", start_id, end_id, vocab);
   AL_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "al_splice_ragged: elem_bytes must be 2 or 4");
   int rc = launch_splice_ragged(table, elem_bytes, d, input_ids, attn_mask, labels, B, t_txt, S_out, span_rows,
                                 span_src_row, n_spans, max_spans, audio_rows, start_id, end_id, out, mask_out,
-                                labels_out, span_start_out, (cudaStream_t)stream);
+                                labels_out, span_start_out, vocab, bad_id_flag, (cudaStream_t)stream);
   if (rc == 0 && B > 0) g_launches += 1;
   return rc;
 }

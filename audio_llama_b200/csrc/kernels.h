@@ -59,16 +59,19 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
                      int out_dtype, long long out_ld, int rows_per_group, long long out_group_stride,
                      long long out_row_offset, cudaStream_t stream);
 // mel [B][n_mels][T] fp32 -> time-major bf16 [B][T+2][c_pad], rows 0 and T+1 and channels >= n_mels zero.
-int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c_pad, cudaStream_t stream);
+int launch_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad,
+                    const unsigned int* clip_max_bits /* null = mel is final */, cudaStream_t stream);
 // Splice gather (S1/S2): see include/audiollm_b200.h al_splice.
 int launch_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
                   const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
-                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, cudaStream_t stream);
+                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, long long vocab,
+                  int* bad_id_flag, cudaStream_t stream);
 int launch_splice_ragged(const void* table, int elem_bytes, int d, const long long* input_ids,
                          const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
                          const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
                          const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
-                         long long* labels_out, int* span_start_out, cudaStream_t stream);
+                         long long* labels_out, int* span_start_out, long long vocab, int* bad_id_flag,
+                         cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, void* out, long long n, cudaStream_t stream);
 int launch_transpose_bf16(const void* in, void* out, int R, int C, int out_ld, cudaStream_t stream);
 int launch_layernorm_bwd(const float* y, const float* dout, const float* gamma, void* dy_bf16, float* dgamma,

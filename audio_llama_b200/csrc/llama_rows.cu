@@ -255,9 +255,12 @@ ce_inplace_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   const long long lab = labels[row];
   const int nvec = vocab / 8;
   uint4* lv = reinterpret_cast<uint4*>(lr);
-  if (lab < 0) {                                   // ignored position: gradient 0, no loss term
+  if (lab < 0 || lab >= vocab) {                   // ignored position: gradient 0, no loss term
     for (int i = threadIdx.x; i < nvec; i += 512) lv[i] = make_uint4(0, 0, 0, 0);
     for (int i = nvec * 8 + threadIdx.x; i < vocab; i += 512) lr[i] = __float2bfloat16_rn(0.f);
+    // a label >= vocab is an error (torch's cross_entropy asserts on it): nothing outside the row is read, and the
+    // loss is poisoned with NaN so that the step fails loudly instead of training on garbage
+    if (lab >= vocab && threadIdx.x == 0) atomicAdd(loss_sum, __int_as_float(0x7fc00000));
     return;
   }
   float m = -INFINITY, s = 0.f;

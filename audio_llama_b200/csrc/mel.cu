@@ -95,7 +95,8 @@ mel_kernel(const float* __restrict__ wave, const int* __restrict__ n_samples, lo
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * MEL_FR;
   const int tid = threadIdx.x;
-  const int nv = n_samples ? min(n_samples[b], N_CLIP) : N_CLIP;       // samples beyond nv are the zero padding
+  // samples beyond nv are the zero padding; never past the clip's own row (wave_stride) whatever n_samples says
+  const int nv = max(0, static_cast<int>(min(static_cast<long long>(n_samples ? min(n_samples[b], N_CLIP) : N_CLIP), wave_stride)));
   const float* w = wave + static_cast<long long>(b) * wave_stride;
 
   // 1. stage the samples of frames f0..f0+FR-1: padded index p = 160*f0 + i  <->  clip index p - 200, reflected

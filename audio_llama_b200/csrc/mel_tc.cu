@@ -356,7 +356,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mel_tc_kernel(const __grid_cons
       for (int t = cluster_id; t < total_tiles; t += n_clusters) {
         const int b = t / TC_TILES_PER_CLIP;
         const int f_cta = (t % TC_TILES_PER_CLIP) * 256 + static_cast<int>(rank) * 128;
-        const int nv = p.n_samples ? min(__ldg(p.n_samples + b), TC_CLIP) : TC_CLIP;
+        // (never past the clip's own row, whatever n_samples says)
+        const int nv = max(0, static_cast<int>(min(static_cast<long long>(p.n_samples ? min(__ldg(p.n_samples + b), TC_CLIP) : TC_CLIP),
+                                                   p.wave_stride)));
         const float* w = p.wave + static_cast<long long>(b) * p.wave_stride;
         const bool base_aligned = (reinterpret_cast<uintptr_t>(w) & 15) == 0;
         for (int q = 0; q < 4; ++q, ++u) {

@@ -93,15 +93,29 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, void
 // [B][n_mels][T] fp32 (what the reference hands the encoder, allm.py:214) -> [B][T+2][c_pad] bf16, time-major
 // with one zero row before and after each clip: row t+1 holds frame t. In this layout the im2col row of
 // conv1 (k=3, pad=1) for output frame t is the 3*c_pad contiguous elements starting at row t.
+// clip_max_bits != null: `mel` holds the log10 values BEFORE the per-clip floor (al_mel_forward_ex, AL_MEL_RAW) and
+// the floor + affine step of the feature extractor, (max(L, clipmax - 8) + 4) / 4 (HF :156-159), is applied here with
+// the very operations of mel_finalize_kernel: the f32 mel is then written once and read once on the pipeline path.
 __global__ void __launch_bounds__(256)
-pack_mel_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int n_mels, int T, int c_pad) {
+pack_mel_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, int n_mels, int T, int c_pad,
+                const unsigned int* __restrict__ clip_max_bits) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
+  float floor_v = 0.f;
+  if (clip_max_bits) {
+    const unsigned int u = clip_max_bits[b];                                   // ordered-int encoding of the clip max
+    floor_v = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u) - 8.0f;
+  }
   const int t0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int m = m0 + i, t = t0 + tx;
-    tile[i][tx] = (m < n_mels && t < T) ? mel[(static_cast<long long>(b) * n_mels + m) * T + t] : 0.f;
+    float v = 0.f;
+    if (m < n_mels && t < T) {
+      v = mel[(static_cast<long long>(b) * n_mels + m) * T + t];
+      if (clip_max_bits) v = (fmaxf(v, floor_v) + 4.0f) / 4.0f;
+    }
+    tile[i][tx] = v;
   }
   __syncthreads();
   __nv_bfloat16* ob = out + static_cast<long long>(b) * (T + 2) * c_pad;
@@ -115,9 +129,10 @@ pack_mel_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ out, 
     ob[static_cast<long long>(T + 1) * c_pad + m0 + tx] = __float2bfloat16_rn(0.f);
 }
 
-int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c_pad, cudaStream_t stream) {
+int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c_pad, const unsigned int* clip_max_bits,
+                    cudaStream_t stream) {
   dim3 grid((T + 31) / 32, (c_pad + 31) / 32, B);
-  pack_mel_kernel<<<grid, 256, 0, stream>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), n_mels, T, c_pad);
+  pack_mel_kernel<<<grid, 256, 0, stream>>>(mel, reinterpret_cast<__nv_bfloat16*>(out), n_mels, T, c_pad, clip_max_bits);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -143,12 +158,18 @@ __device__ __forceinline__ void copy_row_16B(void* dst, const void* src, int n16
 // COPY_AUDIO = false: the audio rows are already in place (the projector's LayerNorm wrote them), so only the
 //   t_txt + 2 gathered rows of a sample get a warp; the mask / labels entries of the A audio rows are written by the
 //   text-row warps, ceil(A / t_txt) each (or all by the <audio> warp when there is no text).
+__device__ __forceinline__ void zero_row_16B(void* dst, int n16, int lane) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dst)[i] = z;
+}
+
 template <bool COPY_AUDIO>
 __global__ void __launch_bounds__(256)
 splice_kernel(const uint8_t* __restrict__ table, long long row_bytes, const long long* __restrict__ input_ids,
               const long long* __restrict__ attn_mask, const long long* __restrict__ labels, int B, int t_txt,
               int n_audio, long long start_id, long long end_id, const uint8_t* __restrict__ audio_rows,
-              uint8_t* __restrict__ out, float* __restrict__ mask_out, long long* __restrict__ labels_out) {
+              uint8_t* __restrict__ out, float* __restrict__ mask_out, long long* __restrict__ labels_out,
+              long long vocab, int* __restrict__ bad_id_flag) {
   const int S = n_audio + 2 + t_txt;
   const int per_sample = COPY_AUDIO ? S : t_txt + 2;
   const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -172,7 +193,14 @@ splice_kernel(const uint8_t* __restrict__ table, long long row_bytes, const long
   } else {
     const int j = r - n_audio - 2;
     const long long id = input_ids[static_cast<long long>(b) * t_txt + j];
-    copy_row_16B(dst, table + id * row_bytes, n16, lane);
+    if (id >= 0 && id < vocab) {
+      copy_row_16B(dst, table + id * row_bytes, n16, lane);
+    } else {
+      // the reference's embed_tokens(input_ids) raises on such an id (allm.py:64); here nothing outside the table is
+      // read: the row is zeroed and the flag makes the host side raise (ops.splice / AudioConditioner)
+      zero_row_16B(dst, n16, lane);
+      if (lane == 0 && bad_id_flag) atomicOr(bad_id_flag, 1);
+    }
     if (attn_mask) mk = static_cast<float>(attn_mask[static_cast<long long>(b) * t_txt + j]);
     if (labels) lb = labels[static_cast<long long>(b) * t_txt + j];
   }
@@ -199,9 +227,6 @@ splice_kernel(const uint8_t* __restrict__ table, long long row_bytes, const long
   }
 }
 
-int launch_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
-                  const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
-                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, cudaStream_t stream);
 
 // Ragged extension (SURVEY.md §8 extension row; not in the reference). Sample b has n_spans[b] <= max_spans
 // spans; span k keeps span_rows[b][k] encoder rows taken from audio_rows at row span_src_row[b][k]. Output rows:
@@ -214,7 +239,8 @@ splice_ragged_kernel(const uint8_t* __restrict__ table, long long row_bytes, con
                      int S_out, const int* __restrict__ span_rows, const int* __restrict__ span_src_row,
                      const int* __restrict__ n_spans, int max_spans, const uint8_t* __restrict__ audio_rows,
                      long long start_id, long long end_id, uint8_t* __restrict__ out, float* __restrict__ mask_out,
-                     long long* __restrict__ labels_out, int* __restrict__ span_start_out) {
+                     long long* __restrict__ labels_out, int* __restrict__ span_start_out, long long vocab,
+                     int* __restrict__ bad_id_flag) {
   const long long gw = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (gw >= static_cast<long long>(B) * S_out) return;
   const int lane = threadIdx.x & 31;
@@ -246,12 +272,16 @@ splice_ragged_kernel(const uint8_t* __restrict__ table, long long row_bytes, con
   } else if (r < text_off + t_txt) {
     const int j = r - text_off;
     const long long id = input_ids[static_cast<long long>(b) * t_txt + j];
-    copy_row_16B(dst, table + id * row_bytes, n16, lane);
+    if (id >= 0 && id < vocab) {
+      copy_row_16B(dst, table + id * row_bytes, n16, lane);
+    } else {
+      zero_row_16B(dst, n16, lane);
+      if (lane == 0 && bad_id_flag) atomicOr(bad_id_flag, 1);
+    }
     mk = attn_mask ? static_cast<float>(attn_mask[static_cast<long long>(b) * t_txt + j]) : 1.0f;
     if (labels) lb = labels[static_cast<long long>(b) * t_txt + j];
   } else {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = lane; i < n16; i += 32) reinterpret_cast<uint4*>(dst)[i] = z;
+    zero_row_16B(dst, n16, lane);
     mk = 0.f;
   }
   if (lane == 0) {
@@ -262,7 +292,8 @@ splice_ragged_kernel(const uint8_t* __restrict__ table, long long row_bytes, con
 
 int launch_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
                   const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
-                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, cudaStream_t stream) {
+                  const void* audio_rows, void* out, float* mask_out, long long* labels_out, long long vocab,
+                  int* bad_id_flag, cudaStream_t stream) {
   const long long row_bytes = static_cast<long long>(d) * elem_bytes;
   AL_REQUIRE(row_bytes % 16 == 0, "splice: row of %lld bytes is not a multiple of 16", row_bytes);
   const bool copy_audio = audio_rows != nullptr;
@@ -272,11 +303,12 @@ int launch_splice(const void* table, int elem_bytes, int d, const long long* inp
   if (copy_audio)
     splice_kernel<true><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id,
-        end_id, reinterpret_cast<const uint8_t*>(audio_rows), reinterpret_cast<uint8_t*>(out), mask_out, labels_out);
+        end_id, reinterpret_cast<const uint8_t*>(audio_rows), reinterpret_cast<uint8_t*>(out), mask_out, labels_out, vocab,
+        bad_id_flag);
   else
     splice_kernel<false><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, n_audio, start_id,
-        end_id, nullptr, reinterpret_cast<uint8_t*>(out), mask_out, labels_out);
+        end_id, nullptr, reinterpret_cast<uint8_t*>(out), mask_out, labels_out, vocab, bad_id_flag);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -285,7 +317,8 @@ int launch_splice_ragged(const void* table, int elem_bytes, int d, const long lo
                          const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
                          const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
                          const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
-                         long long* labels_out, int* span_start_out, cudaStream_t stream) {
+                         long long* labels_out, int* span_start_out, long long vocab, int* bad_id_flag,
+                         cudaStream_t stream) {
   const long long row_bytes = static_cast<long long>(d) * elem_bytes;
   AL_REQUIRE(row_bytes % 16 == 0, "splice: row of %lld bytes is not a multiple of 16", row_bytes);
   const long long rows = static_cast<long long>(B) * S_out;
@@ -293,7 +326,7 @@ int launch_splice_ragged(const void* table, int elem_bytes, int d, const long lo
   splice_ragged_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
       reinterpret_cast<const uint8_t*>(table), row_bytes, input_ids, attn_mask, labels, B, t_txt, S_out, span_rows,
       span_src_row, n_spans, max_spans, reinterpret_cast<const uint8_t*>(audio_rows), start_id, end_id,
-      reinterpret_cast<uint8_t*>(out), mask_out, labels_out, span_start_out);
+      reinterpret_cast<uint8_t*>(out), mask_out, labels_out, span_start_out, vocab, bad_id_flag);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -93,7 +93,10 @@ class WhisperEncoderB200:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, mel: torch.Tensor, n_layers_run: int = -1, out: torch.Tensor = None) -> torch.Tensor:
+    def forward(self, mel: torch.Tensor, n_layers_run: int = -1, out: torch.Tensor = None,
+                clip_max: torch.Tensor = None) -> torch.Tensor:
+        """clip_max: `mel` is the raw (pre-floor) output of ops.mel_forward(raw=True) and this is its `ws`; the
+        per-clip floor and the (x + 4) / 4 step then run inside the plan's first kernel."""
         if mel.dim() == 4:                       # [B, 1, n_mels, 3000] as the dataloader hands it (allm.py:214)
             mel = mel.squeeze(1)
         if mel.shape[-1] != 2 * self.cfg.n_ctx:  # same error as HF modeling_whisper.py:613-617
@@ -110,9 +113,10 @@ class WhisperEncoderB200:
         done = 0
         while done < B:                          # larger batches run in max_batch chunks
             n = min(self.max_batch, B - done)
-            check(lib().al_encoder_forward(self._h, ptr(mel[done:]), n, ptr(out[done:]),
-                                           1 if out.dtype == torch.float32 else 0, n_layers_run, stream_ptr()),
-                  "al_encoder_forward")
+            check(lib().al_encoder_forward_ex(self._h, ptr(mel[done:]),
+                                              ptr(clip_max[done:]) if clip_max is not None else None, n,
+                                              ptr(out[done:]), 1 if out.dtype == torch.float32 else 0, n_layers_run,
+                                              stream_ptr()), "al_encoder_forward_ex")
             done += n
         return out
 

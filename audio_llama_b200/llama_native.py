@@ -229,16 +229,21 @@ def causal_lm_loss(h: torch.Tensor, weight: torch.Tensor, labels: torch.Tensor, 
     return linear_cross_entropy(h.reshape(-1, h.shape[-1]), weight, shifted.reshape(-1), chunk_rows)
 
 
-def causal_only_mask(attention_mask):
-    """None when `attention_mask` only right-pads (ones then zeros in every row): under causal attention the padded keys
-    lie after every real query, so the real positions see exactly the same keys with or without the explicit mask, and
-    HF's SDPA path can then run `is_causal=True` (half the score tiles) instead of a dense [B, 1, S, S] bias. Rows that
-    are padded on the left or in the middle keep their mask. One tiny device->host read."""
+def causal_only_mask(attention_mask, labels=None):
+    """None when `attention_mask` only right-pads (ones then zeros in every row) AND no padded position enters the
+    loss: under causal attention the padded keys lie after every real query, so the real positions see exactly the
+    same keys with or without the explicit mask, and HF's SDPA path can then run `is_causal=True` (half the score
+    tiles) instead of a dense [B, 1, S, S] bias. The PADDED positions themselves do see other keys without the mask,
+    so the mask is only dropped when their labels are all -100 (the reference's dataset pads `labels` with the pad
+    token id, dataset.py:82-92, so its batches keep the mask and the stock numerics). Rows padded on the left or in
+    the middle keep their mask. One tiny device->host read."""
     if attention_mask is None:
         return None
     m = attention_mask
-    right_padded = bool((m[:, 1:] <= m[:, :-1]).all()) if m.shape[1] > 1 else True
-    return None if right_padded else attention_mask
+    ok = (m[:, 1:] <= m[:, :-1]).all() if m.shape[1] > 1 else torch.ones((), dtype=torch.bool, device=m.device)
+    if labels is not None:
+        ok = ok & ((labels == -100) | (m != 0)).all()
+    return None if bool(ok) else attention_mask
 
 
 # ----------------------------------------------------------------------------- wiring

@@ -21,6 +21,24 @@ from .lora import apply_lora_to_llama, lora_forward_hook
 from .projector import AudioProjector
 
 
+class _PlaceAudioRows(torch.autograd.Function):
+    """inputs_embeds[:, 1:1+A] = projected_audio, in place, differentiable w.r.t. the audio rows only: the splice
+    kernel has already gathered the delimiter and text rows from the frozen table into `emb` (no gradient there), so
+    the backward is the slice of the incoming gradient (cast to the projector's dtype)."""
+
+    @staticmethod
+    def forward(ctx, emb, projected_audio, A):
+        ctx.A = A
+        ctx.src_dtype = projected_audio.dtype
+        emb[:, 1:1 + A].copy_(projected_audio)
+        ctx.mark_dirty(emb)
+        return emb
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, grad_out[:, 1:1 + ctx.A].to(ctx.src_dtype), None
+
+
 class AudioLLM(nn.Module):
     def __init__(self, llama_path, whisper_path, lora_rank=64):
         super().__init__()
@@ -88,7 +106,7 @@ class AudioLLM(nn.Module):
 
         if getattr(self, "native_causal_only", False):
             from .. import llama_native
-            combined_attention_mask = llama_native.causal_only_mask(combined_attention_mask)
+            combined_attention_mask = llama_native.causal_only_mask(combined_attention_mask, adjusted_labels)
         if getattr(self, "native_ce", False) and adjusted_labels is not None and combined_embeddings.dtype == torch.bfloat16:
             # lm_head + cross-entropy fused per chunk of rows (no [tokens, vocab] logits; `logits` is None in this mode)
             from transformers.modeling_outputs import CausalLMOutputWithPast
@@ -118,13 +136,15 @@ class AudioLLM(nn.Module):
         B, A, _ = projected_audio.shape
         emb, mask, lab = ops.splice(table.detach(), input_ids, attention_mask, labels, A, start_id, end_id,
                                     audio_rows=None)
-        # audio rows go in through autograd so the projector still receives gradients
-        combined = torch.cat([emb[:, :1], projected_audio.to(emb.dtype), emb[:, A + 1:]], dim=1) \
-            if projected_audio.requires_grad else self._place(emb, projected_audio, A)
-        return combined, mask, lab
+        return self._place(emb, projected_audio, A), mask, lab
 
     @staticmethod
     def _place(emb, projected_audio, A):
+        """Rows 1..A of the spliced buffer <- the projected audio, in place (the reference builds a second tensor with a
+        4-way torch.cat, allm.py:165-170). When the projector is being trained the copy goes through _PlaceAudioRows
+        so that it receives the gradient of exactly those rows."""
+        if projected_audio.requires_grad and torch.is_grad_enabled():
+            return _PlaceAudioRows.apply(emb, projected_audio, A)
         emb[:, 1:1 + A] = projected_audio.to(emb.dtype)
         return emb
 
@@ -139,8 +159,6 @@ class AudioLLM(nn.Module):
         A = projected_audio.shape[1]
         emb, _, _ = ops.splice(table.detach(), input_ids, None, None, A, start_id, end_id, audio_rows=None,
                                want_mask=False, want_labels=False)
-        if projected_audio.requires_grad:
-            return torch.cat([emb[:, :1], projected_audio.to(emb.dtype), emb[:, A + 1:]], dim=1)
         return self._place(emb, projected_audio, A)
 
     # ------------------------------------------------------------------ allm.py:176-196

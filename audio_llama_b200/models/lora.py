@@ -6,7 +6,7 @@
 What changes is the arithmetic order: the reference materialises the dense [out, in] delta `B @ A` on every
 call and runs a second full-size GEMM (lora.py:20-21). Here the update is the rank-r side path
 `(x @ A^T) @ B^T * scaling` — 2*M*r*(in+out) FLOPs instead of 2*out*in*r + 2*M*in*out — identical in exact
-arithmetic, within fp32 round-off in practice (tests/test_lora.py pins it to the reference's own output).
+arithmetic, within fp32 round-off in practice (tests/test_oracle_golden.py pins it to the reference's own output, tests/test_gpu_lora.py checks the fused kernel).
 """
 from __future__ import annotations
 

@@ -33,8 +33,21 @@ def projector_forward_raw(w: Dict[str, torch.Tensor], x_bf16: torch.Tensor, out_
         c["w1"] = W1.detach().to(torch.bfloat16).contiguous()
         c["w2"] = W2.detach().to(torch.bfloat16).contiguous()
     f32 = lambda k: w[k].detach().to(torch.float32).contiguous()
-    h_ws = torch.empty(rows, hidden, dtype=torch.bfloat16, device=x2.device)
-    y_ws = torch.empty(rows, d_out, dtype=torch.float32, device=x2.device)
+    if keep is None and cache is not None:
+        # inference path: the two scratch matrices live in the caller's cache (no allocation in steady state); the
+        # training path (keep) hands them to autograd, so it gets fresh ones
+        if c.get("ws_rows") != rows or c["h_ws"].device != x2.device:
+            c["h_ws"] = torch.empty(rows, hidden, dtype=torch.bfloat16, device=x2.device)
+            c["y_ws"] = torch.empty(rows, d_out, dtype=torch.float32, device=x2.device)
+            c["ws_rows"] = rows
+        h_ws, y_ws = c["h_ws"], c["y_ws"]
+    else:
+        h_ws = torch.empty(rows, hidden, dtype=torch.bfloat16, device=x2.device)
+        y_ws = torch.empty(rows, d_out, dtype=torch.float32, device=x2.device)
+    if out is not None and out.dtype not in (torch.bfloat16, torch.float32):
+        # the LayerNorm kernel stores bf16 or fp32 only: anything else (an fp16 inputs_embeds buffer, say) would be
+        # filled with bf16 bit patterns
+        raise TypeError(f"projector output buffer must be bfloat16 or float32, got {out.dtype}")
     if out is None:
         out = torch.empty(*x_bf16.shape[:-1], d_out, dtype=out_dtype, device=x2.device)
         rows_per_group, out_group_stride, out_row_offset = max(rows, 1), 0, 0

@@ -24,8 +24,12 @@ def _req(t: torch.Tensor, dtype, name: str):
 
 
 def mel_forward(wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None, n_mels: int = 128,
-                mode: int = MEL_WHISPER, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """wave [B, n] float32 (n >= 480000 unless n_samples is given) -> [B, n_mels, 3000] float32."""
+                mode: int = MEL_WHISPER, out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None,
+                raw: bool = False) -> torch.Tensor:
+    """wave [B, n] float32 (n >= 480000 unless n_samples is given) -> [B, n_mels, 3000] float32.
+    `ws` = a caller-owned int32 [>= B] scratch (per-clip maxima), so a steady-state caller allocates nothing.
+    raw=True (Whisper mode): stop before the per-clip floor; `out` then holds log10 values and `ws` the clip maxima,
+    to be finished by WhisperEncoderB200.forward(mel, clip_max=ws) / ops.pack_mel(..., clip_max=ws)."""
     _req(wave, torch.float32, "wave")
     B, n = wave.shape
     if n_samples is None and n < 480000:
@@ -34,11 +38,16 @@ def mel_forward(wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None, n_
         _req(n_samples, torch.int32, "n_samples")
     if out is None:
         out = torch.empty(B, n_mels, N_FRAMES, dtype=torch.float32, device=wave.device)
-    ws = torch.empty(max(B, 1), dtype=torch.int32, device=wave.device)
+    if ws is None:
+        ws = torch.empty(max(B, 1), dtype=torch.int32, device=wave.device)
+    elif ws.dtype != torch.int32 or ws.numel() < B or not ws.is_cuda:
+        raise ValueError("mel_forward: ws must be a CUDA int32 tensor with at least B elements")
+    if raw and mode != MEL_WHISPER:
+        raise ValueError("mel_forward: raw=True only applies to the Whisper mode")
     if mode == MEL_TRAIN:
         _ensure_train_bank(n_mels)
-    check(lib().al_mel_forward(ptr(wave), ptr(n_samples), B, n, n_mels, mode, ptr(out), ptr(ws), stream_ptr()),
-          "al_mel_forward")
+    check(lib().al_mel_forward_ex(ptr(wave), ptr(n_samples), B, n, n_mels, mode, 1 if raw else 0, ptr(out), ptr(ws),
+                                  stream_ptr()), "al_mel_forward_ex")
     return out
 
 
@@ -124,6 +133,8 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     _req(x, torch.float32, "x")
     d = x.shape[-1]
     rows = x.numel() // d
+    if (out.dtype if out is not None else out_dtype) not in (torch.bfloat16, torch.float32):
+        raise TypeError("layernorm stores bfloat16 or float32 only")
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         rows_per_group, out_group_stride, out_row_offset = max(rows, 1), 0, 0
@@ -146,11 +157,12 @@ def attention(qkv: torch.Tensor, n_heads: int, q_log2: bool = False) -> torch.Te
     return out
 
 
-def pack_mel(mel: torch.Tensor, c_pad: int) -> torch.Tensor:
+def pack_mel(mel: torch.Tensor, c_pad: int, clip_max: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """clip_max = the `ws` of mel_forward(raw=True): the per-clip floor and (x + 4) / 4 are applied while packing."""
     _req(mel, torch.float32, "mel")
     B, n_mels, T = mel.shape
     out = torch.empty(B, T + 2, c_pad, dtype=torch.bfloat16, device=mel.device)
-    check(lib().al_pack_mel(ptr(mel), ptr(out), B, n_mels, T, c_pad, stream_ptr()), "al_pack_mel")
+    check(lib().al_pack_mel_ex(ptr(mel), ptr(clip_max), ptr(out), B, n_mels, T, c_pad, stream_ptr()), "al_pack_mel_ex")
     return out
 
 
@@ -164,9 +176,14 @@ def f32_to_bf16(x: torch.Tensor) -> torch.Tensor:
 def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor],
            labels: Optional[torch.Tensor], n_audio: int, start_id: int, end_id: int,
            audio_rows: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-           want_mask: bool = True, want_labels: bool = True):
+           want_mask: bool = True, want_labels: bool = True, mask_out: Optional[torch.Tensor] = None,
+           labels_out: Optional[torch.Tensor] = None, check_ids: bool = True):
     """S1/S2. Returns (inputs_embeds [B, n_audio+2+T, d], mask float32 | None, labels int64 | None).
-    With audio_rows=None rows 1..n_audio of `out` are left for the projector to fill in place."""
+    With audio_rows=None rows 1..n_audio of `out` are left for the projector to fill in place.
+    `out` / `mask_out` / `labels_out` may be caller-owned buffers (a steady-state caller then allocates nothing).
+    An input id outside the table raises IndexError, as the reference's embed_tokens(input_ids) does (allm.py:64);
+    check_ids=False defers that to raise_if_bad_ids() (no host sync on the hot path; the kernel never reads outside
+    the table either way)."""
     if not table.is_cuda or not table.is_contiguous():
         raise ValueError("table must be a contiguous CUDA tensor")
     if table.dtype not in (torch.bfloat16, torch.float32, torch.float16):
@@ -187,12 +204,46 @@ def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optiona
         _req(attention_mask, torch.int64, "attention_mask")
     if labels is not None:
         _req(labels, torch.int64, "labels")
-    mask_out = torch.empty(B, S, dtype=torch.float32, device=table.device) if want_mask else None
-    labels_out = torch.empty(B, S, dtype=torch.int64, device=table.device) if (want_labels and labels is not None) else None
+    if mask_out is None:
+        mask_out = torch.empty(B, S, dtype=torch.float32, device=table.device) if want_mask else None
+    else:
+        _req(mask_out, torch.float32, "mask_out")
+    if labels is None:
+        labels_out = None
+    elif labels_out is None:
+        labels_out = torch.empty(B, S, dtype=torch.int64, device=table.device) if want_labels else None
+    else:
+        _req(labels_out, torch.int64, "labels_out")
+    flag = bad_id_flag(table.device)
     check(lib().al_splice(ptr(table), table.element_size(), d, ptr(input_ids), ptr(attention_mask), ptr(labels), B, T,
                           n_audio, start_id, end_id, ptr(audio_rows), ptr(out), ptr(mask_out), ptr(labels_out),
-                          stream_ptr()), "al_splice")
+                          vocab, ptr(flag), stream_ptr()), "al_splice")
+    if check_ids:
+        raise_if_bad_ids(table.device, vocab)
     return out, mask_out, labels_out
+
+
+_bad_id_flags = {}
+
+
+def bad_id_flag(device) -> torch.Tensor:
+    """The per-device int32 word the splice kernels OR with 1 when they meet an input id outside the table."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    f = _bad_id_flags.get(key)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _bad_id_flags[key] = f
+    return f
+
+
+def raise_if_bad_ids(device, vocab=None):
+    """Synchronises; raises IndexError if a splice launch on this device met an out-of-range input id since the last
+    check (and clears the flag)."""
+    f = bad_id_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError("index out of range in self: input_ids outside the embedding table"
+                         + (f" (vocabulary size {vocab})" if vocab is not None else ""))
 
 
 def pack_lora(lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float):

@@ -48,10 +48,34 @@ class FlatGradBucket:
             off += p.numel()
 
     def zero(self):
+        """Use this (or optimizer.zero_grad(set_to_none=False)) between steps: the gradients stay views of the bucket."""
+        self.rebind()
         self.flat.zero_()
 
+    def rebind(self) -> int:
+        """Re-establish p.grad as a view of the bucket for every parameter whose gradient was detached from it.
+        The reference loop calls optimizer.zero_grad() (train.py:300), whose default set_to_none=True drops the
+        views; autograd then allocates fresh gradient tensors OUTSIDE the bucket and an all-reduce of the bucket
+        would average stale zeros. A detached gradient is copied into its slot (a None gradient zeroes the slot);
+        returns how many parameters had to be re-bound."""
+        off, n = 0, 0
+        for p in self.params:
+            view = self.flat[off:off + p.numel()].view_as(p)
+            g = p.grad
+            if g is None or g.data_ptr() != view.data_ptr() or g.dtype != self.flat.dtype:
+                if g is None:
+                    view.zero_()
+                else:
+                    view.copy_(g)
+                p.grad = view
+                n += 1
+            off += p.numel()
+        return n
+
     def allreduce_mean(self, group=None):
-        """sum over ranks then / world (the gradient of the mean loss over the global batch)."""
+        """sum over ranks then / world (the gradient of the mean loss over the global batch). Gradients that were
+        detached from the bucket since the last call (zero_grad(set_to_none=True)) are gathered back first."""
+        self.rebind()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(dist.get_world_size(group))

@@ -54,6 +54,9 @@ class AudioConditioner:
         if start_id >= vocab or end_id >= vocab:       # allm.py:140-141
             raise ValueError(f"Token IDs {start_id}, {end_id} are outside vocabulary size {vocab}")
         self.start_id, self.end_id = int(start_id), int(end_id)
+        if embed_table.dtype not in (torch.bfloat16, torch.float32):
+            # inputs_embeds takes the table's dtype and the projector's LayerNorm stores bf16 or fp32 only
+            raise TypeError(f"embedding table must be bfloat16 or float32 for the audio-conditioning path, got {embed_table.dtype}")
         self.table = embed_table.to(self.device).contiguous()
         self.encoder = WhisperEncoderB200(cfg, encoder_weights, max_batch, device=self.device, out_dtype=torch.bfloat16)
         self.pw = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in projector_weights.items()}
@@ -61,6 +64,7 @@ class AudioConditioner:
         self.d_out = self.pw["layers.2.weight"].shape[0]
         self._mel = torch.empty(max_batch, cfg.n_mels, N_FRAMES, dtype=torch.float32, device=self.device)
         self._enc = torch.empty(max_batch, N_CTX, cfg.d_model, dtype=torch.bfloat16, device=self.device)
+        self._clip_max = torch.empty(max_batch, dtype=torch.int32, device=self.device)   # per-clip log-mel maxima
 
     # ------------------------------------------------------------------ host-buffer entry point
     def _host_state(self, B, T):
@@ -73,6 +77,8 @@ class AudioConditioner:
                 wave=torch.empty(B, 480000, dtype=torch.float32, device=dev), ids=torch.empty(B, T, dtype=torch.int64, device=dev),
                 mask=torch.empty(B, T, dtype=torch.int64, device=dev), labels=torch.empty(B, T, dtype=torch.int64, device=dev),
                 emb=torch.empty(B, S, self.d_out, dtype=self.table.dtype, device=dev),
+                mask_out=torch.empty(B, S, dtype=torch.float32, device=dev),
+                labels_out=torch.empty(B, S, dtype=torch.int64, device=dev),
                 h2d_done=torch.cuda.Event(), compute_done=torch.cuda.Event(), d2h_done=torch.cuda.Event())
             st = dict(key=key, slots=[mk(), mk()], i=0, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev), primed=None)
             self._hs = st
@@ -110,7 +116,8 @@ class AudioConditioner:
                 upload(batches[i + 1], slots[(i + 1) & 1])
             cur.wait_event(slot["h2d_done"])
             cur.wait_event(slot["d2h_done"])                      # the slot's previous result has left `emb`
-            emb, mo, lo = self(slot["wave"], slot["ids"], slot["mask"], slot["labels"], out=slot["emb"])
+            emb, mo, lo = self(slot["wave"], slot["ids"], slot["mask"], slot["labels"], out=slot["emb"],
+                               mask_out=slot["mask_out"], labels_out=slot["labels_out"])
             slot["compute_done"].record(cur)
             with torch.cuda.stream(st["d2h"]):
                 st["d2h"].wait_event(slot["compute_done"])
@@ -118,26 +125,32 @@ class AudioConditioner:
                 hb.out_mask.copy_(mo, non_blocking=True)
                 hb.out_labels.copy_(lo, non_blocking=True)
                 slot["d2h_done"].record(st["d2h"])
-                mo.record_stream(st["d2h"])
-                lo.record_stream(st["d2h"])
         cur.wait_stream(st["d2h"])
         cur.wait_stream(st["h2d"])
+        self.raise_if_bad_ids()              # (synchronises: every output is on the host when this returns)
 
     @torch.no_grad()
-    def mel(self, wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None) -> torch.Tensor:
-        return ops.mel_forward(wave, n_samples, n_mels=self.cfg.n_mels, out=self._mel[: wave.shape[0]])
+    def mel(self, wave: torch.Tensor, n_samples: Optional[torch.Tensor] = None, raw: bool = False) -> torch.Tensor:
+        """The extractor's features [B, n_mels, 3000] f32 (raw=True: before the per-clip floor, which the encoder's
+        first kernel then applies from self._clip_max -- the form __call__ uses)."""
+        B = wave.shape[0]
+        return ops.mel_forward(wave, n_samples, n_mels=self.cfg.n_mels, out=self._mel[:B], ws=self._clip_max[:B], raw=raw)
 
     @torch.no_grad()
     def __call__(self, wave: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
                  labels: Optional[torch.Tensor] = None, n_samples: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None):
+                 out: Optional[torch.Tensor] = None, mask_out: Optional[torch.Tensor] = None,
+                 labels_out: Optional[torch.Tensor] = None):
         """wave [B, n] fp32, input_ids/attention_mask/labels [B, T] int64 (all on the GPU) ->
-        (inputs_embeds [B, 1502+T, d_l] in the table's dtype, mask fp32 [B, 1502+T], labels int64 | None)."""
+        (inputs_embeds [B, 1502+T, d_l] in the table's dtype, mask fp32 [B, 1502+T], labels int64 | None).
+        With `out`, `mask_out` and `labels_out` given the call launches kernels only (no allocation, no host sync);
+        an input id outside the table is reported by raise_if_bad_ids() (run_host calls it; the kernels never read
+        outside the table)."""
         B, T = input_ids.shape
         if B > self.max_batch:
             raise ValueError(f"batch {B} > max_batch {self.max_batch}")
-        mel = self.mel(wave, n_samples)
-        enc = self.encoder(mel, out=self._enc[:B])
+        mel = self.mel(wave, n_samples, raw=True)
+        enc = self.encoder(mel, out=self._enc[:B], clip_max=self._clip_max[:B])
         S = N_CTX + 2 + T
         if out is None:
             out = torch.empty(B, S, self.d_out, dtype=self.table.dtype, device=self.device)
@@ -146,8 +159,13 @@ class AudioConditioner:
                               out_group_stride=S, out_row_offset=1, cache=self._pcache)
         # splice: delimiter + text rows, mask, labels (audio rows already in place)
         emb, mask, lab = ops.splice(self.table, input_ids, attention_mask, labels, N_CTX, self.start_id, self.end_id,
-                                    audio_rows=None, out=out)
+                                    audio_rows=None, out=out, mask_out=mask_out, labels_out=labels_out, check_ids=False)
         return emb, mask, lab
+
+    def raise_if_bad_ids(self):
+        """IndexError if any splice launched since the last check met an input id outside the embedding table (what
+        the reference's embed_tokens(input_ids) raises on, allm.py:64). Synchronises the device."""
+        ops.raise_if_bad_ids(self.device, self.table.shape[0])
 
     # ------------------------------------------------------------------ config 5: ragged clips, several spans per sample
     @torch.no_grad()

@@ -14,6 +14,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
+from . import ops
 from ._lib import check, lib, ptr, stream_ptr
 from .config import HOP, N_CTX, N_SAMPLES
 
@@ -65,6 +66,8 @@ def splice_ragged(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: 
     starts = torch.zeros(B, max_spans, dtype=torch.int32, device=dev)
     check(lib().al_splice_ragged(ptr(table), table.element_size(), d, ptr(input_ids), ptr(attention_mask), ptr(labels),
                                  B, T, S, ptr(rows_d), ptr(src_d), ptr(ns_d), max_spans, ptr(audio), start_id, end_id,
-                                 ptr(out), ptr(mask_out), ptr(labels_out), ptr(starts), stream_ptr()),
+                                 ptr(out), ptr(mask_out), ptr(labels_out), ptr(starts), table.shape[0],
+                                 ptr(ops.bad_id_flag(dev)), stream_ptr()),
           "al_splice_ragged")
+    ops.raise_if_bad_ids(dev, table.shape[0])
     return out, mask_out, labels_out, starts

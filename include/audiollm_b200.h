@@ -42,6 +42,12 @@ long long al_launch_count(void);
  */
 int al_mel_forward(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels,
                    int mode, float* out, unsigned int* clip_max_ws, al_stream_t stream);
+/* flags: AL_MEL_RAW (mode 0) = stop before the per-clip floor: out holds log10(max(mel, 1e-10)) and clip_max_ws the
+ * per-clip maximum (ordered-uint encoding); al_encoder_forward_ex / al_pack_mel_ex finish the job while they repack
+ * the features, which saves the floor pass's launch and its re-read + re-write of the f32 features. */
+enum { AL_MEL_RAW = 1 };
+int al_mel_forward_ex(const float* wave, const int* n_samples, int n_clips, long long wave_stride, int n_mels,
+                      int mode, int flags, float* out, unsigned int* clip_max_ws, al_stream_t stream);
 /* Host-side copy of the filter bank the kernel uses, [201][n_mels] float64 row-major (for parity tests
  * against transformers.audio_utils.mel_filter_bank / torchaudio melscale_fbanks). */
 int al_mel_filterbank_host(int n_mels, int mode, double* out_host);
@@ -112,6 +118,10 @@ int al_attention(const void* qkv, void* out, int B, int T, int H, al_stream_t st
 int al_attention_ex(const void* qkv, void* out, int B, int T, int H, int flags, al_stream_t stream);
 
 int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream);
+/* clip_max_ws != NULL: mel is the AL_MEL_RAW output of al_mel_forward_ex and the extractor's floor + affine step is
+ * applied while packing (bit-identical to al_mel_forward followed by al_pack_mel). */
+int al_pack_mel_ex(const float* mel, const unsigned int* clip_max_ws, void* out_bf16, int B, int n_mels, int T,
+                   int c_pad, al_stream_t stream);
 int al_f32_to_bf16(const float* x, void* out_bf16, long long n, al_stream_t stream);
 
 /* ---- E1/E2: frozen Whisper encoder forward --------------------------------------------------------
@@ -135,6 +145,10 @@ int al_encoder_set_options(al_encoder* e, int attention_flags);
 /* mel [B][n_mels][3000] f32 -> out [B][1500][d] (out_dtype 0 bf16 / 1 f32). n_layers_run < 0 = all. */
 int al_encoder_forward(al_encoder* e, const float* mel, int B, void* out, int out_dtype, int n_layers_run,
                        al_stream_t stream);
+/* The same with mel = the AL_MEL_RAW output of al_mel_forward_ex and its clip_max_ws: the per-clip floor and the
+ * (x + 4) / 4 step run inside the plan's first kernel (the f32 mel is written once and read once). */
+int al_encoder_forward_ex(al_encoder* e, const float* mel, const unsigned int* clip_max_ws, int B, void* out,
+                          int out_dtype, int n_layers_run, al_stream_t stream);
 /* Live per-kernel timing of the plan's launches (CUDA events recorded on the launch stream around every
  * kernel while profiling is on). al_encoder_profile_read synchronises, sums milliseconds and launch counts per
  * kind since the last read / set, and resets. Kinds index ms_by_kind_host[AL_K_COUNT]. */
@@ -223,17 +237,22 @@ int al_linear_ce(const void* h, const void* W, const void* W_T, const long long*
  *   table [vocab][d] (elem_bytes 2 or 4), input_ids / attn_mask / labels [B][t_txt] int64 (mask, labels may
  *   be NULL), audio_rows [B][n_audio][d] or NULL when the projector already wrote them in place,
  *   out [B][n_audio+2+t_txt][d]; mask_out float32, labels_out int64 (either may be NULL).
- * The delimiter-id bounds check (ValueError, allm.py:140-141) is the host wrapper's job. */
+ * vocab = rows of `table`. Delimiter ids >= vocab are refused (-1; the reference's ValueError, allm.py:140-141).
+ * An input id outside [0, vocab) -- on which the reference's embed_tokens(input_ids) raises (allm.py:64) -- is never
+ * used as an address: its output row is zeroed and *bad_id_flag (device int32, may be NULL) is OR-ed with 1; the
+ * host wrapper turns the flag into the exception. */
 int al_splice(const void* table, int elem_bytes, int d, const long long* input_ids, const long long* attn_mask,
               const long long* labels, int B, int t_txt, int n_audio, long long start_id, long long end_id,
-              const void* audio_rows, void* out, float* mask_out, long long* labels_out, al_stream_t stream);
+              const void* audio_rows, void* out, float* mask_out, long long* labels_out, long long vocab,
+              int* bad_id_flag, al_stream_t stream);
 /* Ragged extension (config 5; not in the reference): see audio_llama_b200/splice.py. span_start_out
  * [B][max_spans] int32 receives the device-computed exclusive prefix sums. */
 int al_splice_ragged(const void* table, int elem_bytes, int d, const long long* input_ids,
                      const long long* attn_mask, const long long* labels, int B, int t_txt, int S_out,
                      const int* span_rows, const int* span_src_row, const int* n_spans, int max_spans,
                      const void* audio_rows, long long start_id, long long end_id, void* out, float* mask_out,
-                     long long* labels_out, int* span_start_out, al_stream_t stream);
+                     long long* labels_out, int* span_start_out, long long vocab, int* bad_id_flag,
+                     al_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,12 @@ def test_linear_cross_entropy(rows, d, V, chunk):
     lz.backward()
     assert float(lz) == 0.0 and float(hz.grad.abs().max()) == 0.0
     del logits
+    # a label >= vocab (torch asserts on it): nothing outside the logits row is read and the loss turns NaN
+    bad = labels.clone()
+    bad[1] = V + 5
+    hb = h.clone().requires_grad_(True)
+    lb = LN.linear_cross_entropy(hb, W, bad, chunk_rows=chunk)
+    assert torch.isnan(lb)
 
 
 def test_causal_lm_loss_shift():

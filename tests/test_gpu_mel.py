@@ -148,3 +148,19 @@ def test_unaligned_wave_pointer():
     from audio_llama_b200._lib import check, ptr, stream_ptr
     check(lib().al_mel_forward(ptr(view), ptr(ns), 2, 480001, 128, 0, ptr(out), ptr(ws), stream_ptr()), "al_mel_forward")
     assert (out.cpu().numpy() == ref).all()
+
+
+def test_raw_then_fused_pack_is_bit_identical():
+    """AL_MEL_RAW + the floor / affine step inside pack_mel (what the pipeline runs) == al_mel_forward followed by
+    pack_mel, bit for bit, on a ragged batch (per-clip maxima differ)."""
+    from audio_llama_b200 import synth
+    waves = torch.from_numpy(synth.synth_batch(3)).cuda()
+    waves[1, 200000:] = 0                                          # a quieter clip: another per-clip floor
+    n = torch.tensor([480000, 200000, 123457], dtype=torch.int32, device="cuda")
+    final = ops.mel_forward(waves, n, n_mels=128)
+    two_pass = ops.pack_mel(final, 128)
+    ws = torch.empty(3, dtype=torch.int32, device="cuda")
+    raw = ops.mel_forward(waves, n, n_mels=128, ws=ws, raw=True)
+    assert not torch.equal(raw, final)
+    fused = ops.pack_mel(raw, 128, clip_max=ws)
+    assert torch.equal(two_pass, fused)

@@ -77,6 +77,54 @@ def test_splice_bad_delimiter_raises():
         ops.splice(E, torch.zeros(1, 3, dtype=torch.long).cuda(), None, None, 5, 10, 9)
 
 
+@pytest.mark.parametrize("bad", [-1, 300, 2 ** 40])
+def test_splice_out_of_range_input_id_raises(bad):
+    """An input id outside the table: the reference's embed_tokens(input_ids) raises (allm.py:64). The kernel must not
+    read outside the table (guard rows around it stay intact), zeroes that output row, and the host side raises."""
+    vocab, d, B, T, A = 300, 64, 2, 9, 4
+    big = torch.full((vocab + 2, d), 7.0).cuda()                     # guard row before and after the real table
+    E = big[1:1 + vocab]
+    E.copy_(torch.randn(vocab, d, generator=torch.Generator().manual_seed(0)))
+    ids, mask, labels = synth.synth_text(B, T, vocab)
+    ids[1, 3] = bad
+    with pytest.raises(IndexError):
+        ops.splice(E, ids.cuda(), mask.cuda(), labels.cuda(), A, vocab - 2, vocab - 1, audio_rows=None)
+    # deferred form: no exception at the call, rows of good ids exact, the bad row zeroed, the flag raised later
+    out, _, _ = ops.splice(E, ids.cuda(), mask.cuda(), labels.cuda(), A, vocab - 2, vocab - 1, audio_rows=None, check_ids=False)
+    good = ids.clone()
+    good[1, 3] = 0
+    ref = E.cpu()[good]
+    ref[1, 3] = 0
+    assert torch.equal(out[:, A + 2:].cpu(), ref)
+    assert (out[:, A + 2:] != 7.0).all()                             # nothing came from the guard rows
+    with pytest.raises(IndexError):
+        ops.raise_if_bad_ids(E.device, vocab)
+    ops.raise_if_bad_ids(E.device, vocab)                            # the flag was cleared
+    # ragged form
+    from audio_llama_b200.splice import splice_ragged
+    audio = torch.randn(B, 1500, d).cuda()
+    with pytest.raises(IndexError):
+        splice_ragged(E, ids.cuda(), mask.cuda(), labels.cuda(), audio, [[10], [20]], vocab - 2, vocab - 1)
+
+
+def test_layernorm_and_projector_refuse_fp16_output():
+    x = torch.randn(8, 64).cuda()
+    with pytest.raises(TypeError):
+        ops.layernorm(x, torch.ones(64).cuda(), torch.zeros(64).cuda(), out=torch.empty(8, 64, dtype=torch.float16).cuda())
+    from audio_llama_b200.models.projector import projector_forward_raw
+    pw = synth.init_projector_weights(64, 32, seed=0)
+    pw = {k: v.cuda() for k, v in pw.items()}
+    with pytest.raises(TypeError):
+        projector_forward_raw(pw, torch.randn(8, 64).bfloat16().cuda(), out=torch.empty(8, 32, dtype=torch.float16).cuda(),
+                              rows_per_group=8, out_group_stride=0, out_row_offset=0)
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.pipeline import AudioConditioner
+    cfg = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+    with pytest.raises(TypeError):
+        AudioConditioner(cfg, synth.init_encoder_weights(cfg, seed=0), synth.init_projector_weights(128, 64, seed=1),
+                         torch.zeros(10, 64, dtype=torch.float16), 8, 9, max_batch=1)
+
+
 def test_f32_to_bf16():
     x = torch.randn(4096 * 3)
     assert torch.equal(ops.f32_to_bf16(x.cuda()).cpu(), x.bfloat16())

@@ -303,3 +303,63 @@ def test_pack_lora_operands():
     ref = (x @ (Bm @ A).T) * 0.25
     got = (x @ a.float().T) @ b.float().T
     assert torch.allclose(got, ref, rtol=0, atol=0.15)          # bf16 operand rounding
+
+
+def test_causal_only_mask_needs_ignored_pad_labels():
+    """The mask is only dropped when every padded position is out of the loss (labels -100 there): the reference's
+    dataset pads labels with token ids (dataset.py:82-92), and a padded query DOES see other keys without the mask."""
+    from audio_llama_b200.llama_native import causal_only_mask
+    m = torch.tensor([[1, 1, 1, 0, 0], [1, 1, 1, 1, 1]])
+    ignored = torch.tensor([[5, 6, 7, -100, -100], [1, 2, 3, 4, 5]])
+    padded_with_ids = torch.tensor([[5, 6, 7, 0, 0], [1, 2, 3, 4, 5]])
+    assert causal_only_mask(m, ignored) is None
+    assert causal_only_mask(m, padded_with_ids) is m
+    assert causal_only_mask(m, None) is None
+
+
+def test_flat_bucket_survives_zero_grad_set_to_none():
+    """optimizer.zero_grad() (set_to_none=True, what the reference loop calls, train.py:300) detaches the gradients from
+    the bucket; the next allreduce_mean() must gather the fresh gradients back instead of reducing stale zeros."""
+    from audio_llama_b200.parallel import FlatGradBucket
+    torch.manual_seed(0)
+    lin = nn.Linear(4, 3)
+    params = list(lin.parameters())
+    bucket = FlatGradBucket(params)
+    opt = torch.optim.SGD(params, lr=0.1)
+    x = torch.randn(5, 4)
+    for step in range(3):
+        lin(x).pow(2).sum().backward()
+        want = torch.cat([p.grad.reshape(-1).clone() for p in params])
+        flat = bucket.allreduce_mean()                      # world size 1: gathers, no communication
+        assert torch.equal(flat, want), step
+        assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() and
+                   p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4 for p in params)
+        opt.step()
+        opt.zero_grad()                                     # default set_to_none=True
+        assert all(p.grad is None for p in params)
+    # and the documented alternative keeps the views alive
+    lin(x).sum().backward()
+    bucket.allreduce_mean()
+    opt.zero_grad(set_to_none=False)
+    assert bucket.rebind() == 0 and float(bucket.flat.abs().sum()) == 0.0
+
+
+def test_place_audio_rows_autograd():
+    """_PlaceAudioRows: in-place row placement whose backward is the slice of the gradient (replaces the reference's
+    4-way torch.cat, allm.py:165-170, on the training path)."""
+    from audio_llama_b200.models.allm import AudioLLM, _PlaceAudioRows
+    torch.manual_seed(1)
+    B, A, T, d = 2, 5, 3, 8
+    emb = torch.randn(B, A + 2 + T, d)
+    proj = torch.randn(B, A, d, dtype=torch.float64, requires_grad=True)
+    ref = torch.cat([emb[:, :1], proj.to(emb.dtype), emb[:, A + 1:]], dim=1)
+    w = torch.randn_like(ref)
+    (g_ref,) = torch.autograd.grad((ref * w).sum(), proj)
+    out = AudioLLM._place(emb.clone(), proj, A)
+    assert torch.equal(out, ref.detach())
+    (g,) = torch.autograd.grad((out * w).sum(), proj)
+    assert g.dtype == torch.float64 and torch.equal(g, g_ref)
+    # without gradients it is a plain in-place store
+    with torch.no_grad():
+        e2 = emb.clone()
+        assert AudioLLM._place(e2, proj, A) is e2 and torch.equal(e2, ref.detach())
