@@ -7,8 +7,10 @@
 * `train_log_mel(...)` is the MelSpectrogram + log of AudioLLMDataset._process_audio
   (/root/reference/src/dataset.py:101-143) for already-loaded waveforms.
 
-The arithmetic is `al_mel_forward` (one fused kernel + the per-clip floor pass). Decoding / resampling audio
-files is not on the hot path and stays with torchaudio, as in the reference.
+The arithmetic is `al_mel_forward` (one fused kernel + the per-clip floor pass). Only DECODING the file stays on
+the host (torchaudio.load, or the stdlib `wave` reader when torchaudio has no backend): the mono mix, the sinc
+resampling and the 30 s pad / truncate run on the GPU through `al_ingest_forward` (audio_llama_b200/ingest.py), in
+the order each reference caller uses.
 """
 from __future__ import annotations
 
@@ -56,23 +58,86 @@ class LogMelExtractor:
             raise ValueError(f"The model corresponding to this feature extractor was trained using a sampling rate of "
                              f"{self.sampling_rate}. Please make sure that the provided `raw_speech` input was sampled "
                              f"with {self.sampling_rate} and not {sampling_rate}.")
-        wave, n = _to_batch(raw_speech, self.device)
-        feats = ops.mel_forward(wave, n, n_mels=self.feature_size, mode=ops.MEL_WHISPER)
+        n_samples = kwargs.get("n_samples")
+        if isinstance(raw_speech, torch.Tensor) and raw_speech.is_cuda and raw_speech.dtype == torch.float32:
+            # already on the GPU (e.g. the output of ingest.ingest): no host round trip
+            wave = raw_speech if raw_speech.dim() == 2 else raw_speech.unsqueeze(0)
+            n = n_samples
+        else:
+            wave, n = _to_batch(raw_speech, self.device)
+        feats = ops.mel_forward(wave.contiguous(), n, n_mels=self.feature_size, mode=ops.MEL_WHISPER)
         return SimpleNamespace(input_features=feats)
 
 
+def load_audio(audio_path):
+    """Decode an audio file on the host -> (waveform [channels, n] float32 in [-1, 1], sample_rate): torchaudio.load as
+    the reference calls it (inference.py:84, dataset.py:105), or the stdlib WAV reader (PCM 8/16/24/32-bit) when this
+    torchaudio build has no decoding backend."""
+    import os
+    if not os.path.exists(audio_path):
+        raise FileNotFoundError(f"Audio file not found: {audio_path}")          # dataset.py:102-103
+    try:
+        import torchaudio
+        waveform, sr = torchaudio.load(audio_path)
+        return waveform.to(torch.float32), int(sr)
+    except (ImportError, RuntimeError, OSError):
+        import wave
+        with wave.open(audio_path, "rb") as f:
+            ch, width, sr, n = f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()
+            raw = f.readframes(n)
+        if width == 1:
+            x = (np.frombuffer(raw, np.uint8).astype(np.float32) - 128.0) / 128.0
+        elif width == 2:
+            x = np.frombuffer(raw, "<i2").astype(np.float32) / 32768.0
+        elif width == 3:
+            b = np.frombuffer(raw, np.uint8).reshape(-1, 3).astype(np.int32)
+            v = b[:, 0] | (b[:, 1] << 8) | (b[:, 2] << 16)
+            x = ((v ^ 0x800000) - 0x800000).astype(np.float32) / 8388608.0
+        elif width == 4:
+            x = np.frombuffer(raw, "<i4").astype(np.float32) / 2147483648.0
+        else:
+            raise RuntimeError(f"unsupported WAV sample width {width}")
+        return torch.from_numpy(x.reshape(-1, ch).T.copy()), int(sr)
+
+
 def process_audio(audio_path, processor, max_length=30, sample_rate=16000, device="cuda"):
-    """Same contract as the reference's process_audio: file -> input_features [1, n_mels, 3000] on `device`."""
-    import torchaudio
-    waveform, sr = torchaudio.load(audio_path)
-    if waveform.shape[0] > 1:
-        waveform = torch.mean(waveform, dim=0, keepdim=True)
-    if sr != sample_rate:
-        waveform = torchaudio.transforms.Resample(orig_freq=sr, new_freq=sample_rate)(waveform)
-    max_samples = sample_rate * max_length
-    if waveform.shape[1] > max_samples:
-        waveform = waveform[:, :max_samples]
-    return processor(waveform.squeeze(0), sampling_rate=sample_rate, return_tensors="pt").input_features.to(device)
+    """Same contract as the reference's process_audio (/root/reference/src/inference.py:79-111): file ->
+    input_features [1, n_mels, 3000] on `device`. The file is decoded on the host; mono mix, resampling to
+    `sample_rate` and the truncation to `max_length` seconds (in that order, inference.py:88-98) run on the GPU
+    (al_ingest_forward). With a LogMelExtractor as `processor` the waveform never leaves the GPU; any other processor
+    (the HF one) is handed the waveform on the host exactly as the reference does."""
+    from .ingest import ingest
+    waveform, sr = load_audio(audio_path)
+    if sample_rate != SAMPLE_RATE or max_length != 30:
+        raise ValueError("the GPU ingest path is fixed to 16 kHz / 30 s clips (the reference's defaults)")
+    wave, n = ingest([waveform], sr, mode="inference", device=device, target_sr=sample_rate)
+    if isinstance(processor, LogMelExtractor):
+        return processor(wave, sampling_rate=sample_rate, n_samples=n).input_features
+    mono = wave[0, : int(n.item())].cpu()
+    return processor(mono, sampling_rate=sample_rate, return_tensors="pt").input_features.to(device)
+
+
+def dataset_process_audio(audio_path, max_audio_length: int = 30, sample_rate: int = SAMPLE_RATE, n_mels: int = 128,
+                          device="cuda") -> torch.Tensor:
+    """AudioLLMDataset._process_audio(path) (/root/reference/src/dataset.py:101-143) on the GPU: file ->
+    log(MelSpectrogram + 1e-9) [1, 128, 3000] float32 (the TRAINING feature variant, M2). Order as the dataset: pad /
+    truncate the decoded file to max_audio_length * sample_rate INPUT samples first (106-112), then mono mix and
+    resampling (114-123), then the mel transform (125-133) and the crop to 3000 frames (136-137).
+    Bug-compatibility: for a file sampled ABOVE 16 kHz the reference's resampled clip is shorter than 3000 frames and
+    its 80-row padding branch (138-140) fails inside torch.cat, so __getitem__ drops the sample (69-72); the same
+    RuntimeError is raised here instead of inventing features the reference never produced. (For a file BELOW 16 kHz
+    that is longer than 15 s the reference's frame 2999 reads 40 resampled samples past 480 000; here the clip ends at
+    480 000 and that one frame sees the reflected edge instead.)"""
+    from .ingest import ingest
+    waveform, sr = load_audio(audio_path)
+    if sample_rate != SAMPLE_RATE or max_audio_length != 30:
+        raise ValueError("the GPU ingest path is fixed to 16 kHz / 30 s clips (the reference's defaults)")
+    if sr > sample_rate:
+        raise RuntimeError(f"Sizes of tensors must match except in dimension 2. Expected size {n_mels} but got size 80 "
+                           f"(the reference pads short clips with 80 rows, dataset.py:138-140: a {sr} Hz file cannot be "
+                           f"processed by AudioLLMDataset._process_audio)")
+    wave, n = ingest([waveform], sr, mode="train", device=device, target_sr=sample_rate)
+    return ops.mel_forward(wave, n, n_mels=n_mels, mode=ops.MEL_TRAIN)
 
 
 def train_log_mel(waveform: Union[torch.Tensor, Sequence], n_mels: int = 128, device="cuda") -> torch.Tensor:

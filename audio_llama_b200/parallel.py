@@ -72,6 +72,80 @@ class FlatGradBucket:
             off += p.numel()
         return n
 
+    # ------------------------------------------------------------------ overlapped form
+    def arm_overlap(self, n_chunks: int = 4, group=None):
+        """Overlap the exchange with the backward pass: the bucket is cut into `n_chunks` contiguous chunks (parameter
+        boundaries), and a chunk's all-reduce is launched (async, on the communicator's own stream) from the
+        post-accumulate-grad hook of the LAST of its parameters to receive its gradient. Parameters are laid out in the
+        order given to the constructor; backward produces gradients roughly in reverse order (last LLaMA layers first,
+        the projector last), so chunks complete from the back and the early ones ride under the remaining backward.
+        Call once; then every step: backward(), finish_overlap() (waits, divides by the world size), clip, step,
+        zero() or zero_grad(set_to_none=False). Requires the gradients to stay views of the bucket."""
+        if getattr(self, "_ov", None) is not None:
+            return self
+        n = len(self.params)
+        n_chunks = max(1, min(n_chunks, n))
+        # chunk boundaries: equal element counts, snapped to parameter boundaries
+        sizes = [p.numel() for p in self.params]
+        target = self.numel / n_chunks
+        bounds, acc, start = [], 0, 0
+        for i, sz in enumerate(sizes):
+            acc += sz
+            if acc >= target * (len(bounds) + 1) and len(bounds) < n_chunks - 1:
+                bounds.append((start, i + 1))
+                start = i + 1
+        bounds.append((start, n))
+        offs = [0]
+        for sz in sizes:
+            offs.append(offs[-1] + sz)
+        chunks = []
+        for (a, b) in bounds:
+            chunks.append(dict(lo=offs[a], hi=offs[b], n_params=b - a, pending=b - a, work=None))
+        owner = {}
+        for ci, (a, b) in enumerate(bounds):
+            for i in range(a, b):
+                owner[i] = ci
+        self._ov = dict(chunks=chunks, group=group, handles=[])
+
+        def make_hook(ci):
+            def hook(param):
+                ch = self._ov["chunks"][ci]
+                ch["pending"] -= 1
+                if ch["pending"] == 0 and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                    ch["work"] = dist.all_reduce(self.flat[ch["lo"]:ch["hi"]], op=dist.ReduceOp.SUM, group=group, async_op=True)
+            return hook
+
+        for i, p in enumerate(self.params):
+            self._ov["handles"].append(p.register_post_accumulate_grad_hook(make_hook(owner[i])))
+        return self
+
+    def disarm_overlap(self):
+        """Remove the gradient hooks (back to the explicit allreduce_mean() form)."""
+        ov = getattr(self, "_ov", None)
+        if ov is not None:
+            for h in ov["handles"]:
+                h.remove()
+            self._ov = None
+
+    def finish_overlap(self):
+        """Wait for the chunk all-reduces of this step (launching those whose parameters received no gradient), divide by
+        the world size, re-arm. Returns the flat gradient."""
+        ov = self._ov
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(ov["group"]) > 1
+        if self.rebind() != 0 and multi:
+            raise RuntimeError("FlatGradBucket: gradients were detached from the bucket during an overlapped step "
+                               "(use bucket.zero() or zero_grad(set_to_none=False))")
+        for ch in ov["chunks"]:
+            if multi:
+                if ch["work"] is None:             # some parameter of the chunk got no gradient this step
+                    ch["work"] = dist.all_reduce(self.flat[ch["lo"]:ch["hi"]], op=dist.ReduceOp.SUM, group=ov["group"], async_op=True)
+                ch["work"].wait()
+            ch["work"] = None
+            ch["pending"] = ch["n_params"]
+        if multi:
+            self.flat.div_(dist.get_world_size(ov["group"]))
+        return self.flat
+
     def allreduce_mean(self, group=None):
         """sum over ranks then / world (the gradient of the mean loss over the global batch). Gradients that were
         detached from the bucket since the last call (zero_grad(set_to_none=True)) are gathered back first."""

@@ -201,6 +201,48 @@ def run_reference(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------- secondary record: configs[4]
+def run_config5(cond, dev, rank, world, timed):
+    """Variable-length clips (1-30 s), 1-3 <audio> spans per sample (SURVEY.md §8 extension row; recipe of §8d: clip i
+    has N_i = rng(seed + i).integers(16000, 480001) samples, sample b has rng.integers(1, 4) spans). 16 samples per GPU.
+    The reference has no such path (it pads every clip to 30 s and takes one clip per sample), so its parity is pinned
+    only by this repo's own oracle; the metric counts the REAL audio seconds of the clips."""
+    n_samples_b = 16
+    g = np.random.default_rng(4321 + rank)
+    spans = [int(g.integers(1, 4)) for _ in range(n_samples_b)]
+    n_clips = sum(spans)
+    lens = [int(np.random.default_rng(1234 + rank * 1000 + i).integers(16000, 480001)) for i in range(n_clips)]
+    wave = np.zeros((n_clips, 480000), np.float32)
+    for i, n in enumerate(lens):
+        wave[i, :n] = synth.synth_clip(rank * 1000 + i, n_samples=n)
+    wave_d = torch.from_numpy(wave).to(dev)
+    n_d = torch.tensor(lens, dtype=torch.int32, device=dev)
+    ids, mask, labels = (t.to(dev) for t in synth.synth_text(n_samples_b, T_TXT, VOCAB, seed=99 + rank))
+    old_max = cond.max_batch
+
+    def step():
+        cond.forward_ragged(wave_d, n_d, spans, ids, mask, labels)
+
+    for _ in range(2):
+        step()
+    steps = 5
+    ms = timed(step, steps) / steps
+    audio_s = sum(lens) / 16000.0
+    tot = torch.tensor([audio_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tot)
+    assert cond.max_batch == old_max
+    if rank != 0:
+        return None
+    return {"workload": "configs[4]: variable-length clips (1-30 s), 1-3 <audio> spans per sample, ragged splice + padding "
+                        f"masks; {n_samples_b} samples / {n_clips} clips per GPU, turbo encoder + projector -> Llama-3.2-1B embeds",
+            "ms_per_step": ms, "steps": steps, "clips_per_gpu": n_clips, "real_audio_s_per_step": float(tot.item()),
+            "audio_s_per_s": float(tot.item()) / (ms / 1e3),
+            "padded_audio_s_per_s": world * n_clips * CLIP_S / (ms / 1e3),
+            "parity": "unpinned by the reference (extension; pinned by oracle.encoder.combine_ragged only)"}
+
+
 # ----------------------------------------------------------------------------- product arm
 def run_product(args):
     import torch.distributed as dist
@@ -225,7 +267,6 @@ def run_product(args):
     table = (torch.randn(VOCAB, D_LLAMA, generator=torch.Generator().manual_seed(2)) * 0.02).to(torch.bfloat16)
     cond = AudioConditioner(cfg, ew, pw, table.to(dev), VOCAB - 2, VOCAB - 1, max_batch=B, device=dev)
     workload = WORKLOAD if B == BATCH else WORKLOAD.replace("batch 32", f"batch {B}")
-    del ew
 
     # this rank's shard of the global batch (weak scaling: 32 clips per rank), pinned host buffers
     from audio_llama_b200.pipeline import HostBatch
@@ -341,6 +382,17 @@ def run_product(args):
     splice_ms = sp0.elapsed_time(sp1) / (4 * SPLICE_SETS)
     del sp_out, sp_ids
 
+    # --- secondary records (headline unchanged): the ragged extension (configs[4]) and the README training step with
+    #     its gradient exchange (configs[2]); every rank takes part, rank 0 reports
+    config5 = None if args.no_config5 else run_config5(cond, dev, rank, world, timed)
+    config3 = None
+    if not args.no_config3:
+        from audio_llama_b200 import train_step
+        del emb_d
+        torch.cuda.empty_cache()
+        config3 = train_step.run_config3(dev, rank, world, llama="3b", batch=8, steps=3, warmup=1, encoder_weights=ew)
+    del ew
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -412,6 +464,8 @@ def run_product(args):
                      "flops_per_launch_avg": gemm_flops / max(gemm_launches, 1), "traffic": traffic},
         "kernels": kernels,
         "cpu_baseline": cpu,
+        "config3": config3,
+        "config5": config5,
     }
     emit(line)
     if world > 1:
@@ -445,6 +499,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true", help="skip the secondary README-training-step record")
+    ap.add_argument("--no-config5", action="store_true", help="skip the secondary ragged-clip record")
     ap.add_argument("--clips", type=int, default=BATCH, help="clips per GPU per step (config 4 uses 256)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -93,6 +93,27 @@ def encoder_golden():
     np.savez_compressed(os.path.join(HERE, "encoder_hf.npz"), **out)
 
 
+def encoder_turbo_golden():
+    """The named architecture itself (whisper-large-v3-turbo encoder: d=1280, 32 layers, 20 heads, 128 mel) with the
+    seeded random-init weights of audio_llama_b200.synth, ONE clip, through the installed HF WhisperEncoder in fp32 on
+    the CPU (about a minute). Written to its own file so that the small fixtures need not be regenerated with it."""
+    from transformers import WhisperConfig, WhisperModel
+    from audio_llama_b200.config import WHISPER_LARGE_V3_TURBO as cfg
+    hf_cfg = WhisperConfig(vocab_size=51866, num_mel_bins=cfg.n_mels, d_model=cfg.d_model,
+                           encoder_layers=cfg.n_layers, encoder_attention_heads=cfg.n_heads,
+                           encoder_ffn_dim=cfg.ffn_dim, decoder_layers=1, decoder_attention_heads=cfg.n_heads,
+                           decoder_ffn_dim=cfg.ffn_dim, max_source_positions=1500)
+    enc = WhisperModel(hf_cfg).eval().encoder
+    enc.load_state_dict(synth.init_encoder_weights(cfg, seed=0, ln_jitter=0.1), strict=True)
+    mel = torch.from_numpy(encoder_input(cfg, 1))
+    with torch.no_grad():
+        y = enc(mel).last_hidden_state
+    out = {"turbo_grid": y[:, ::25, ::16].numpy().copy(), "turbo_row7": y[:, 7, :].numpy().copy(),
+           "turbo_row1499": y[:, 1499, :].numpy().copy(),
+           "turbo_norm": np.array([float(y.double().norm()), float(y.double().sum())])}
+    np.savez_compressed(os.path.join(HERE, "encoder_hf_turbo.npz"), **out)
+
+
 def reference_modules_golden():
     from models.projector import AudioProjector
     from models.lora import LoRALayer, lora_forward_hook
@@ -232,6 +253,10 @@ def checkpoint_golden():
 
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "turbo":      # python tests/golden/make_golden.py turbo
+        encoder_turbo_golden()
+        print("encoder_hf_turbo.npz", os.path.getsize(os.path.join(HERE, "encoder_hf_turbo.npz")))
+        sys.exit(0)
     mel_golden()
     encoder_golden()
     reference_modules_golden()

@@ -83,6 +83,34 @@ def test_encoder_turbo_one_clip():
     assert rel <= TOL, rel
 
 
+def test_encoder_turbo_matches_hf_golden(golden_dir):
+    """The named architecture (whisper-large-v3-turbo encoder) against the installed HF WhisperEncoder itself (fp32 CPU
+    run of tests/golden/make_golden.py turbo): sub-sampled grid and two full rows, rel-L2 <= 2e-2 (north-star bound)."""
+    g = np.load(os.path.join(golden_dir, "encoder_hf_turbo.npz"))
+    cfg = WHISPER_LARGE_V3_TURBO
+    w = synth.init_encoder_weights(cfg, seed=0, ln_jitter=0.1)
+    enc = WhisperEncoderB200(cfg, w, max_batch=1, out_dtype=torch.float32)
+    y = enc(torch.from_numpy(encoder_input(cfg, 1)).cuda()).cpu()
+    assert O.rel_l2(y[:, ::25, ::16], torch.from_numpy(g["turbo_grid"])) <= TOL
+    assert O.rel_l2(y[:, 7, :], torch.from_numpy(g["turbo_row7"])) <= TOL
+    assert O.rel_l2(y[:, 1499, :], torch.from_numpy(g["turbo_row1499"])) <= TOL
+    nrm = float(y.double().norm())
+    assert abs(nrm - g["turbo_norm"][0]) <= 1e-2 * g["turbo_norm"][0]
+
+
+def test_encoder_turbo_batch_independence():
+    """Turbo shape, B = 3 (M = 4500 rows: the 256-row GEMM tiles and the attention tiles straddle clip boundaries):
+    clip 1 alone is bit-identical to clip 1 inside the batch, and so is the last clip."""
+    cfg = WHISPER_LARGE_V3_TURBO
+    w = synth.init_encoder_weights(cfg, seed=0, ln_jitter=0.1)
+    enc = WhisperEncoderB200(cfg, w, max_batch=3, out_dtype=torch.bfloat16)
+    mel = torch.from_numpy(encoder_input(cfg, 3)).cuda()
+    y3 = enc(mel).clone()
+    assert torch.equal(enc(mel[1:2]), y3[1:2])
+    assert torch.equal(enc(mel[2:3]), y3[2:3])
+    assert not torch.equal(y3[0], y3[1])
+
+
 @pytest.mark.parametrize("d_in,d_out,rows", [(384, 256, 300), (1280, 2048, 1500), (1280, 3072, 257)])
 def test_projector(d_in, d_out, rows):
     from audio_llama_b200.models.projector import projector_forward_raw

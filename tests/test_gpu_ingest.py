@@ -56,3 +56,64 @@ def test_ingest_feeds_mel():
     f = ops.mel_forward(wave, n).cpu().numpy()[0]
     ref = M.log_mel_whisper([R.ingest_inference(x, 44100)], 128)[0]
     assert np.abs(f - ref).max() <= 1e-4
+
+
+def _write_wav(path, x, sr):
+    """[channels, n] float32 in [-1, 1] -> 16-bit PCM WAV (stdlib)."""
+    import wave
+    pcm = np.clip(np.round(x.T * 32768.0), -32768, 32767).astype("<i2")
+    with wave.open(str(path), "wb") as f:
+        f.setnchannels(x.shape[0])
+        f.setsampwidth(2)
+        f.setframerate(sr)
+        f.writeframes(pcm.tobytes())
+    return pcm.astype(np.float32).T / 32768.0              # what a decoder returns
+
+
+def test_process_audio_file_api(tmp_path):
+    """features.process_audio(path, processor) -- the reference's inference.process_audio (inference.py:79-111) -- on a
+    stereo 22.05 kHz file: decode on the host, mono mix + resample + truncate + log-mel on the GPU."""
+    from audio_llama_b200.features import LogMelExtractor, process_audio
+    x = resample_input(22050)
+    dec = _write_wav(tmp_path / "a.wav", x, 22050)
+    f = process_audio(str(tmp_path / "a.wav"), LogMelExtractor(128))
+    assert f.shape == (1, 128, 3000) and f.is_cuda
+    ref = M.log_mel_whisper([R.ingest_inference(dec, 22050)], 128)
+    assert np.abs(f.cpu().numpy() - ref).max() <= 1e-4
+    # any other processor (the HF extractor's call convention) gets the mono waveform on the host
+    seen = {}
+
+    class HostProcessor:
+        def __call__(self, wave, sampling_rate=None, return_tensors=None):
+            from types import SimpleNamespace
+            seen["wave"], seen["sr"] = wave, sampling_rate
+            return SimpleNamespace(input_features=torch.zeros(1, 128, 3000))
+
+    process_audio(str(tmp_path / "a.wav"), HostProcessor())
+    want = R.ingest_inference(dec, 22050)
+    assert seen["sr"] == 16000 and not seen["wave"].is_cuda and seen["wave"].shape == (len(want),)
+    assert np.abs(seen["wave"].numpy() - want).max() <= 2e-5
+    with pytest.raises(FileNotFoundError):
+        process_audio(str(tmp_path / "missing.wav"), LogMelExtractor(128))
+
+
+def test_dataset_process_audio_file_api(tmp_path):
+    """features.dataset_process_audio(path) -- AudioLLMDataset._process_audio (dataset.py:101-143): pad / truncate the
+    decoded file to 480 000 input samples, mono mix, resample, ln(MelSpectrogram + 1e-9), crop to 3000 frames."""
+    from audio_llama_b200.features import dataset_process_audio
+    rng = np.random.default_rng(3)
+    x = (0.2 * rng.standard_normal((2, 30000))).astype(np.float32)          # stereo, 8 kHz, 3.75 s
+    dec = _write_wav(tmp_path / "b.wav", x, 8000)
+    f = dataset_process_audio(str(tmp_path / "b.wav"))
+    assert f.shape == (1, 128, 3000)
+    mono16k = R.ingest_train(dec, 8000)[:480000]
+    ref = M.log_mel_train([mono16k], 128)[0]
+    # (the resampler agrees with torchaudio to 2e-5 absolute on the waveform: bins that hold real signal energy are
+    #  compared; the empty upper half of an upsampled 8 kHz file is round-off in both implementations)
+    live = ref > -6.0
+    assert live.mean() > 0.03
+    assert np.abs(f.cpu().numpy() - ref)[live].max() <= 1e-3
+    # a file above 16 kHz: the reference's own padding branch fails (80 rows vs 128) and the sample is dropped
+    _write_wav(tmp_path / "c.wav", x, 22050)
+    with pytest.raises(RuntimeError):
+        dataset_process_audio(str(tmp_path / "c.wav"))

@@ -67,15 +67,20 @@ def test_mel_vs_oracle_and_golden(golden_dir, name, n_mels):
     mel_close(f[10, :], gm[k + "_row10"], "vs HF row")
 
 
-def test_mel_pure_tone(golden_dir):
+def test_mel_pure_tone(golden_dir, mel_form):
     gm = np.load(os.path.join(golden_dir, "mel_whisper.npz"))
     x = kat_signals()["sine440"]
     f = gpu_mel([x])[0]
     s, mn, mx = gm["sine440_128_stats"]
     assert abs(f.max() - mx) <= 1e-5 and abs(f.min() - mn) <= 1e-5
-    assert np.abs(f[::8, ::50] - gm["sine440_128_grid"]).max() <= 2e-3    # see test_oracle_golden.test_mel_oracle_pure_tone
+    # The tone is the worst case (80 dB of in-frame dynamic range, bins at the max - 8 floor). Gates = 2x the measured
+    # errors of profiles/r02_mel_errors.json (tools/mel_error_report.py on a B200): against the HF fixture grid
+    # 2.3e-6 (tensor-core form) / 1.4e-6 (FFT form), HF itself sitting 2.0e-6 from the float64 formula; against the
+    # float64 oracle over all 384 000 values 2.7e-5 / 9.4e-6 (a handful of floor-level bins).
+    assert np.abs(f[::8, ::50] - gm["sine440_128_grid"]).max() <= 5e-6
     ref64 = M.log_mel_whisper([x], 128, dtype=np.float64)[0]
-    assert np.abs(f - ref64).max() <= 2e-3
+    assert np.abs(f - ref64).max() <= (6e-5 if mel_form == "tc" else 2e-5)
+    assert np.linalg.norm(f - ref64) / np.linalg.norm(ref64) <= 1e-6
 
 
 def test_batch_ragged_equals_per_clip():

@@ -159,6 +159,61 @@ def _ddp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _ddp_overlap_worker(rank, world, port, out):
+    """Two steps with the overlapped (chunked, hook-driven) exchange; the second step also checks the re-arming."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    proj = nn.Sequential(nn.Linear(6, 5), nn.GELU(), nn.Linear(5, 4), nn.LayerNorm(4))
+    lora = LoRALayer(4, 3, rank=2)
+    unused = nn.Parameter(torch.zeros(3))                  # a trainable parameter that receives no gradient
+    with torch.no_grad():
+        lora.lora_A.normal_(0, 0.1)
+    params = list(proj.parameters()) + list(lora.parameters()) + [unused]
+    bucket = parallel.FlatGradBucket(params).arm_overlap(n_chunks=3)
+    g = torch.Generator().manual_seed(123)
+    x_all, y_all = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    lo, hi = parallel.shard_range(8, rank, world)
+    flats = []
+    for step in range(2):
+        bucket.zero()
+        loss = ((lora(proj(x_all[lo:hi] * (step + 1))) - y_all[lo:hi]) ** 2).mean()
+        loss.backward()
+        flats.append(bucket.finish_overlap().clone())
+    n_chunks = len(bucket._ov["chunks"])
+    bucket.disarm_overlap()                                # the reference pass below must not launch collectives
+    if rank == 0:
+        refs = []
+        for step in range(2):
+            for p in params:
+                p.grad = None
+            ((lora(proj(x_all * (step + 1))) - y_all) ** 2).mean().backward()
+            refs.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).flatten() for p in params]))
+        out.put((flats, refs, n_chunks))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_overlapped_world2_gloo():
+    """FlatGradBucket.arm_overlap / finish_overlap: chunk all-reduces launched from the gradient hooks during backward
+    give the gradient of the full batch, step after step, including a chunk whose parameter got no gradient."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_ddp_overlap_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    flats, refs, n_chunks = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert n_chunks == 3
+    for f, r in zip(flats, refs):
+        assert torch.allclose(f, r, atol=1e-6)
+
+
 def test_gradient_allreduce_world2_gloo():
     """One flat-bucket allreduce of projector + LoRA grads over 2 ranks == the gradient of the full batch."""
     import torch.multiprocessing as mp

@@ -81,9 +81,9 @@ def test_mel_oracle_matches_hf_noise_like(gm, name, n_mels):
 
 def test_mel_oracle_pure_tone(gm):
     """A pure tone has 80 dB of in-frame dynamic range: bins near the max-8 floor carry float32 FFT
-    round-off that is not small relative to THEM, so two float32 implementations legitimately differ by
-    more than 1e-5 there. max / min / sum still agree; element-wise agreement is checked at 2e-3 and the
-    float64 value is shown to sit equally far from HF (i.e. the spread is HF's own round-off)."""
+    round-off, so this is the worst case for element-wise agreement. Measured on the fixture grid: float32
+    oracle 1.8e-6, float64 oracle 2.0e-6 from HF (the spread is HF's own float32 round-off) -- gated at 5e-6,
+    i.e. within 2.5x of the measured value and still inside the north star's 1e-5."""
     x = kat_signals()["sine440"]
     f32 = M.log_mel_whisper([x], 128, dtype=np.float32)[0]
     f64 = M.log_mel_whisper([x], 128, dtype=np.float64)[0]
@@ -91,7 +91,7 @@ def test_mel_oracle_pure_tone(gm):
     for f in (f32, f64):
         assert abs(f.max() - mx) <= 1e-5 and abs(f.min() - mn) <= 1e-5
         assert abs(f.max() - f.min() - 2.0) <= 1e-5
-        assert np.abs(f[::8, ::50] - gm["sine440_128_grid"]).max() <= 2e-3
+        assert np.abs(f[::8, ::50] - gm["sine440_128_grid"]).max() <= 5e-6
     assert abs(f32[0, 0] - 0.9075196) < 1e-5
 
 
