@@ -143,15 +143,43 @@ int launch_pack_mel(const float* mel, void* out, int B, int n_mels, int T, int c
 //   normally writes them in place) ; A+1 <- E[</audio>] ; A+2+j <- E[input_ids[b][j]].
 // mask_out = [1.0f x (A+2), attention_mask] (float32, allm.py:192-194); labels_out = [-100 x (A+2), labels].
 // Four 16-byte loads in flight per lane before the first store (a 4 KB row is 8 of them per lane).
+#ifndef AL_SPLICE_VARIANT
+#define AL_SPLICE_VARIANT 2
+#endif
+// Streaming 16-byte accesses: every byte of the splice is read once and written once, so loads skip L1 allocation and
+// stores carry the cache-streaming hint (evict-first in L2: the written rows start their way to HBM at once instead of
+// lingering as dirty lines that a later kernel has to push out).
+__device__ __forceinline__ uint4 ld_stream_16B(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream_16B(uint4* p, const uint4& v) {
+#if AL_SPLICE_VARIANT >= 2
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#else
+  *p = v;
+#endif
+}
 __device__ __forceinline__ void copy_row_16B(void* dst, const void* src, int n16, int lane) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
   int i = lane;
-  for (; i + 96 < n16; i += 128) {
-    const uint4 a = __ldg(s + i), b = __ldg(s + i + 32), c = __ldg(s + i + 64), e = __ldg(s + i + 96);
-    d[i] = a; d[i + 32] = b; d[i + 64] = c; d[i + 96] = e;
+#if AL_SPLICE_VARIANT >= 1
+  // eight 16-byte loads in flight per lane before the first store (a 4 KB row = exactly one such batch per lane)
+  for (; i + 224 < n16; i += 256) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ld_stream_16B(s + i + 32 * k);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) st_stream_16B(d + i + 32 * k, v[k]);
   }
-  for (; i < n16; i += 32) d[i] = __ldg(s + i);
+#endif
+  for (; i + 96 < n16; i += 128) {
+    const uint4 a = ld_stream_16B(s + i), b = ld_stream_16B(s + i + 32), c = ld_stream_16B(s + i + 64), e = ld_stream_16B(s + i + 96);
+    st_stream_16B(d + i, a); st_stream_16B(d + i + 32, b); st_stream_16B(d + i + 64, c); st_stream_16B(d + i + 96, e);
+  }
+  for (; i < n16; i += 32) st_stream_16B(d + i, ld_stream_16B(s + i));
 }
 
 // COPY_AUDIO = true : one warp per output row, audio rows copied from `audio_rows`.

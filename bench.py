@@ -279,8 +279,11 @@ def run_product(args):
     emb_d = torch.empty(B, S, D_LLAMA, dtype=torch.bfloat16, device=dev)
     h2d, d2h = hb.h2d_bytes(), hb.d2h_bytes()
 
+    res_mask = torch.empty(B, S, dtype=torch.float32, device=dev)
+    res_lab = torch.empty(B, S, dtype=torch.int64, device=dev)
+
     def step_resident():
-        return cond(wave_d, ids_d, mask_d, labels_d, out=emb_d)
+        return cond(wave_d, ids_d, mask_d, labels_d, out=emb_d, mask_out=res_mask, labels_out=res_lab)
 
     def run_e2e(steps):
         # the public host-buffer call: every step uploads its waveforms / ids from pinned host memory and downloads
@@ -318,7 +321,8 @@ def run_product(args):
     # stage timers at the Python level (same stream): mel and projector+splice
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * args.steps)]
     stage_i = [0]
-    orig_call = cond.__call__
+    stage_mask = torch.empty(B, S, dtype=torch.float32, device=dev)
+    stage_lab = torch.empty(B, S, dtype=torch.int64, device=dev)
 
     def step_resident_staged():
         i = stage_i[0]
@@ -330,7 +334,8 @@ def run_product(args):
         from audio_llama_b200.models.projector import projector_forward_raw
         projector_forward_raw(cond.pw, enc.view(B * 1500, cfg.d_model), out=emb_d, rows_per_group=1500,
                               out_group_stride=S, out_row_offset=1, cache=cond._pcache)
-        ops.splice(cond.table, ids_d, mask_d, labels_d, 1500, cond.start_id, cond.end_id, audio_rows=None, out=emb_d)
+        ops.splice(cond.table, ids_d, mask_d, labels_d, 1500, cond.start_id, cond.end_id, audio_rows=None, out=emb_d,
+                   mask_out=stage_mask, labels_out=stage_lab, check_ids=False)
         ev[4 * i + 3].record()
         stage_i[0] += 1
 
@@ -370,13 +375,13 @@ def run_product(args):
     sp_mask, sp_lab = torch.empty(B, S, dtype=torch.float32, device=dev), torch.empty(B, S, dtype=torch.int64, device=dev)
     for k in range(SPLICE_SETS):
         ops.splice(cond.table, sp_ids[k], mask_d, labels_d, 1500, cond.start_id, cond.end_id, audio_rows=None, out=sp_out[k],
-                   mask_out=sp_mask, labels_out=sp_lab)
+                   mask_out=sp_mask, labels_out=sp_lab, check_ids=False)
     sp0, sp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sp0.record()
     for i in range(4 * SPLICE_SETS):
         k = i % SPLICE_SETS
         ops.splice(cond.table, sp_ids[k], mask_d, labels_d, 1500, cond.start_id, cond.end_id, audio_rows=None, out=sp_out[k],
-                   mask_out=sp_mask, labels_out=sp_lab)
+                   mask_out=sp_mask, labels_out=sp_lab, check_ids=False)
     sp1.record()
     torch.cuda.synchronize()
     splice_ms = sp0.elapsed_time(sp1) / (4 * SPLICE_SETS)
