@@ -191,7 +191,29 @@ class AudioLLM(nn.Module):
         self.projector = self.projector.to(device)
         for layer_name in self.lora_layers:
             self.lora_layers[layer_name] = self.lora_layers[layer_name].to(device)
-        return super().to(device)
+        out = super().to(device)
+        self._auto_enable_native(device)
+        return out
+
+    def _auto_enable_native(self, device):
+        """On a CUDA device with bf16 LLaMA weights the fused frozen + LoRA GEMM and the native row kernels are the
+        DEFAULT (the hook path runs two cuBLAS GEMMs and a dense [out, in] delta per linear). Anything
+        else (fp32 / fp16 LLaMA weights, CPU) keeps the reference's hook arithmetic, which stays the tested fallback;
+        which path is active is logged once. AUDIOLLM_B200_NATIVE=0 keeps the hooks everywhere."""
+        import logging
+        import os
+        log = logging.getLogger("audio_llama_b200")
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        w = next(self.llama.model.parameters())
+        want = dev.type == "cuda" and w.dtype == torch.bfloat16 and os.environ.get("AUDIOLLM_B200_NATIVE", "1") != "0"
+        if want and not getattr(self, "fused_lora", False):
+            self.enable_fused_lora()
+            self.enable_native_llama_ops()
+            log.info("AudioLLM: fused frozen+LoRA GEMMs and native LLaMA row kernels enabled (bf16 weights on %s)", dev)
+        elif not want and not getattr(self, "_logged_fallback", False):
+            self._logged_fallback = True
+            log.info("AudioLLM: LoRA runs through the reference-style forward hooks (LLaMA weights %s on %s: the fused "
+                     "kernels need bf16 on CUDA)", w.dtype, dev)
 
     # ------------------------------------------------------------------ allm.py:263-348
     def generate(self, input_ids=None, attention_mask=None, audio_features=None, max_new_tokens=256,

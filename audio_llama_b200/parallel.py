@@ -12,6 +12,21 @@ import torch
 import torch.distributed as dist
 
 
+def init_nccl(device) -> None:
+    """One process per GPU: NCCL process group whose collectives run on a HIGH-PRIORITY stream, so that the chunk
+    all-reduces launched during the backward pass (FlatGradBucket.arm_overlap) get SMs between the compute kernels
+    instead of queueing behind them. Rendezvous comes from the torchrun environment (RANK / WORLD_SIZE / MASTER_*)."""
+    opts = None
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    except Exception:
+        opts = None
+    if opts is not None:
+        dist.init_process_group("nccl", device_id=device, pg_options=opts)
+    else:
+        dist.init_process_group("nccl", device_id=device)
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous split of [0, n_items): rank r gets [lo, hi); the first n_items % world ranks get one extra."""
     if not (0 <= rank < world):
@@ -135,6 +150,7 @@ class FlatGradBucket:
         if self.rebind() != 0 and multi:
             raise RuntimeError("FlatGradBucket: gradients were detached from the bucket during an overlapped step "
                                "(use bucket.zero() or zero_grad(set_to_none=False))")
+        ov["launched_in_backward"] = sum(1 for ch in ov["chunks"] if ch["work"] is not None)
         for ch in ov["chunks"]:
             if multi:
                 if ch["work"] is None:             # some parameter of the chunk got no gradient this step

@@ -72,8 +72,10 @@ class TrainStep:
         self.params = model.get_trainable_params()
         self.bucket = parallel.FlatGradBucket(self.params)
         self.overlap = overlap and world > 1
+        self.n_chunks = 1
         if self.overlap:
             self.bucket.arm_overlap(n_chunks)
+            self.n_chunks = len(self.bucket._ov["chunks"])
         self.opt = torch.optim.AdamW(self.params, lr=lr)
         self.ids, self.mask, self.labels = (t.to(dev) for t in synth.synth_text(batch, t_txt, vocab, seed=7 + rank))
         self.fe = LogMelExtractor(ecfg.n_mels, device=dev)
@@ -90,6 +92,7 @@ class TrainStep:
         ev[1].record()
         if self.overlap:
             self.bucket.finish_overlap()
+            self.chunks_in_backward = self.bucket._ov.get("launched_in_backward")
         else:
             self.bucket.allreduce_mean()
         ev[2].record()
@@ -151,6 +154,8 @@ def run_config3(dev, rank: int, world: int, llama: str = "3b", batch: int = 8, s
         "optimizer_ms": mean["optimizer_ms"], "audio_s_per_s": world * batch * 30.0 / (mean["step_ms"] / 1e3),
         "trainable_params": ts.bucket.numel, "loss": ts.loss,
         "allreduce": {"bytes": nbytes, "overlapped_with_backward": bool(ts.overlap),
+                      "chunks": ts.n_chunks,
+                      "chunks_launched_during_backward": getattr(ts, "chunks_in_backward", None),
                       "exposed_ms": mean["exchange_exposed_ms"], "alone_ms": alone,
                       "bus_gbs": (2 * (world - 1) / world * nbytes / 1e9 / (alone / 1e3)) if alone else None},
         "llama": "stock HF LlamaForCausalLM, random init, fused frozen+LoRA GEMMs and native RMSNorm / SwiGLU / RoPE / "

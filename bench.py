@@ -257,7 +257,8 @@ def run_product(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from audio_llama_b200 import parallel
+        parallel.init_nccl(dev)
 
     cfg = WHISPER_LARGE_V3_TURBO
     B = args.clips

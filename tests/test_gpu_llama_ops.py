@@ -6,6 +6,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+def _manual(model, device="cuda"):
+    """Move to the GPU WITHOUT the default switch to the fused / native paths (AUDIOLLM_B200_NATIVE=0): these tests
+    turn each path on themselves and compare it with the reference-style hook path."""
+    import os
+    from unittest.mock import patch
+    with patch.dict(os.environ, {"AUDIOLLM_B200_NATIVE": "0"}):
+        return model.to(device)
+
 from audio_llama_b200 import llama_native as LN
 from oracle import encoder as O
 from oracle import llama as OL
@@ -139,7 +148,7 @@ def test_native_llama_in_audio_llm_matches_hf():
 
     def run(native):
         with patch.object(B, "load_base_models", fake):
-            m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+            m = _manual(AudioLLM("x", "y", lora_rank=8))
         g = torch.Generator().manual_seed(3)
         for l in m.lora_layers.values():
             with torch.no_grad():
@@ -198,7 +207,7 @@ def test_frozen_linear_and_inference_logits():
 
     def logits(native):
         with patch.object(B, "load_base_models", fake):
-            m = AudioLLM("x", "y", lora_rank=8).to("cuda").eval()
+            m = _manual(AudioLLM("x", "y", lora_rank=8)).eval()
         if native:
             m.enable_fused_lora()
             m.enable_native_llama_ops()
@@ -234,7 +243,7 @@ def test_generate_in_native_mode():
                 B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=1, out_dtype=torch.bfloat16)))
 
     with patch.object(B, "load_base_models", fake):
-        m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+        m = _manual(AudioLLM("x", "y", lora_rank=8))
     m.projector.to(torch.bfloat16)
     tok = Mock()
     tok.convert_tokens_to_ids = lambda t: {"<audio>": 320, "</audio>": 321}[t]

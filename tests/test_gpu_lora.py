@@ -8,6 +8,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+def _manual(model, device="cuda"):
+    """Move to the GPU WITHOUT the default switch to the fused / native paths (AUDIOLLM_B200_NATIVE=0): these tests
+    turn each path on themselves and compare it with the reference-style hook path."""
+    import os
+    from unittest.mock import patch
+    with patch.dict(os.environ, {"AUDIOLLM_B200_NATIVE": "0"}):
+        return model.to(device)
+
 from audio_llama_b200 import ops
 from oracle import encoder as O
 
@@ -61,7 +70,7 @@ def test_fused_lora_in_llama_matches_hooks():
 
     def run(fused):
         with patch.object(B, "load_base_models", fake):
-            m = AudioLLM("x", "y", lora_rank=8).to("cuda")
+            m = _manual(AudioLLM("x", "y", lora_rank=8))
         g = torch.Generator().manual_seed(3)
         for l in m.lora_layers.values():
             with torch.no_grad():
@@ -104,3 +113,48 @@ def test_lora_linear_backward(in_dim, out_dim, rank, rows):
     # dx skipped when the input needs no gradient
     dx2, dA2, _ = ops.lora_linear_backward(xc, dy.cuda(), None, a_pad, b_pad, t, rank, need_dx=False)
     assert dx2 is None and O.rel_l2(dA2.cpu(), dA.cpu()) <= 1e-5      # (split-K reduce-add: not bit-reproducible)
+
+
+def test_fused_and_native_paths_are_the_default_for_bf16_cuda():
+    """AudioLLM.to("cuda") with bf16 LLaMA weights switches to the fused frozen+LoRA GEMMs and the native row kernels
+    by itself; fp32 weights keep the reference-style hooks. Loss of the default path == loss of the hook path."""
+    from unittest.mock import patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as B
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200 import llama_native, synth
+
+    def fake(dtype):
+        def f(lp, wp):
+            torch.manual_seed(0)
+            lc = LlamaConfig(vocab_size=320, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                             num_attention_heads=4, num_key_value_heads=4)
+            ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+            return (B.FrozenModelWrapper(LlamaForCausalLM(lc).to(dtype)),
+                    B.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=2)))
+        return f
+
+    def loss_of(m):
+        g = torch.Generator().manual_seed(3)
+        for l in m.lora_layers.values():
+            with torch.no_grad():
+                l.lora_A.copy_(torch.randn(l.lora_A.shape, generator=g) * 0.05)
+                l.lora_B.copy_(torch.randn(l.lora_B.shape, generator=g) * 0.05)
+        ids, mask, labels = (t.cuda() for t in synth.synth_text(2, 16, 320))
+        return float(m(input_ids=ids, attention_mask=mask, labels=labels).loss)
+
+    try:
+        with patch.object(B, "load_base_models", fake(torch.bfloat16)):
+            m_default = AudioLLM("x", "y", lora_rank=8).to("cuda")
+            m_hooks = _manual(AudioLLM("x", "y", lora_rank=8))
+        assert getattr(m_default, "fused_lora", False) and getattr(m_default, "native_llama", False) and not m_default.hooks
+        assert not getattr(m_hooks, "fused_lora", False) and len(m_hooks.hooks) == len(m_hooks.lora_layers)
+        a, b = loss_of(m_default), loss_of(m_hooks)
+        assert abs(a - b) <= 2e-2 * abs(b)
+        with patch.object(B, "load_base_models", fake(torch.float32)):
+            m32 = AudioLLM("x", "y", lora_rank=8).to("cuda")
+        assert not getattr(m32, "fused_lora", False) and len(m32.hooks) == len(m32.lora_layers)
+    finally:
+        llama_native.disable_rope_patch()

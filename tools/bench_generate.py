@@ -33,7 +33,8 @@ def build(native):
         enc = WhisperEncoderModule(WHISPER_LARGE_V3_TURBO, synth.init_encoder_weights(WHISPER_LARGE_V3_TURBO, seed=0), max_batch=1,
                                    out_dtype=torch.bfloat16)
         return B.FrozenModelWrapper(llama), B.FrozenModelWrapper(enc)
-    with patch.object(B, "load_base_models", fake):
+    # native=False keeps the reference-style hooks (the default for bf16 CUDA weights is the fused / native path)
+    with patch.object(B, "load_base_models", fake), patch.dict(os.environ, {"AUDIOLLM_B200_NATIVE": "1" if native else "0"}):
         m = AudioLLM("x", "y", lora_rank=64).to(dev)
     m.projector.to(torch.bfloat16)
     v = LLAMAS[args.llama]["vocab_size"]

@@ -34,7 +34,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        from audio_llama_b200 import parallel
+        parallel.init_nccl(dev)
     ecfg = WHISPER_LARGE_V3_TURBO if args.encoder == "turbo" else WHISPER_TINY_128
     rec = train_step.run_config3(dev, rank, world, llama=args.llama, batch=args.batch, steps=args.steps,
                                  overlap=not args.no_overlap, ecfg=ecfg)
