@@ -41,8 +41,8 @@ constexpr int ATT_TAU_LOG2 = 40;          // the reference follows a tile whose 
 constexpr float ATT_RAW_LIMIT = 40.0f;    // QLOG2 fast form only while every first score of the warp's rows is within 2^+-40
 constexpr float ATT_RISK_SUM = 1.2676506e30f;   // 2^100: a tile sum this large sends the CTA's rows to the exact path
 #ifndef ATT_POLY_NUM
-#define ATT_POLY_NUM 1
-#define ATT_POLY_DEN 4
+#define ATT_POLY_NUM 3
+#define ATT_POLY_DEN 8
 #endif
 constexpr int POLY_NUM = ATT_POLY_NUM, POLY_DEN = ATT_POLY_DEN;   // of every DEN element pairs, NUM take exp2 on the FMA pipe
 // softmax warps -> MMA warp hand-offs are named barriers (256 arrive + 32 sync); id 0 is __syncthreads
