@@ -415,10 +415,22 @@ def run_product(args):
     gemm_launches = sum(prof[k][1] for k in gemm_kinds)
     gemm_flops = sum(fl[k] for k in gemm_kinds) * B * args.steps
     achieved_tf = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    traffic = None
+    # DRAM bytes per launch from the ncu --set full captures kept in profiles/traffic.json (a profiler run cannot be
+    # part of a timed bench): per GEMM shape, and their launch-weighted mean for the dominant-kernel roofline
+    traffic, ncu_bytes = None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("gemm_bf16_kernel_bytes_per_launch")
+        tj = json.load(open(tpath))
+        for name, v in tj.get("per_shape_bytes_per_launch", {}).items():
+            ncu_bytes[name.split(" ")[0]] = v
+        for name, v in tj.get("r02", {}).items():
+            if isinstance(v, dict) and "dram_read_bytes" in v:
+                key = "attention" if name.startswith("attention") else "layernorm" if name.startswith("layernorm") else \
+                    "splice" if name.startswith("splice") else None
+                if key:
+                    ncu_bytes[key] = v["dram_read_bytes"] + v["dram_write_bytes"]
+        per_layer = [ncu_bytes[k] for k in ("qkv", "out_proj", "fc1", "fc2") if k in ncu_bytes]
+        traffic = sum(per_layer) / len(per_layer) if per_layer else tj.get("gemm_bf16_kernel_bytes_per_launch")
     kernels = {}
     for k, (ms, n) in prof.items():
         if n == 0:
@@ -427,6 +439,8 @@ def run_product(args):
         if k in fl:
             ent["tflops"] = fl[k] * B * args.steps / (ms / 1e3) / 1e12
             ent["frac_of_bf16_sustained"] = ent["tflops"] / pk["tf_sustained"]
+        if k in ncu_bytes:
+            ent["dram_bytes_per_launch_ncu"] = ncu_bytes[k]
         kernels[k] = ent
     mel_bytes = B * (480000 * 4 + cfg.n_mels * 3000 * 4)          # algorithmic: read wave once + write fp32 mel once
     kernels["mel (1 launch; floor + affine fused into pack_mel)"] = {
@@ -435,6 +449,7 @@ def run_product(args):
     splice_bytes = B * (2 * (T_TXT + 2) * D_LLAMA * 2 + S * (4 + 8) + T_TXT * 24)   # rows read+written, mask+labels out, ids/mask/labels in
     kernels["splice (1 launch, cold)"] = {"ms": splice_ms, "gbs_algorithmic": splice_bytes / (splice_ms / 1e3) / 1e9,
                                           "frac_of_hbm": splice_bytes / (splice_ms / 1e3) / 1e9 / pk["hbm"],
+                                          "dram_bytes_per_launch_ncu": ncu_bytes.get("splice"),
                                           "note": "6 rotating (ids, output) sets: 810 MB footprint >> 126 MB L2"}
     kernels["projector+splice (4 launches)"] = {"ms_per_step": tail_ms,
                                                 "projector_tflops_lower_bound": fl["projector"] * B / (tail_ms / 1e3) / 1e12}
