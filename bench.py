@@ -390,13 +390,21 @@ def run_product(args):
 
     # --- secondary records (headline unchanged): the ragged extension (configs[4]) and the README training step with
     #     its gradient exchange (configs[2]); every rank takes part, rank 0 reports
-    config5 = None if args.no_config5 else run_config5(cond, dev, rank, world, timed)
-    config3 = None
+    # (a failure here must not cost the headline line: it is reported inside the record instead)
+    config5 = config3 = None
+    if not args.no_config5:
+        try:
+            config5 = run_config5(cond, dev, rank, world, timed)
+        except Exception as e:                                    # noqa: BLE001
+            config5 = {"error": f"{type(e).__name__}: {e}"[:300]}
     if not args.no_config3:
-        from audio_llama_b200 import train_step
-        del emb_d
-        torch.cuda.empty_cache()
-        config3 = train_step.run_config3(dev, rank, world, llama="3b", batch=8, steps=3, warmup=1, encoder_weights=ew)
+        try:
+            from audio_llama_b200 import train_step
+            del emb_d
+            torch.cuda.empty_cache()
+            config3 = train_step.run_config3(dev, rank, world, llama="3b", batch=8, steps=3, warmup=1, encoder_weights=ew)
+        except Exception as e:                                    # noqa: BLE001
+            config3 = {"error": f"{type(e).__name__}: {e}"[:300]}
     del ew
 
     if rank != 0:
