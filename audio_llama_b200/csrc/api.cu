@@ -576,6 +576,29 @@ int al_attention_ex(const void* qkv, void* out, int B, int T, int H, int flags, 
   return rc;
 }
 
+// [B][S][H][128] bf16 -> rank-4 map {128, H, S, B}, box {64, 1, 128, 1}: one (row tile, head) half-tile per copy
+static int tmap_bshd(CUtensorMap* m, const void* base, uint64_t B, uint64_t S, uint64_t H) {
+  const uint64_t dims[4] = {128, H, S, B};
+  const uint64_t str[4] = {2, 256, H * 256, S * H * 256};
+  const uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap(m, base, 2, 4, dims, str, box, true);
+}
+
+int al_gqa_attention_forward(const void* q, const void* k, const void* v, void* out, float* lse, const int* kv_len, int B,
+                             int S, int Hq, int Hkv, int head_dim, float scale, al_stream_t stream) {
+  AL_REQUIRE(q && k && v && out && lse, "al_gqa_attention_forward: NULL argument");
+  AL_REQUIRE(head_dim == 128, "al_gqa_attention_forward: head_dim must be 128, got %d", head_dim);
+  AL_REQUIRE(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "al_gqa_attention_forward: bad shape B=%d S=%d Hq=%d Hkv=%d", B, S, Hq, Hkv);
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = tmap_bshd(&tq, q, B, S, Hq))) return rc;
+  if ((rc = tmap_bshd(&tk, k, B, S, Hkv))) return rc;
+  if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
+  rc = launch_gqa_fwd(tq, tk, tv, out, lse, kv_len, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
 int al_pack_mel(const float* mel, void* out_bf16, int B, int n_mels, int T, int c_pad, al_stream_t stream) {
   return al_pack_mel_ex(mel, nullptr, out_bf16, B, n_mels, T, c_pad, stream);
 }

@@ -51,6 +51,11 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
 // q_log2 != 0: q carries log2(e) as well as head_dim^-1/2 (scores in log2 units; the encoder folds both into Wq).
 int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, int q_log2, cudaStream_t stream);
 
+// ------------------------------------------------------------------ causal GQA attention, head_dim 128 (gqa_attention_sm100.cu)
+// Tensor maps: rank 4 over [B][S][H][128] bf16, box {64, 1, 128, 1}, SW128 (see api.cu tmap_bshd).
+int launch_gqa_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
+                   const int* kv_len, int B, int S, int Hq, int Hkv, float scale, cudaStream_t stream);
+
 // ------------------------------------------------------------------ row kernels (rowwise.cu)
 // LayerNorm over the last dim of fp32 rows. out_dtype 0 = bf16, 1 = fp32. Output row of input row r is
 // (r / rows_per_group) * out_group_stride + out_row_offset + (r % rows_per_group)   (in rows of out_ld elements),

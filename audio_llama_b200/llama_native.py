@@ -246,6 +246,22 @@ def causal_only_mask(attention_mask, labels=None):
     return None if bool(ok) else attention_mask
 
 
+# ----------------------------------------------------------------------------- causal GQA attention (head_dim 128)
+def gqa_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_len, scale: float):
+    """q [B, S, Hq, 128], k / v [B, S, Hkv, 128] bf16 contiguous (q, k after RoPE); kv_len int32 [B] or None.
+    Returns (out [B, S, Hq, 128] bf16, lse [B, Hq, S] f32, base-2)."""
+    B, S, Hq, D = q.shape
+    Hkv = k.shape[2]
+    if D != 128 or q.dtype != torch.bfloat16 or not q.is_cuda:
+        raise ValueError("gqa_attention: bf16 CUDA tensors with head_dim 128 only")
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    out = torch.empty_like(q)
+    lse = torch.empty(B, Hq, S, dtype=torch.float32, device=q.device)
+    check(lib().al_gqa_attention_forward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(kv_len), B, S, Hq, Hkv, D,
+                                         float(scale), stream_ptr()), "al_gqa_attention_forward")
+    return out, lse
+
+
 # ----------------------------------------------------------------------------- wiring
 _ORIG = {}
 

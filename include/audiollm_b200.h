@@ -230,6 +230,17 @@ size_t al_linear_ce_workspace_bytes(int chunk_rows, int vocab);
 int al_linear_ce(const void* h, const void* W, const void* W_T, const long long* labels, int rows, int d, int vocab,
                  float grad_scale, int chunk_rows, void* workspace, float* loss_sum, void* dh, al_stream_t stream);
 
+/* ---- §8 f-1: causal grouped-query attention of the LLaMA layers (head_dim 128) ---------------------
+ * Replaces the attention_interface call of LlamaAttention.forward (transformers/models/llama/modeling_llama.py),
+ * which the reference reaches through self.llama.model(inputs_embeds=..., attention_mask=..., labels=...)
+ * (/root/reference/src/models/allm.py:99-104), together with what autograd derives from it.
+ *   q [B][S][Hq][128], k / v [B][S][Hkv][128] bf16 (q, k after the rotary embedding), out [B][S][Hq][128] bf16,
+ *   lse [B][Hq][S] f32 (base-2 log-sum-exp of the scaled scores; saved for the backward),
+ *   kv_len [B] int32 or NULL: keys at positions >= kv_len[b] are masked (a right-padded attention_mask).
+ * softmax(scale * q k^T + causal mask + key-padding mask) v, query head h reading kv head h / (Hq / Hkv). */
+int al_gqa_attention_forward(const void* q, const void* k, const void* v, void* out, float* lse, const int* kv_len,
+                             int B, int S, int Hq, int Hkv, int head_dim, float scale, al_stream_t stream);
+
 /* ---- S1 / S2: splice ------------------------------------------------------------------------------
  * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask
  * (allm.py:176-196) and the label extension (allm.py:81-89). Row map per sample (bit-exact contract):

@@ -43,3 +43,24 @@ def causal_lm_loss(logits: torch.Tensor, labels: torch.Tensor, ignore_index: int
     shifted = torch.nn.functional.pad(labels, (0, 1), value=ignore_index)[..., 1:].contiguous()
     return torch.nn.functional.cross_entropy(logits.view(-1, logits.shape[-1]), shifted.view(-1), ignore_index=ignore_index,
                                              reduction="mean")
+
+
+def gqa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: float, kv_len=None) -> torch.Tensor:
+    """What HF LlamaAttention computes between the rotary embedding and o_proj (modeling_llama.py eager_attention_forward
+    / the sdpa interface with a causal + key-padding mask), restated in float32: q [B, S, Hq, D], k / v [B, S, Hkv, D]
+    -> [B, S, Hq, D]. kv_len [B]: keys at positions >= kv_len[b] are masked (right padding)."""
+    B, S, Hq, D = q.shape
+    Hkv = k.shape[2]
+    g = Hq // Hkv
+    qf = q.float().permute(0, 2, 1, 3)                                    # [B, Hq, S, D]
+    kf = k.float().permute(0, 2, 1, 3).repeat_interleave(g, dim=1)        # repeat_kv
+    vf = v.float().permute(0, 2, 1, 3).repeat_interleave(g, dim=1)
+    s = qf @ kf.transpose(2, 3) * scale
+    mask = torch.ones(S, S, dtype=torch.bool, device=q.device).tril()
+    mask = mask[None, None].expand(B, 1, S, S)
+    if kv_len is not None:
+        key_ok = torch.arange(S, device=q.device)[None, :] < torch.as_tensor(kv_len, device=q.device)[:, None]
+        mask = mask & key_ok[:, None, None, :]
+    s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ vf).permute(0, 2, 1, 3).contiguous()
