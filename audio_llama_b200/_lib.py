@@ -40,6 +40,7 @@ SIGNATURES = {
     "al_attention": (i32, [vp, vp, i32, i32, i32, vp]),
     "al_attention_ex": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "al_gqa_attention_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
+    "al_gqa_attention_backward": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp]),
     "al_encoder_set_options": (i32, [vp, i32]),
     "al_pack_mel": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "al_f32_to_bf16": (i32, [vp, vp, i64, vp]),

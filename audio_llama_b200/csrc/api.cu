@@ -48,6 +48,13 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
               const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
   EncodeTiledFn enc = get_encode();
   AL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  // the driver call needs a current context on THIS thread: autograd runs backward functions on its own threads, where
+  // only the runtime has been used so far (CUDA_ERROR_INVALID_CONTEXT otherwise)
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   AL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p is not 16-byte aligned", base);
   cuuint64_t gdim[5];
   cuuint64_t gstr[5];
@@ -596,6 +603,23 @@ int al_gqa_attention_forward(const void* q, const void* k, const void* v, void* 
   if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
   rc = launch_gqa_fwd(tq, tk, tv, out, lse, kv_len, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
+  return rc;
+}
+
+int al_gqa_attention_backward(const void* q, const void* k, const void* v, const void* out, const float* lse,
+                              const void* d_out, const int* kv_len, void* dq, void* dk, void* dv, float* dsum_ws, int B, int S,
+                              int Hq, int Hkv, int head_dim, float scale, al_stream_t stream) {
+  AL_REQUIRE(q && k && v && out && lse && d_out && dq && dk && dv && dsum_ws, "al_gqa_attention_backward: NULL argument");
+  AL_REQUIRE(head_dim == 128, "al_gqa_attention_backward: head_dim must be 128, got %d", head_dim);
+  AL_REQUIRE(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "al_gqa_attention_backward: bad shape B=%d S=%d Hq=%d Hkv=%d", B, S, Hq, Hkv);
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = tmap_bshd(&tq, q, B, S, Hq))) return rc;
+  if ((rc = tmap_bshd(&tk, k, B, S, Hkv))) return rc;
+  if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
+  if ((rc = tmap_bshd(&tdo, d_out, B, S, Hq))) return rc;
+  rc = launch_gqa_bwd(tq, tk, tv, tdo, out, d_out, lse, dsum_ws, kv_len, dq, dk, dv, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
+  if (rc == 0) g_launches += 3;
   return rc;
 }
 

@@ -262,6 +262,38 @@ def gqa_attention_forward(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_
     return out, lse
 
 
+class _GqaAttentionFn(torch.autograd.Function):
+    """softmax(scale q k^T + causal + key-padding mask) v with grouped kv heads; backward on the native kernels too
+    (scores recomputed from q, k and the saved log-sum-exp)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, kv_len, scale):
+        out, lse = gqa_attention_forward(q, k, v, kv_len, scale)
+        ctx.save_for_backward(q.contiguous(), k.contiguous(), v.contiguous(), out, lse)
+        ctx.kv_len, ctx.scale = kv_len, float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, v, out, lse = ctx.saved_tensors
+        B, S, Hq, D = q.shape
+        Hkv = k.shape[2]
+        d_out = d_out.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        dsum = torch.empty(B, Hq, S, dtype=torch.float32, device=q.device)
+        check(lib().al_gqa_attention_backward(ptr(q), ptr(k), ptr(v), ptr(out), ptr(lse), ptr(d_out), ptr(ctx.kv_len), ptr(dq),
+                                              ptr(dk), ptr(dv), ptr(dsum), B, S, Hq, Hkv, D, ctx.scale, stream_ptr()),
+              "al_gqa_attention_backward")
+        return dq, dk, dv, None, None
+
+
+def gqa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_len=None, scale: float = None) -> torch.Tensor:
+    """q [B, S, Hq, 128], k / v [B, S, Hkv, 128] bf16 on the GPU -> [B, S, Hq, 128]; differentiable."""
+    if scale is None:
+        scale = q.shape[-1] ** -0.5
+    return _GqaAttentionFn.apply(q, k, v, kv_len, scale)
+
+
 # ----------------------------------------------------------------------------- wiring
 _ORIG = {}
 

@@ -240,6 +240,12 @@ int al_linear_ce(const void* h, const void* W, const void* W_T, const long long*
  * softmax(scale * q k^T + causal mask + key-padding mask) v, query head h reading kv head h / (Hq / Hkv). */
 int al_gqa_attention_forward(const void* q, const void* k, const void* v, void* out, float* lse, const int* kv_len,
                              int B, int S, int Hq, int Hkv, int head_dim, float scale, al_stream_t stream);
+/* Backward of the above (what autograd derives from scaled_dot_product_attention in the reference's stack): given the
+ * forward's operands, its out and lse, and d_out [B][S][Hq][128] bf16, writes dq / dk / dv (bf16, layouts of q / k / v;
+ * dk / dv summed over the query heads of each group). dsum_ws: [B][Hq][S] f32 scratch. Scores are recomputed. */
+int al_gqa_attention_backward(const void* q, const void* k, const void* v, const void* out, const float* lse,
+                              const void* d_out, const int* kv_len, void* dq, void* dk, void* dv, float* dsum_ws,
+                              int B, int S, int Hq, int Hkv, int head_dim, float scale, al_stream_t stream);
 
 /* ---- S1 / S2: splice ------------------------------------------------------------------------------
  * Replaces AudioLLM._combine_text_and_audio_embeddings (allm.py:143-170), _extend_attention_mask

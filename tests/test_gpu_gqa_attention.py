@@ -41,3 +41,27 @@ def test_gqa_forward(B, S, Hq, Hkv, kv_len):
         m = m & (torch.arange(S)[None, :] < torch.tensor(kv_len)[:, None])[:, None, None, :]
     ref_lse = torch.logsumexp(s.masked_fill(~m, float("-inf")), dim=-1) * 1.4426950408889634
     assert (lse.cpu() - ref_lse).abs().max() <= 2e-2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hkv,kv_len", [(1, 128, 1, 1, None), (2, 300, 4, 2, None), (1, 1000, 6, 2, [700]),
+                                               (2, 515, 3, 1, [515, 130]), (1, 2014, 6, 2, None)])
+def test_gqa_backward(B, S, Hq, Hkv, kv_len):
+    q, k, v = make(B, S, Hq, Hkv, seed=7 * S + Hq, spread=1.2)
+    scale = 128 ** -0.5
+    g = torch.Generator().manual_seed(1)
+    d_out = torch.randn(B, S, Hq, 128, generator=g).bfloat16()
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = OL.gqa_attention(qr, kr, vr, scale, kv_len)
+    ref.backward(d_out.float())
+    kl = torch.tensor(kv_len, dtype=torch.int32).cuda() if kv_len is not None else None
+    qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    out = LN.gqa_attention(qc, kc, vc, kl, scale)
+    out.backward(d_out.cuda())
+    assert rel(out.detach().cpu(), ref.detach()) <= 1e-2
+    for name, got, want in (("dq", qc.grad, qr.grad), ("dk", kc.grad, kr.grad), ("dv", vc.grad, vr.grad)):
+        assert torch.isfinite(got).all(), name
+        assert rel(got.cpu(), want) <= 3e-2, (name, rel(got.cpu(), want))
+    if kv_len is not None:                                  # padded keys receive exactly zero gradient
+        for b, n in enumerate(kv_len):
+            assert float(kc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
+            assert float(vc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
