@@ -294,11 +294,65 @@ def gqa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_len=None
     return _GqaAttentionFn.apply(q, k, v, kv_len, scale)
 
 
+# What AudioLLM.forward hands the patched LlamaAttention.forward for the duration of one model call: whether the native
+# attention may be used (the 2-D attention mask was None or purely right-padded) and the per-sample key count.
+_ATTN_STATE = {"active": False, "kv_len": None}
+
+
+def attention_plan(attention_mask):
+    """(usable, kv_len): the native attention covers causal + right-padding masks. `attention_mask` is the 2-D [B, S]
+    mask the reference passes (float after _extend_attention_mask). None -> no padding. A mask that is ones-then-zeros
+    in every row -> kv_len = number of ones (padded queries still see every real key before them, exactly as HF's
+    causal-and-key-padding bias lets them). Anything else (left padding, holes) -> not usable, stock path with the
+    mask. One tiny device->host read."""
+    if attention_mask is None:
+        return True, None
+    m = attention_mask
+    if m.dim() != 2:
+        return False, None
+    ok = (m[:, 1:] <= m[:, :-1]).all() if m.shape[1] > 1 else torch.ones((), dtype=torch.bool, device=m.device)
+    ok = ok & (m[:, 0] != 0).all()                      # every row has at least one real key (HF would hit an all-masked row otherwise)
+    if not bool(ok):
+        return False, None
+    return True, (m != 0).sum(dim=1).to(torch.int32).contiguous()
+
+
+def _attention_forward(m, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, _orig=None,
+                       **kwargs):
+    """LlamaAttention.forward with the rotary embedding and the attention product on the native kernels: q / k / v stay
+    in the [B, S, H, hd] layout the projections write (no transposes), al_rope rotates q and k, al_gqa_attention_* does
+    softmax(scale q k^T + causal + key padding) v and its backward. Falls back to HF's forward whenever the case is not
+    covered (KV cache in use, head_dim != 128, non-bf16, a mask that is not right padding)."""
+    st = _ATTN_STATE
+    hd = m.head_dim
+    usable = (past_key_values is None and hd == 128 and _ok(hidden_states)
+              and m.q_proj.weight.dtype == torch.bfloat16 and position_embeddings is not None)
+    if st["active"] and not usable:
+        # AudioLLM.forward has replaced the padding mask by kv_len for this call: silently running HF's path without it
+        # would attend to the padding
+        raise RuntimeError("native attention was planned for this forward but the layer cannot run it "
+                           "(KV cache in use, head_dim != 128 or non-bf16 tensors)")
+    if not st["active"]:
+        return _orig(m, hidden_states, position_embeddings=position_embeddings, attention_mask=attention_mask,
+                     past_key_values=past_key_values, **kwargs)
+    B, S, _ = hidden_states.shape
+    q = m.q_proj(hidden_states).view(B, S, -1, hd)
+    k = m.k_proj(hidden_states).view(B, S, -1, hd)
+    v = m.v_proj(hidden_states).view(B, S, -1, hd)
+    cos, sin = position_embeddings
+    cc, ss = cos.contiguous(), sin.contiguous()
+    q = _RoPEFn.apply(q.contiguous(), cc, ss)
+    k = _RoPEFn.apply(k.contiguous(), cc, ss)
+    out = gqa_attention(q, k, v.contiguous(), st["kv_len"], m.scaling)
+    return m.o_proj(out.reshape(B, S, -1)), None
+
+
 # ----------------------------------------------------------------------------- wiring
 _ORIG = {}
 
 
-def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True, frozen_linears=True):
+def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True, frozen_linears=True,
+           attention=True):
     """Patch the HF LLaMA inside `audio_llm` (an audio_llama_b200.models.allm.AudioLLM) to the native ops."""
     from transformers.models.llama import modeling_llama as ML
     llama = audio_llm.llama.model
@@ -321,6 +375,12 @@ def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_
                     return rmsnorm(hidden_states, m.weight, m.variance_epsilon)
                 return _orig(m, hidden_states)
             mod.forward = types.MethodType(norm_fwd, mod)
+        if attention and isinstance(mod, ML.LlamaAttention) and mod.head_dim == 128:
+            def attn_fwd(m, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None,
+                         _orig=type(mod).forward, **kw):
+                return _attention_forward(m, hidden_states, position_embeddings, attention_mask, past_key_values,
+                                          _orig=_orig, **kw)
+            mod.forward = types.MethodType(attn_fwd, mod)
         if mlp and isinstance(mod, ML.LlamaMLP):
             def mlp_fwd(m, x, _orig=type(mod).forward):
                 if _ok(x) and m.config.hidden_act == "silu":
@@ -330,6 +390,10 @@ def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_
     if rope and "rope" not in _ORIG:
         _ORIG["rope"] = ML.apply_rotary_pos_emb
         ML.apply_rotary_pos_emb = apply_rotary_pos_emb
+    # the plan (mask -> kv_len) is only taken when EVERY attention layer runs the native kernels
+    attn_mods = [mod for mod in llama.modules() if isinstance(mod, ML.LlamaAttention)]
+    audio_llm.native_attention = bool(attention) and bool(attn_mods) and all(
+        mod.head_dim == 128 and mod.q_proj.weight.dtype == torch.bfloat16 for mod in attn_mods)
     audio_llm.native_ce = bool(fused_ce)
     audio_llm.native_causal_only = bool(causal_only)
     audio_llm.native_llama = True

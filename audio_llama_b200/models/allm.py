@@ -104,9 +104,24 @@ class AudioLLM(nn.Module):
             combined_attention_mask = attention_mask
             adjusted_labels = labels
 
+        if getattr(self, "native_attention", False):
+            # causal + right-padding masks run on the native GQA attention (forward and backward): the key count per
+            # sample replaces the mask, HF builds no [B, 1, S, S] bias, padded positions keep HF's exact semantics
+            from .. import llama_native
+            usable, kv_len = llama_native.attention_plan(combined_attention_mask)
+            if usable and combined_embeddings.is_cuda and combined_embeddings.dtype == torch.bfloat16:
+                kwargs["use_cache"] = False        # (this forward returns a loss / logits, never a cache: generate() goes elsewhere)
+                llama_native._ATTN_STATE.update(active=True, kv_len=kv_len)
+                try:
+                    return self._llama_forward(combined_embeddings, None, adjusted_labels, kwargs)
+                finally:
+                    llama_native._ATTN_STATE.update(active=False, kv_len=None)
         if getattr(self, "native_causal_only", False):
             from .. import llama_native
             combined_attention_mask = llama_native.causal_only_mask(combined_attention_mask, adjusted_labels)
+        return self._llama_forward(combined_embeddings, combined_attention_mask, adjusted_labels, kwargs)
+
+    def _llama_forward(self, combined_embeddings, combined_attention_mask, adjusted_labels, kwargs):
         if getattr(self, "native_ce", False) and adjusted_labels is not None and combined_embeddings.dtype == torch.bfloat16:
             # lm_head + cross-entropy fused per chunk of rows (no [tokens, vocab] logits; `logits` is None in this mode)
             from transformers.modeling_outputs import CausalLMOutputWithPast

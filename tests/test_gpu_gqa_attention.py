@@ -65,3 +65,58 @@ def test_gqa_backward(B, S, Hq, Hkv, kv_len):
         for b, n in enumerate(kv_len):
             assert float(kc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
             assert float(vc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
+
+
+def test_native_attention_inside_audio_llm_matches_hf_with_padding():
+    """AudioLLM on a bf16 LLaMA with head_dim 128 and GQA: the native attention (causal + kv_len from a right-padded
+    mask, labels carrying pad ids at the padded positions as the reference's dataset produces them) gives HF's loss and
+    LoRA gradients; a left-padded mask keeps the stock path."""
+    import os
+    from unittest.mock import patch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from audio_llama_b200.models import base as Bm
+    from audio_llama_b200.models.allm import AudioLLM
+    from audio_llama_b200.config import EncoderConfig
+    from audio_llama_b200.encoder import WhisperEncoderModule
+    from audio_llama_b200 import synth
+
+    def fake(lp, wp):
+        torch.manual_seed(0)
+        lc = LlamaConfig(vocab_size=320, hidden_size=512, intermediate_size=512, num_hidden_layers=2,
+                         num_attention_heads=4, num_key_value_heads=2)          # head_dim 128, 2 query heads per kv head
+        ec = EncoderConfig(d_model=128, n_layers=1, n_heads=2, ffn_dim=256, n_mels=80)
+        return (Bm.FrozenModelWrapper(LlamaForCausalLM(lc).to(torch.bfloat16)),
+                Bm.FrozenModelWrapper(WhisperEncoderModule(ec, synth.init_encoder_weights(ec), max_batch=2)))
+
+    ids, mask, labels = (t.cuda() for t in synth.synth_text(2, 200, 320))
+    mask[0, 150:] = 0                                        # right padding; its labels stay token ids
+    mask[1, :] = 1
+
+    def run(attention, m=mask):
+        with patch.object(Bm, "load_base_models", fake), patch.dict(os.environ, {"AUDIOLLM_B200_NATIVE": "0"}):
+            mdl = AudioLLM("x", "y", lora_rank=8).to("cuda")
+        g = torch.Generator().manual_seed(3)
+        for l in mdl.lora_layers.values():
+            with torch.no_grad():
+                l.lora_A.copy_(torch.randn(l.lora_A.shape, generator=g) * 0.05)
+                l.lora_B.copy_(torch.randn(l.lora_B.shape, generator=g) * 0.05)
+        mdl.enable_fused_lora()
+        mdl.enable_native_llama_ops(attention=attention)
+        assert mdl.native_attention == attention
+        out = mdl(input_ids=ids, attention_mask=m, labels=labels)
+        out.loss.backward()
+        l0 = mdl.lora_layers["model.layers.0.self_attn.q_proj"]
+        l1 = mdl.lora_layers["model.layers.1.self_attn.v_proj"]
+        return float(out.loss), l0.lora_B.grad.float().cpu(), l1.lora_A.grad.float().cpu()
+
+    try:
+        a, b = run(False), run(True)
+        assert abs(a[0] - b[0]) <= 2e-2 * abs(a[0]), (a[0], b[0])
+        assert rel(b[1], a[1]) <= 8e-2 and rel(b[2], a[2]) <= 8e-2, (rel(b[1], a[1]), rel(b[2], a[2]))
+        left = mask.clone()
+        left[0] = 0
+        left[0, 50:] = 1                                     # left padding: not a kv_len mask -> stock path, still finite
+        c = run(True, left)
+        assert c[0] == c[0]
+    finally:
+        LN.disable_rope_patch()
