@@ -89,7 +89,8 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
+  // heavy tiles first: query tile qt visits qt + 1 kv tiles (causal), so the block order runs from the last tile down
+  const int qt = gridDim.x - 1 - blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (Hq / Hkv);
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
@@ -344,7 +345,8 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
+  // heavy tiles first: query tile qt visits qt + 1 kv tiles (causal), so the block order runs from the last tile down
+  const int qt = gridDim.x - 1 - blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
   const int hkv = hq / (Hq / Hkv);
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
