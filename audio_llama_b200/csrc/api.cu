@@ -618,7 +618,7 @@ int al_gqa_attention_backward(const void* q, const void* k, const void* v, const
   if ((rc = tmap_bshd(&tk, k, B, S, Hkv))) return rc;
   if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
   if ((rc = tmap_bshd(&tdo, d_out, B, S, Hq))) return rc;
-  rc = launch_gqa_bwd(tq, tk, tv, tdo, out, d_out, lse, dsum_ws, kv_len, dq, dk, dv, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
+  rc = launch_gqa_bwd(tq, tk, tv, tdo, q, out, d_out, lse, dsum_ws, kv_len, dq, dk, dv, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
   if (rc == 0) g_launches += 3;
   return rc;
 }

@@ -20,6 +20,8 @@
 //                       P^T / dS^T overwrite the first 64 columns of S^T / dP^T (the next tile's S^T is issued after the
 //                       products that read them: tensor-core operations of one thread execute in issue order).
 // D = rowsum(dO * O) comes from gqa_rowdot_kernel. Scores are recomputed in the backward (nothing but O and lse is saved).
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,10 +30,27 @@ namespace al {
 constexpr int GQ_T = 128;                      // tile rows (queries or keys) and head_dim
 constexpr int GQ_TILE_BYTES = GQ_T * GQ_T * 2; // 32 KB: one 128 x 128 bf16 tile = two [128][64] SW128 boxes
 constexpr int GQ_BOX_BYTES = GQ_T * 64 * 2;    // 16 KB
-constexpr int GQ_THREADS = 384;                // warps 0-3 control (TMA, MMA, TMEM allocator, idle), warps 4-11 compute
+#ifndef GQ_SPLIT
+#define GQ_SPLIT 4                             // compute threads per tile row (2 or 4)
+#endif
+constexpr int GQ_CW = GQ_T / GQ_SPLIT;         // columns of a 128-wide tile row that one compute thread owns
+constexpr int GQ_COMPUTE = GQ_T * GQ_SPLIT;    // compute threads
+constexpr int GQ_THREADS = 128 + GQ_COMPUTE;   // warps 0-3 control (TMA, MMA, TMEM allocator, idle), then the compute warps
 constexpr float GQ_TAU = 8.0f;                 // lazy-rescale threshold of the forward, log2 units
-constexpr int GQ_BAR_EXCH = 1;                 // named barrier of the 256 compute threads
+constexpr int GQ_BAR_EXCH = 1;                 // named barrier of the compute threads
 constexpr float LOG2E_GQ = 1.4426950408889634f;
+
+// -DGQ_CYCLES: per-role cycle accounting (development builds only; tools/bench_gqa_attention.py CYCLES=1 reads it back)
+#ifdef GQ_CYCLES
+__device__ unsigned long long gq_cyc[64];
+#define GQC_DECL(...) long long __VA_ARGS__
+#define GQC_NOW() clock64()
+#define GQC_ADD(slot, v) atomicAdd(&gq_cyc[slot], static_cast<unsigned long long>(v))
+#else
+#define GQC_DECL(...)
+#define GQC_NOW() 0
+#define GQC_ADD(slot, v)
+#endif
 
 __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -53,30 +72,61 @@ __device__ __forceinline__ void gq_load_tile(uint32_t dst, const CUtensorMap* m,
   tma_load_4d_a(dst, m, bar, 0, h, s0, b);
   tma_load_4d_a(dst + GQ_BOX_BYTES, m, bar, 64, h, s0, b);
 }
-// D[tmem 128 x 128] (+)= A[smem tile, K-major over d] * B[smem tile, K-major over d]^T   (contraction over head_dim)
-__device__ __forceinline__ void gq_mma_kk(uint32_t d_tmem, uint32_t a_tile, uint32_t b_tile, bool accumulate) {
-  constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T);
+// The MMA issuer is ONE thread, and every instruction it spends on building operand descriptors delays the next product
+// (measured: ~80 cycles per product with descriptors rebuilt from addresses, against 32 - 64 cycles of tensor time).
+// So descriptors are kept as a 32-bit low word (start address >> 4 | LBO >> 4 << 16) computed once per tile, the per
+// k-step advance is an add of a compile-time constant, and the high word (SBO 1024, version 1, SWIZZLE_128B) is constant.
+constexpr uint32_t GQ_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t gq_desc_kmajor(uint32_t tile) { return ((tile & 0x3FFFFu) >> 4) | ((16u >> 4) << 16); }
+__device__ __forceinline__ uint32_t gq_desc_mnmajor(uint32_t tile) {   // the two 64-column atoms are 16 KB apart (LBO)
+  return ((tile & 0x3FFFFu) >> 4) | ((static_cast<uint32_t>(GQ_BOX_BYTES) >> 4) << 16);
+}
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(GQ_DESC_HI)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(GQ_DESC_HI)
+      : "memory");
+}
+// D[tmem 128 x N] (+)= A[smem tile, 128 rows, K-major over d] * B[rows 64 H .. of a smem tile, K-major over d]^T, N = 128 or 64
+// (contraction over head_dim: 8 k-steps across the two 64-column SW128 boxes)
+template <int N, int H>
+__device__ __forceinline__ void gq_mma_kk(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, bool accumulate) {
+  constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, N);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const uint32_t off = (k >> 2) * GQ_BOX_BYTES + (k & 3) * 32;
-    umma_ss(d_tmem, umma_desc_sw128(a_tile + off, 16, 1024), umma_desc_sw128(b_tile + off, 16, 1024), IDESC,
-            (k != 0) || accumulate);
+    const uint32_t off = ((k >> 2) * GQ_BOX_BYTES + (k & 3) * 32) >> 4;
+    umma_ss_lo(d_tmem, a_lo + off, b_lo + off + ((H * 8192) >> 4), IDESC, (k != 0) || accumulate);
   }
 }
-// D[tmem 128 x 128] (+)= A[tmem: 128 lanes x 128 bf16 = 64 columns] * B[smem tile [rows = contraction][128 cols], MN-major]
-__device__ __forceinline__ void gq_mma_tm(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_tile, bool accumulate) {
+// D[tmem 128 x 128] (+)= A[tmem: 128 lanes x (16 STEPS) bf16] * B[contraction rows 64 H .. of a smem tile, 128 columns, MN-major]
+// (16 contraction rows = 2048 B per step)
+template <int STEPS, int H>
+__device__ __forceinline__ void gq_mma_tm(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, bool accumulate) {
   constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T, 0, 1);
 #pragma unroll
-  for (int k = 0; k < 8; ++k)   // 16 contraction rows = 2048 B per step; the two 64-column atoms are 16 KB apart (LBO)
-    umma_ts(d_tmem, a_tmem + k * 8, umma_desc_sw128(b_tile + 2048 * k, GQ_BOX_BYTES, 1024), IDESC, (k != 0) || accumulate);
+  for (int k = 0; k < STEPS; ++k)
+    umma_ts_lo(d_tmem, a_tmem + k * 8, b_lo + ((2048 * (4 * H + k)) >> 4), IDESC, (k != 0) || accumulate);
 }
 
 // ============================================================================ forward
 constexpr uint32_t GF_OFF_Q = 0;
 constexpr uint32_t GF_OFF_K = GQ_TILE_BYTES;
 constexpr uint32_t GF_OFF_V = GF_OFF_K + 2 * GQ_TILE_BYTES;
-constexpr uint32_t GF_OFF_EXCH = GF_OFF_V + 2 * GQ_TILE_BYTES;       // [2 parities][2 halves][128] f32 row maxima, then [2][128] sums
-constexpr uint32_t GF_OFF_BARS = GF_OFF_EXCH + 3 * 2 * GQ_T * 4;
+constexpr uint32_t GF_OFF_EXCH = GF_OFF_V + 2 * GQ_TILE_BYTES;       // [2 parities][GQ_SPLIT][128] f32 row maxima, then [GQ_SPLIT][128] sums
+constexpr uint32_t GF_OFF_BARS = GF_OFF_EXCH + 3 * GQ_SPLIT * GQ_T * 4;
 constexpr uint32_t GF_Q_FULL = GF_OFF_BARS, GF_K_FULL = GF_Q_FULL + 8, GF_K_EMPTY = GF_K_FULL + 16, GF_V_FULL = GF_K_EMPTY + 16,
                    GF_V_EMPTY = GF_V_FULL + 16, GF_S_FULL = GF_V_EMPTY + 16, GF_S_EMPTY = GF_S_FULL + 16, GF_P_FULL = GF_S_EMPTY + 16,
                    GF_O_FULL = GF_P_FULL + 8, GF_TMEM_PTR = GF_O_FULL + 8;
@@ -106,9 +156,9 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init_a(sb + GF_V_FULL + 8 * s, 1);
       mbar_init_a(sb + GF_V_EMPTY + 8 * s, 1);
       mbar_init_a(sb + GF_S_FULL + 8 * s, 1);
-      mbar_init_a(sb + GF_S_EMPTY + 8 * s, 256);
+      mbar_init_a(sb + GF_S_EMPTY + 8 * s, GQ_COMPUTE);
     }
-    mbar_init_a(sb + GF_P_FULL, 256);
+    mbar_init_a(sb + GF_P_FULL, GQ_COMPUTE);
     mbar_init_a(sb + GF_O_FULL, 1);
     fence_barrier_init();
   }
@@ -137,70 +187,107 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: S_j one tile ahead of P V_{j-1}
     mbar_wait_a(sb + GF_Q_FULL, 0);
+    const uint32_t q_lo = gq_desc_kmajor(sb + GF_OFF_Q), k_lo = gq_desc_kmajor(sb + GF_OFF_K), v_lo = gq_desc_mnmajor(sb + GF_OFF_V);
     auto issue_qk = [&](int j) {
       const int s = j & 1;
       mbar_wait_a(sb + GF_K_FULL + 8 * s, (j >> 1) & 1);
       if (j >= 2) mbar_wait_a(sb + GF_S_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        gq_mma_kk(tmem_base + s * 128, sb + GF_OFF_Q, sb + GF_OFF_K + s * GQ_TILE_BYTES, false);
+        gq_mma_kk<128, 0>(tmem_base + s * 128, q_lo, k_lo + s * (GQ_TILE_BYTES >> 4), false);
         umma_commit_a(sb + GF_K_EMPTY + 8 * s);
         umma_commit_a(sb + GF_S_FULL + 8 * s);
       }
       __syncwarp();
     };
     issue_qk(0);
+#ifdef GQ_CYCLES
+    long long w_p = 0, t_begin = GQC_NOW(), t0;
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       if (j + 1 < n_tiles) issue_qk(j + 1);
       const int s = j & 1;
       mbar_wait_a(sb + GF_V_FULL + 8 * s, (j >> 1) & 1);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
       mbar_wait_a(sb + GF_P_FULL, j & 1);
+#ifdef GQ_CYCLES
+      w_p += GQC_NOW() - t0;
+#endif
       tc_fence_after();
       if (elect_one()) {
-        gq_mma_tm(tmem_base + 256, tmem_base + 384, sb + GF_OFF_V + s * GQ_TILE_BYTES, j != 0);
+        gq_mma_tm<8, 0>(tmem_base + 256, tmem_base + 384, v_lo + s * (GQ_TILE_BYTES >> 4), j != 0);
         umma_commit_a(sb + GF_V_EMPTY + 8 * s);
         umma_commit_a(sb + GF_O_FULL);
       }
       __syncwarp();
     }
+#ifdef GQ_CYCLES
+    if (lane == 0) {
+      GQC_ADD(0, n_tiles);
+      GQC_ADD(1, GQC_NOW() - t_begin);
+      GQC_ADD(2, w_p);
+    }
+#endif
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax: two threads per query row
-    const int half = (warp - 4) >> 2;
+    // ------------------------------------------------------------------ softmax: GQ_SPLIT threads per query row
+    const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
     const int q_glob = qt * GQ_T + static_cast<int>(row);
-    const uint32_t ex_mine = sb + GF_OFF_EXCH + half * (GQ_T * 4) + row * 4;
-    const uint32_t ex_other = ex_mine ^ (GQ_T * 4);
+    constexpr uint32_t EX_STRIDE = GQ_T * 4, EX_SET = GQ_SPLIT * GQ_T * 4;   // one part's slots | one parity's set
+    const uint32_t ex_row = sb + GF_OFF_EXCH + row * 4;
     float m_ref = -INFINITY, l = 0.f;
+#ifdef GQ_CYCLES
+    long long w_s = 0, w_bar = 0, w_o = 0, c_a = 0, c_b = 0, c_c = 0, t_begin = GQC_NOW(), t0, t1;
+#endif
     for (int j = 0; j < n_tiles; ++j) {
       const int sbuf = j & 1;
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
       mbar_wait_a(sb + GF_S_FULL + 8 * sbuf, (j >> 1) & 1);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      w_s += t1 - t0;
+#endif
       tc_fence_after();
-      uint32_t s[64];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        tmem_ld_32x32(tlane + sbuf * 128 + half * 64, s0);
-        tmem_ld_32x32(tlane + sbuf * 128 + half * 64 + 32, s1);
-        tmem_ld_wait();
+      uint32_t s[GQ_CW];
+#pragma unroll
+      for (int c = 0; c < GQ_CW / 32; ++c) {
+        uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]);
+        tmem_ld_32x32(tlane + sbuf * 128 + part * GQ_CW + 32 * c, sc);
       }
+      tmem_ld_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GF_S_EMPTY + 8 * sbuf);
-      const int col0 = j * GQ_T + half * 64;
-      if (j == qt || col0 + 64 > kvl) {                    // diagonal tile or the tile holding the padding boundary
+      const int col0 = j * GQ_T + part * GQ_CW;
+      if (j == qt || col0 + GQ_CW > kvl) {                 // diagonal tile or the tile holding the padding boundary
 #pragma unroll
-        for (int k = 0; k < 64; ++k)
+        for (int k = 0; k < GQ_CW; ++k)
           if (col0 + k > q_glob || col0 + k >= kvl) s[k] = 0xff800000u;
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
 #pragma unroll
-      for (int k = 2; k < 64; k += 4) {
+      for (int k = 2; k < GQ_CW; k += 4) {
         mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-        if (k + 2 < 64) mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        if (k + 2 < GQ_CW) mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
       }
-      sts_f32(ex_mine + sbuf * (2 * GQ_T * 4), fmaxf(mx0, mx1));
-      named_bar_sync(GQ_BAR_EXCH, 256);
-      const float tile_max = fmaxf(fmaxf(mx0, mx1), lds_f32(ex_other + sbuf * (2 * GQ_T * 4))) * scale_log2;
+      sts_f32(ex_row + sbuf * EX_SET + part * EX_STRIDE, fmaxf(mx0, mx1));
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+      c_a += t0 - t1;
+#endif
+      named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      w_bar += t1 - t0;
+#endif
+      float tile_max = lds_f32(ex_row + sbuf * EX_SET);
+#pragma unroll
+      for (int q = 1; q < GQ_SPLIT; ++q) tile_max = fmaxf(tile_max, lds_f32(ex_row + sbuf * EX_SET + q * EX_STRIDE));
+      tile_max *= scale_log2;
       float alpha = 1.0f;
       const bool rescale = __any_sync(0xffffffffu, tile_max > m_ref + GQ_TAU);
       if (rescale && tile_max > m_ref + GQ_TAU) {          // (per row; the TMEM traffic below stays warp-uniform)
@@ -210,9 +297,9 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       const unsigned long long c2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_ref, -m_ref);
       unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);
-      uint32_t pk[32];
+      uint32_t pk[GQ_CW / 2];
 #pragma unroll
-      for (int k = 0; k < 64; k += 2) {
+      for (int k = 0; k < GQ_CW; k += 2) {
         const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), c2, nm2);
         float x0, x1;
         unpk2(x2, x0, x1);
@@ -227,46 +314,71 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         unpk2(l2b, e, f);
         l += (a + c) + (e + f);
       }
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+      c_b += t0 - t1;
+#endif
       if (j > 0) {                                         // the previous P V has read P and finished its part of O
         mbar_wait_a(sb + GF_O_FULL, (j - 1) & 1);
+#ifdef GQ_CYCLES
+        t1 = GQC_NOW();
+        w_o += t1 - t0;
+        t0 = t1;
+#endif
         tc_fence_after();
         if (rescale) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < GQ_CW / 32; ++c) {
             uint32_t r[32];
-            tmem_ld_32x32(tlane + 256 + half * 64 + c * 32, r);
+            tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
             tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-            tmem_st_32x32(tlane + 256 + half * 64 + c * 32, r);
+            tmem_st_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
           }
         }
       }
-      {
-        uint32_t(&p0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[0]);
-        uint32_t(&p1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16]);
-        tmem_st_32x16(tlane + 384 + half * 32, p0);
-        tmem_st_32x16(tlane + 384 + half * 32 + 16, p1);
+#pragma unroll
+      for (int c = 0; c < GQ_CW / 32; ++c) {
+        uint32_t(&pc)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16 * c]);
+        tmem_st_32x16(tlane + 384 + part * (GQ_CW / 2) + 16 * c, pc);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GF_P_FULL);
+#ifdef GQ_CYCLES
+      c_c += GQC_NOW() - t0;
+#endif
     }
-    // row sum of both halves, normalise, store O (this half's 64 columns) and the log-sum-exp
-    sts_f32(ex_mine + 2 * (2 * GQ_T * 4), l);
-    named_bar_sync(GQ_BAR_EXCH, 256);
-    const float l_tot = l + lds_f32(ex_other + 2 * (2 * GQ_T * 4));
+#ifdef GQ_CYCLES
+    if (lane == 0 && warp == 4) {
+      GQC_ADD(8, n_tiles);
+      GQC_ADD(9, GQC_NOW() - t_begin);
+      GQC_ADD(10, w_s);
+      GQC_ADD(11, c_a);
+      GQC_ADD(12, w_bar);
+      GQC_ADD(13, c_b);
+      GQC_ADD(14, w_o);
+      GQC_ADD(15, c_c);
+    }
+#endif
+    // row sum of all parts, normalise, store O (this part's columns) and the log-sum-exp
+    sts_f32(ex_row + 2 * EX_SET + part * EX_STRIDE, l);
+    named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
+    float l_tot = lds_f32(ex_row + 2 * EX_SET);
+#pragma unroll
+    for (int q = 1; q < GQ_SPLIT; ++q) l_tot += lds_f32(ex_row + 2 * EX_SET + q * EX_STRIDE);
     const float inv_l = 1.0f / l_tot;
     mbar_wait_a(sb + GF_O_FULL, (n_tiles - 1) & 1);
     tc_fence_after();
     if (q_glob < S) {
-      if (half == 0) lse[(static_cast<size_t>(b) * Hq + hq) * S + q_glob] = m_ref + log2f(l_tot);
+      if (part == 0) lse[(static_cast<size_t>(b) * Hq + hq) * S + q_glob] = m_ref + log2f(l_tot);
     }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + half * 64);
+    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GQ_CW);
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < GQ_CW / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_32x32(tlane + 256 + half * 64 + c * 32, r);
+      tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
       tmem_ld_wait();
       if (q_glob < S) {
 #pragma unroll
@@ -331,15 +443,36 @@ gqa_rowdot_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 }
 
 // ---------------------------------------------------------------------------- dQ
-constexpr uint32_t GD_OFF_Q = 0, GD_OFF_DO = GQ_TILE_BYTES, GD_OFF_K = 2 * GQ_TILE_BYTES, GD_OFF_V = 4 * GQ_TILE_BYTES;
-constexpr uint32_t GD_OFF_BARS = 6 * GQ_TILE_BYTES;
-constexpr uint32_t GD_QDO_FULL = GD_OFF_BARS, GD_KV_FULL = GD_QDO_FULL + 8, GD_KV_EMPTY = GD_KV_FULL + 16, GD_SDP_FULL = GD_KV_EMPTY + 16,
-                   GD_SDP_EMPTY = GD_SDP_FULL + 8, GD_DS_FULL = GD_SDP_EMPTY + 8, GD_DQ_DONE = GD_DS_FULL + 8, GD_TMEM_PTR = GD_DQ_DONE + 8;
+// Q_i and dO_i are the A operands of every product of this kernel's loop (S = Q K_j^T, dP = dO V_j^T), so they live
+// in TMEM for the whole CTA (written once from global memory by the compute threads) and the products read only their
+// B operand from shared memory: shared-memory bandwidth, not the tensor pipe, is what bounds the SS form here
+// (tools/att_lab/mma_rate.cu: 8 KB of operands per 64-cycle product = the full 128 B / cycle of the SM).
+constexpr int GD_SPLIT = 4;                    // compute threads per query row (16 warps: the exponent phase is latency-bound
+                                               // with fewer - tools/ncu_hot.py on the 8-warp form: 'wait' + 'branch' stalls)
+constexpr int GD_CW = GQ_T / GD_SPLIT;         // 32 columns per thread
+constexpr int GD_COMPUTE = GQ_T * GD_SPLIT;
+constexpr int GD_THREADS = 128 + GD_COMPUTE;   // warps 0-3 control, then the compute warps
+constexpr uint32_t GD_OFF_K = 0, GD_OFF_V = 2 * GQ_TILE_BYTES;
+constexpr uint32_t GD_OFF_BARS = 4 * GQ_TILE_BYTES;
+constexpr uint32_t GD_QDO_FULL = GD_OFF_BARS, GD_KV_FULL = GD_QDO_FULL + 8, GD_KV_EMPTY = GD_KV_FULL + 16, GD_S_FULL = GD_KV_EMPTY + 16,
+                   GD_S_EMPTY = GD_S_FULL + 8, GD_DP_FULL = GD_S_EMPTY + 8, GD_DS_FULL = GD_DP_FULL + 8, GD_DQ_DONE = GD_DS_FULL + 8,
+                   GD_TMEM_PTR = GD_DQ_DONE + 8;
 constexpr int GD_SMEM = GD_TMEM_PTR + 16 + 1024;
+// TMEM columns
+static_assert(GD_CW == 32, "the dQ kernel's compute loop handles one 32-column chunk per thread");
+constexpr uint32_t GD_TM_S = 0, GD_TM_DP = 128, GD_TM_DQ = 256, GD_TM_Q = 384, GD_TM_DO = 448;
 
-__global__ void __launch_bounds__(GQ_THREADS, 1)
-gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+// D[tmem 128 x 128] = A[tmem: 128 lanes x 128 bf16 = 64 columns] * B[smem tile, K-major over d]^T
+__device__ __forceinline__ void gq_mma_tk(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo) {
+  constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_ts_lo(d_tmem, a_tmem + k * 8, b_lo + (((k >> 2) * GQ_BOX_BYTES + (k & 3) * 32) >> 4), IDESC, k != 0);
+}
+
+__global__ void __launch_bounds__(GD_THREADS, 1)
+gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __nv_bfloat16* __restrict__ d_out,
                   const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_len,
                   __nv_bfloat16* __restrict__ dq, int S, int Hq, int Hkv, float scale) {
   extern __shared__ uint8_t smem_raw[];
@@ -353,18 +486,17 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   const float scale_log2 = scale * LOG2E_GQ;
 
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    tma_prefetch_desc(&tmDO);
-    mbar_init_a(sb + GD_QDO_FULL, 1);
+    mbar_init_a(sb + GD_QDO_FULL, GD_COMPUTE);
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GD_KV_FULL + 8 * s, 1);
       mbar_init_a(sb + GD_KV_EMPTY + 8 * s, 1);
     }
-    mbar_init_a(sb + GD_SDP_FULL, 1);
-    mbar_init_a(sb + GD_SDP_EMPTY, 256);
-    mbar_init_a(sb + GD_DS_FULL, 256);
+    mbar_init_a(sb + GD_S_FULL, 1);
+    mbar_init_a(sb + GD_S_EMPTY, GD_COMPUTE);
+    mbar_init_a(sb + GD_DP_FULL, 1);
+    mbar_init_a(sb + GD_DS_FULL, GD_COMPUTE);
     mbar_init_a(sb + GD_DQ_DONE, 1);
     fence_barrier_init();
   }
@@ -377,16 +509,20 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GD_TMEM_PTR) : "memory");
-  // TMEM columns: S 0..127 | dP 128..255 | dQ 256..383 | dS 384..447 (bf16 pairs)
+  // TMEM columns: S 0..127 | dP 128..255 (each thread's dS, bf16 pairs, over the first half of its own dP columns)
+  //               | dQ 256..383 | Q 384..447 | dO 448..511 (bf16 pairs, A operands)
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
-      mbar_arrive_expect_tx_a(sb + GD_QDO_FULL, 2 * GQ_TILE_BYTES);
-      gq_issue_tile(sb + GD_OFF_Q, &tmQ, sb + GD_QDO_FULL, hq, qt * GQ_T, b);
-      gq_issue_tile(sb + GD_OFF_DO, &tmDO, sb + GD_QDO_FULL, hq, qt * GQ_T, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         if (j >= 2) mbar_wait_a(sb + GD_KV_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
+#ifdef GQ_HACK_NOTMA   // timing experiment only (wrong results): tiles after the first two are not loaded
+        if (j >= 2) {
+          mbar_arrive_a(sb + GD_KV_FULL + 8 * s);
+          continue;
+        }
+#endif
         mbar_arrive_expect_tx_a(sb + GD_KV_FULL + 8 * s, 2 * GQ_TILE_BYTES);
         gq_issue_tile(sb + GD_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, b);
         gq_issue_tile(sb + GD_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, b);
@@ -394,105 +530,198 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // Order: S_{j+1} as soon as S_j is in registers; dQ_j when dS_j is written; dP_{j+1} behind dQ_j (dS_j lives in
+    // the dP columns; tensor-core operations of one thread execute in issue order).
+    const uint32_t k_lo = gq_desc_kmajor(sb + GD_OFF_K), v_lo = gq_desc_kmajor(sb + GD_OFF_V), kmn_lo = gq_desc_mnmajor(sb + GD_OFF_K);
+    constexpr uint32_t STAGE = GQ_TILE_BYTES >> 4;
     mbar_wait_a(sb + GD_QDO_FULL, 0);
-    auto issue_sdp = [&](int j) {                          // S = Q K_j^T and dP = dO V_j^T
-      const int s = j & 1;
-      mbar_wait_a(sb + GD_KV_FULL + 8 * s, (j >> 1) & 1);
-      if (j >= 1) mbar_wait_a(sb + GD_SDP_EMPTY, (j - 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        gq_mma_kk(tmem_base, sb + GD_OFF_Q, sb + GD_OFF_K + s * GQ_TILE_BYTES, false);
-        gq_mma_kk(tmem_base + 128, sb + GD_OFF_DO, sb + GD_OFF_V + s * GQ_TILE_BYTES, false);
-        umma_commit_a(sb + GD_SDP_FULL);
-      }
-      __syncwarp();
-    };
-    issue_sdp(0);
+    mbar_wait_a(sb + GD_KV_FULL, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      gq_mma_tk(tmem_base + GD_TM_S, tmem_base + GD_TM_Q, k_lo);
+      umma_commit_a(sb + GD_S_FULL);
+      gq_mma_tk(tmem_base + GD_TM_DP, tmem_base + GD_TM_DO, v_lo);
+      umma_commit_a(sb + GD_DP_FULL);
+    }
+    __syncwarp();
+#ifdef GQ_CYCLES
+    long long w_ds = 0, w_se = 0, t_begin = GQC_NOW(), t0;
+#endif
     for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_sdp(j + 1);
+      const int s1 = (j + 1) & 1;
+      if (j + 1 < n_tiles) {
+        mbar_wait_a(sb + GD_KV_FULL + 8 * s1, ((j + 1) >> 1) & 1);
+#ifdef GQ_CYCLES
+        t0 = GQC_NOW();
+#endif
+        mbar_wait_a(sb + GD_S_EMPTY, j & 1);
+#ifdef GQ_CYCLES
+        w_se += GQC_NOW() - t0;
+#endif
+        tc_fence_after();
+        if (elect_one()) {
+          gq_mma_tk(tmem_base + GD_TM_S, tmem_base + GD_TM_Q, k_lo + s1 * STAGE);
+          umma_commit_a(sb + GD_S_FULL);
+        }
+        __syncwarp();
+      }
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
       mbar_wait_a(sb + GD_DS_FULL, j & 1);
+#ifdef GQ_CYCLES
+      w_ds += GQC_NOW() - t0;
+#endif
       tc_fence_after();
-      if (elect_one()) {                                   // dQ += dS K_j
-        gq_mma_tm(tmem_base + 256, tmem_base + 384, sb + GD_OFF_K + (j & 1) * GQ_TILE_BYTES, j != 0);
+      if (elect_one()) {                                   // dQ += dS K_j: k-step k = keys 16 k .., from the part that owns them
+        constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T, 0, 1);
+        const uint32_t b_lo = kmn_lo + (j & 1) * STAGE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts_lo(tmem_base + GD_TM_DQ, tmem_base + GD_TM_DP + (16 * k / GD_CW) * GD_CW + ((16 * k % GD_CW) >> 1),
+                     b_lo + ((2048 * k) >> 4), IDESC, (k != 0) || (j != 0));
         umma_commit_a(sb + GD_KV_EMPTY + 8 * (j & 1));
-        umma_commit_a(sb + GD_DQ_DONE);
+        if (j + 1 < n_tiles) {
+          gq_mma_tk(tmem_base + GD_TM_DP, tmem_base + GD_TM_DO, v_lo + s1 * STAGE);
+          umma_commit_a(sb + GD_DP_FULL);
+        } else {
+          umma_commit_a(sb + GD_DQ_DONE);
+        }
       }
       __syncwarp();
     }
+#ifdef GQ_CYCLES
+    if (lane == 0) {
+      GQC_ADD(16, n_tiles);
+      GQC_ADD(17, GQC_NOW() - t_begin);
+      GQC_ADD(18, w_se);
+      GQC_ADD(19, w_ds);
+    }
+#endif
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ dS: two threads per query row
-    const int half = (warp - 4) >> 2;
+    // ------------------------------------------------------------------ dS: GD_SPLIT threads per query row
+    const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
     const int q_glob = qt * GQ_T + static_cast<int>(row);
     const bool live = q_glob < S;
+    {   // this thread's GD_CW columns of the Q and dO rows -> TMEM (bf16 pairs are already the A-operand layout)
+      const size_t g = ((static_cast<size_t>(b) * S + (live ? q_glob : 0)) * Hq + hq) * GQ_T + part * GD_CW;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint4* src = reinterpret_cast<const uint4*>((which == 0 ? q : d_out) + g);
+        uint32_t r[GD_CW / 2];
+#pragma unroll
+        for (int u = 0; u < GD_CW / 8; ++u) {
+          const uint4 v = live ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+          r[4 * u] = v.x;
+          r[4 * u + 1] = v.y;
+          r[4 * u + 2] = v.z;
+          r[4 * u + 3] = v.w;
+        }
+        tmem_st_32x16(tlane + (which == 0 ? GD_TM_Q : GD_TM_DO) + part * (GD_CW / 2), r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_a(sb + GD_QDO_FULL);
+    }
     const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + (live ? q_glob : 0);
     const float neg_lse = live ? -lse[stat] : -INFINITY;   // rows past S: p = 0
-    const float dsum_row = live ? dsum[stat] : 0.f;
-    const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse);
+    const float neg_d = live ? -dsum[stat] : 0.f;
+    const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse), nd2 = pk2(neg_d, neg_d);
+#ifdef GQ_CYCLES
+    long long w_s = 0, w_dp = 0, c_a = 0, c_b = 0, t_begin = GQC_NOW(), t0, t1;
+#endif
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait_a(sb + GD_SDP_FULL, j & 1);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
+      mbar_wait_a(sb + GD_S_FULL, j & 1);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      w_s += t1 - t0;
+#endif
       tc_fence_after();
-      uint32_t pk[32];
-      const int col0 = j * GQ_T + half * 64;
-      const bool edge = (j == qt) || (col0 + 64 > kvl);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dp[32];
-        tmem_ld_32x32(tlane + half * 64 + c * 32, sv);
-        tmem_ld_32x32(tlane + 128 + half * 64 + c * 32, dp);
+      const int col0 = j * GQ_T + part * GD_CW;
+      float pf[GD_CW];                                     // this thread's probabilities
+      {
+        uint32_t sv[32];
+        tmem_ld_32x32(tlane + GD_TM_S + part * GD_CW, sv);
         tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before();
-          mbar_arrive_a(sb + GD_SDP_EMPTY);                // S and dP of this tile are in registers
-        }
+        tc_fence_before();
+        mbar_arrive_a(sb + GD_S_EMPTY);                    // S of this tile is in registers
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
           const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2, nl2);
           float x0, x1;
           unpk2(x2, x0, x1);
-          float p0 = ex2f(x0), p1 = ex2f(x1);
-          if (edge) {
-            const int cg = col0 + c * 32 + k;
-            if (cg > q_glob || cg >= kvl) p0 = 0.f;
-            if (cg + 1 > q_glob || cg + 1 >= kvl) p1 = 0.f;
-          }
-          const float d0 = p0 * (__uint_as_float(dp[k]) - dsum_row) * scale;
-          const float d1 = p1 * (__uint_as_float(dp[k + 1]) - dsum_row) * scale;
-          pk[c * 16 + (k >> 1)] = pack_bf16(d0, d1);
+          pf[k] = ex2f(x0);
+          pf[k + 1] = ex2f(x1);
+        }
+        if ((j == qt) || (col0 + GD_CW > kvl)) {           // diagonal tile or the tile holding the padding boundary
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (col0 + k > q_glob || col0 + k >= kvl) pf[k] = 0.f;
         }
       }
-      if (j > 0) {                                         // the previous dQ product has read dS
-        mbar_wait_a(sb + GD_DQ_DONE, (j - 1) & 1);
-        tc_fence_after();
-      }
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+      c_a += t0 - t1;
+#endif
+      mbar_wait_a(sb + GD_DP_FULL, j & 1);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      w_dp += t1 - t0;
+#endif
+      tc_fence_after();
       {
-        uint32_t(&p0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[0]);
-        uint32_t(&p1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16]);
-        tmem_st_32x16(tlane + 384 + half * 32, p0);
-        tmem_st_32x16(tlane + 384 + half * 32 + 16, p1);
+        uint32_t dp[32], ds[16];
+        tmem_ld_32x32(tlane + GD_TM_DP + part * GD_CW, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[k]), __uint_as_float(dp[k + 1])), nd2);
+          const unsigned long long d2 = fmul2(pk2(pf[k], pf[k + 1]), t2);
+          float d0, d1;
+          unpk2(d2, d0, d1);
+          ds[k >> 1] = pack_bf16(d0, d1);                  // (the 1/sqrt(d) factor is applied to dQ at the end)
+        }
+        // dS over the first half of this thread's own dP columns (columns it has read; nobody else touches them)
+        tmem_st_32x16(tlane + GD_TM_DP + part * GD_CW, ds);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GD_DS_FULL);
+#ifdef GQ_CYCLES
+      c_b += GQC_NOW() - t1;
+#endif
     }
-    mbar_wait_a(sb + GD_DQ_DONE, (n_tiles - 1) & 1);
+#ifdef GQ_CYCLES
+    if (lane == 0 && warp == 4) {
+      GQC_ADD(24, n_tiles);
+      GQC_ADD(25, GQC_NOW() - t_begin);
+      GQC_ADD(26, w_s);
+      GQC_ADD(27, c_a);
+      GQC_ADD(28, w_dp);
+      GQC_ADD(29, c_b);
+    }
+#endif
+    mbar_wait_a(sb + GD_DQ_DONE, 0);
     tc_fence_after();
-    uint4* dst = reinterpret_cast<uint4*>(dq + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + half * 64);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    uint4* dst = reinterpret_cast<uint4*>(dq + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GD_CW);
+    {
       uint32_t r[32];
-      tmem_ld_32x32(tlane + 256 + half * 64 + c * 32, r);
+      tmem_ld_32x32(tlane + GD_TM_DQ + part * GD_CW, r);
       tmem_ld_wait();
       if (live) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[8 * u]), __uint_as_float(r[8 * u + 1]));
-          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3]));
-          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]), __uint_as_float(r[8 * u + 5]));
-          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]), __uint_as_float(r[8 * u + 7]));
-          dst[c * 4 + u] = v;
+          v.x = pack_bf16(__uint_as_float(r[8 * u]) * scale, __uint_as_float(r[8 * u + 1]) * scale);
+          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * scale, __uint_as_float(r[8 * u + 3]) * scale);
+          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * scale, __uint_as_float(r[8 * u + 5]) * scale);
+          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * scale, __uint_as_float(r[8 * u + 7]) * scale);
+          dst[u] = v;
         }
       }
     }
@@ -503,14 +732,19 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------- dK, dV
+// Each 128-query tile is processed as two 64-query halves with their own TMEM regions, barriers and compute group
+// (warps 4-7: half 0, warps 8-11: half 1), so that one half's exponentials run under the other half's products and
+// the tensor pipe always has the next S^T / dP^T half queued behind the dV / dK update of the previous one.
+constexpr int GK_THREADS = 384;
 constexpr uint32_t GK_OFF_K = 0, GK_OFF_V = GQ_TILE_BYTES, GK_OFF_Q = 2 * GQ_TILE_BYTES, GK_OFF_DO = 4 * GQ_TILE_BYTES;
-constexpr uint32_t GK_OFF_STAT = 6 * GQ_TILE_BYTES;                 // [2 stages][lse | D][128] f32
+constexpr uint32_t GK_OFF_STAT = 6 * GQ_TILE_BYTES;                 // [2 halves][2 stages][-lse 64 | -D 64] f32
 constexpr uint32_t GK_OFF_BARS = GK_OFF_STAT + 2 * 2 * GQ_T * 4;
 constexpr uint32_t GK_KV_FULL = GK_OFF_BARS, GK_QDO_FULL = GK_KV_FULL + 8, GK_QDO_EMPTY = GK_QDO_FULL + 16, GK_ST_FULL = GK_QDO_EMPTY + 16,
-                   GK_PT_FULL = GK_ST_FULL + 8, GK_ACC_DONE = GK_PT_FULL + 8, GK_TMEM_PTR = GK_ACC_DONE + 8;
+                   GK_DPT_FULL = GK_ST_FULL + 16, GK_PT_FULL = GK_DPT_FULL + 16, GK_DST_FULL = GK_PT_FULL + 16,
+                   GK_ACC_DONE = GK_DST_FULL + 16, GK_TMEM_PTR = GK_ACC_DONE + 8;
 constexpr int GK_SMEM = GK_TMEM_PTR + 16 + 1024;
 
-__global__ void __launch_bounds__(GQ_THREADS, 1)
+__global__ void __launch_bounds__(GK_THREADS, 1)
 gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_len,
@@ -552,9 +786,11 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GK_QDO_FULL + 8 * s, 1);
       mbar_init_a(sb + GK_QDO_EMPTY + 8 * s, 1);
+      mbar_init_a(sb + GK_ST_FULL + 8 * s, 1);
+      mbar_init_a(sb + GK_DPT_FULL + 8 * s, 1);
+      mbar_init_a(sb + GK_PT_FULL + 8 * s, 128);
+      mbar_init_a(sb + GK_DST_FULL + 8 * s, 128);
     }
-    mbar_init_a(sb + GK_ST_FULL, 1);
-    mbar_init_a(sb + GK_PT_FULL, 256);
     mbar_init_a(sb + GK_ACC_DONE, 1);
     fence_barrier_init();
   }
@@ -567,7 +803,8 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GK_TMEM_PTR) : "memory");
-  // TMEM columns: S^T 0..127 (P^T bf16 over 0..63) | dP^T 128..255 (dS^T bf16 over 128..191) | dV 256..383 | dK 384..511
+  // TMEM columns: S^T 0..127 (query half h at 64 h; its P^T bf16 over the first 32 of them) | dP^T 128..255 (dS^T alike)
+  //               | dV 256..383 | dK 384..511
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
@@ -586,113 +823,233 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     mbar_wait_a(sb + GK_KV_FULL, 0);
-    for (int it = 0; it < n_it; ++it) {
+    // Per query half h the chain is  S^T -> (P^T) -> dV -> next S^T   and   dP^T -> (dS^T) -> dK -> next dP^T : the
+    // products that overwrite a region are issued behind the ones that read it (tensor-core operations of one thread
+    // execute in issue order), and the two halves' chains interleave on the tensor pipe.
+    const uint32_t k_lo = gq_desc_kmajor(sb + GK_OFF_K), v_lo = gq_desc_kmajor(sb + GK_OFF_V), q_lo = gq_desc_kmajor(sb + GK_OFF_Q),
+                   do_lo = gq_desc_kmajor(sb + GK_OFF_DO), qmn_lo = gq_desc_mnmajor(sb + GK_OFF_Q),
+                   domn_lo = gq_desc_mnmajor(sb + GK_OFF_DO);
+    constexpr uint32_t STAGE = GQ_TILE_BYTES >> 4;
+    auto issue_s = [&](int it, auto hc) {                  // S^T = K Q^T for query half h of tile it
+      constexpr int h = decltype(hc)::value;
       const int s = it & 1;
-      mbar_wait_a(sb + GK_QDO_FULL + 8 * s, (it >> 1) & 1);
+      if (h == 0) mbar_wait_a(sb + GK_QDO_FULL + 8 * s, (it >> 1) & 1);
       tc_fence_after();
-      if (elect_one()) {                                   // S^T = K Q_i^T, dP^T = V dO_i^T (after the previous dV / dK: in order)
-        gq_mma_kk(tmem_base, sb + GK_OFF_K, sb + GK_OFF_Q + s * GQ_TILE_BYTES, false);
-        gq_mma_kk(tmem_base + 128, sb + GK_OFF_V, sb + GK_OFF_DO + s * GQ_TILE_BYTES, false);
-        umma_commit_a(sb + GK_ST_FULL);
+      if (elect_one()) {
+        gq_mma_kk<64, h>(tmem_base + h * 64, k_lo, q_lo + s * STAGE, false);
+        umma_commit_a(sb + GK_ST_FULL + 8 * h);
       }
       __syncwarp();
-      mbar_wait_a(sb + GK_PT_FULL, it & 1);
-      tc_fence_after();
-      if (elect_one()) {                                   // dV += P^T dO_i, dK += dS^T Q_i
-        gq_mma_tm(tmem_base + 256, tmem_base, sb + GK_OFF_DO + s * GQ_TILE_BYTES, it != 0);
-        gq_mma_tm(tmem_base + 384, tmem_base + 128, sb + GK_OFF_Q + s * GQ_TILE_BYTES, it != 0);
-        umma_commit_a(sb + GK_QDO_EMPTY + 8 * s);
-        if (it == n_it - 1) umma_commit_a(sb + GK_ACC_DONE);
+    };
+    auto issue_dp = [&](int it, auto hc) {                 // dP^T = V dO^T
+      constexpr int h = decltype(hc)::value;
+      const int s = it & 1;
+      if (elect_one()) {
+        gq_mma_kk<64, h>(tmem_base + 128 + h * 64, v_lo, do_lo + s * STAGE, false);
+        umma_commit_a(sb + GK_DPT_FULL + 8 * h);
       }
       __syncwarp();
+    };
+    using H0 = std::integral_constant<int, 0>;
+    using H1 = std::integral_constant<int, 1>;
+    issue_s(0, H0{});
+    issue_dp(0, H0{});
+    issue_s(0, H1{});
+    issue_dp(0, H1{});
+#ifdef GQ_CYCLES
+    long long w_pt = 0, w_dst = 0, t_begin = GQC_NOW(), t0;
+#endif
+    auto half_step = [&](int it, auto hc) {
+      constexpr int h = decltype(hc)::value;
+      const int s = it & 1;
+      const bool first = (it == 0) && (h == 0), last = (it == n_it - 1) && (h == 1);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
+      mbar_wait_a(sb + GK_PT_FULL + 8 * h, it & 1);
+#ifdef GQ_CYCLES
+      w_pt += GQC_NOW() - t0;
+#endif
+      tc_fence_after();
+      if (elect_one())                                     // dV += P^T dO over this half's 64 queries
+        gq_mma_tm<4, h>(tmem_base + 256, tmem_base + h * 64, domn_lo + s * STAGE, !first);
+      __syncwarp();
+      if (it + 1 < n_it) issue_s(it + 1, hc);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
+      mbar_wait_a(sb + GK_DST_FULL + 8 * h, it & 1);
+#ifdef GQ_CYCLES
+      w_dst += GQC_NOW() - t0;
+#endif
+      tc_fence_after();
+      if (elect_one()) {                                   // dK += dS^T Q
+        gq_mma_tm<4, h>(tmem_base + 384, tmem_base + 128 + h * 64, qmn_lo + s * STAGE, !first);
+        if (h == 1) umma_commit_a(sb + GK_QDO_EMPTY + 8 * s);
+        if (last) umma_commit_a(sb + GK_ACC_DONE);
+      }
+      __syncwarp();
+      if (it + 1 < n_it) issue_dp(it + 1, hc);
+    };
+    for (int it = 0; it < n_it; ++it) {
+      half_step(it, H0{});
+      half_step(it, H1{});
     }
+#ifdef GQ_CYCLES
+    if (lane == 0) {
+      GQC_ADD(32, 2 * n_it);
+      GQC_ADD(33, GQC_NOW() - t_begin);
+      GQC_ADD(34, w_pt);
+      GQC_ADD(35, w_dst);
+    }
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ P^T, dS^T: lane = key row, columns = queries
-    const int half = (warp - 4) >> 2;
+    const int h = (warp - 4) >> 2;                         // this group's query half
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
     const int kv_glob = kt * GQ_T + static_cast<int>(row);
     const bool key_ok = kv_glob < kvl;
-    const int tid_c = threadIdx.x - 128;
+    const int tg = threadIdx.x - 128 - 128 * h;            // 0..127 inside the group
     const unsigned long long c2 = pk2(scale_log2, scale_log2);
+    const uint32_t stat_base = sb + GK_OFF_STAT + h * (2 * GQ_T * 4);
+    auto load_stat = [&](int it) -> float {                // -lse (threads 0..63) / -D (64..127) of this half's queries
+      const int hq = hkv * G + it / n_q_local, i = kt + it % n_q_local;
+      const int qi = i * GQ_T + 64 * h + (tg & 63);
+      const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + min(qi, S - 1);
+      float v = (tg < 64) ? -lse[stat] : -dsum[stat];
+      if (qi >= S) v = (tg < 64) ? -INFINITY : 0.f;        // rows past S: p = 2^(-inf) = 0
+      return v;
+    };
+    float stat_next = load_stat(0);
+#ifdef GQ_CYCLES
+    long long w_bar = 0, w_st = 0, w_dpt = 0, c_p = 0, c_ds = 0, t_begin = GQC_NOW(), t0, t1;
+#endif
     for (int it = 0; it < n_it; ++it) {
       const int s = it & 1;
-      const int hq = hkv * G + it / n_q_local, i = kt + it % n_q_local;
-      {  // this query tile's lse / D rows -> shared memory (under the S^T / dP^T products)
-        const int qi = i * GQ_T + (tid_c & 127);
-        const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + min(qi, S - 1);
-        float v = (tid_c < 128) ? lse[stat] : dsum[stat];
-        if (qi >= S) v = (tid_c < 128) ? INFINITY : 0.f;   // rows past S: p = 2^(-inf) = 0
-        sts_f32(sb + GK_OFF_STAT + s * (2 * GQ_T * 4) + tid_c * 4, v);
-      }
-      named_bar_sync(GQ_BAR_EXCH, 256);
-      mbar_wait_a(sb + GK_ST_FULL, it & 1);
+      const int i = kt + it % n_q_local;
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+#endif
+      sts_f32(stat_base + s * (GQ_T * 4) + tg * 4, stat_next);
+      if (it + 1 < n_it) stat_next = load_stat(it + 1);
+      named_bar_sync(GQ_BAR_EXCH + h, 128);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      w_bar += t1 - t0;
+#endif
+      mbar_wait_a(sb + GK_ST_FULL + 8 * h, it & 1);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+      w_st += t0 - t1;
+#endif
       tc_fence_after();
-      const int q0 = i * GQ_T + half * 64;                 // first query column of this thread
+      const int q0 = i * GQ_T + 64 * h;                    // first query column of this half
       const bool edge = (i == kt);                         // diagonal tile: query < key is masked
-      const uint32_t st_lse = sb + GK_OFF_STAT + s * (2 * GQ_T * 4) + half * 256, st_d = st_lse + GQ_T * 4;
-      uint32_t pt[32], ds[32];
+      const uint32_t st_nl = stat_base + s * (GQ_T * 4), st_nd = st_nl + 64 * 4;
+      unsigned long long p2[32];                           // this row's 64 probabilities, fp32 pairs
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], dp[32];
-        tmem_ld_32x32(tlane + half * 64 + c * 32, sv);
-        tmem_ld_32x32(tlane + 128 + half * 64 + c * 32, dp);
+        uint32_t sv[32], pt[16];
+        tmem_ld_32x32(tlane + h * 64 + c * 32, sv);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          float l0, l1, e0, e1;
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(l0), "=f"(l1) : "r"(st_lse + (c * 32 + k) * 4));
-          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e0), "=f"(e1) : "r"(st_d + (c * 32 + k) * 4));
-          const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2, pk2(-l0, -l1));
-          float x0, x1;
-          unpk2(x2, x0, x1);
-          float p0 = key_ok ? ex2f(x0) : 0.f, p1 = key_ok ? ex2f(x1) : 0.f;
-          if (edge) {
-            const int qg = q0 + c * 32 + k;
-            if (qg < kv_glob) p0 = 0.f;
-            if (qg + 1 < kv_glob) p1 = 0.f;
+        for (int k = 0; k < 32; k += 4) {
+          unsigned long long nl_a, nl_b;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nl_a), "=l"(nl_b) : "r"(st_nl + (c * 32 + k) * 4));
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kk = k + 2 * u;
+            const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[kk]), __uint_as_float(sv[kk + 1])), c2, u ? nl_b : nl_a);
+            float x0, x1;
+            unpk2(x2, x0, x1);
+            float p0 = ex2f(x0), p1 = ex2f(x1);
+            if (edge || !key_ok) {
+              const int qg = q0 + c * 32 + kk;
+              if (qg < kv_glob || !key_ok) p0 = 0.f;
+              if (qg + 1 < kv_glob || !key_ok) p1 = 0.f;
+            }
+            pt[kk >> 1] = pack_bf16(p0, p1);
+            p2[c * 16 + (kk >> 1)] = pk2(p0, p1);
           }
-          pt[c * 16 + (k >> 1)] = pack_bf16(p0, p1);
-          ds[c * 16 + (k >> 1)] = pack_bf16(p0 * (__uint_as_float(dp[k]) - e0) * scale, p1 * (__uint_as_float(dp[k + 1]) - e1) * scale);
         }
-      }
-      tc_fence_before();
-      named_bar_sync(GQ_BAR_EXCH, 256);                    // every thread has read S^T / dP^T: P^T / dS^T may overwrite them
-      tc_fence_after();
-      {
-        uint32_t(&a0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pt[0]);
-        uint32_t(&a1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pt[16]);
-        uint32_t(&b0)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ds[0]);
-        uint32_t(&b1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&ds[16]);
-        tmem_st_32x16(tlane + half * 32, a0);
-        tmem_st_32x16(tlane + half * 32 + 16, a1);
-        tmem_st_32x16(tlane + 128 + half * 32, b0);
-        tmem_st_32x16(tlane + 128 + half * 32 + 16, b1);
+        // P^T overwrites the first 32 columns of this thread's own S^T row half (columns it has already read; no other
+        // thread touches them)
+        tmem_st_32x16(tlane + h * 64 + c * 16, pt);
       }
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_a(sb + GK_PT_FULL);
+      mbar_arrive_a(sb + GK_PT_FULL + 8 * h);
+#ifdef GQ_CYCLES
+      t1 = GQC_NOW();
+      c_p += t1 - t0;
+#endif
+      mbar_wait_a(sb + GK_DPT_FULL + 8 * h, it & 1);
+#ifdef GQ_CYCLES
+      t0 = GQC_NOW();
+      w_dpt += t0 - t1;
+#endif
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t dp[32], ds[16];
+        tmem_ld_32x32(tlane + 128 + h * 64 + c * 32, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+          unsigned long long nd_a, nd_b;
+          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nd_a), "=l"(nd_b) : "r"(st_nd + (c * 32 + k) * 4));
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kk = k + 2 * u;
+            const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[kk]), __uint_as_float(dp[kk + 1])), u ? nd_b : nd_a);
+            const unsigned long long d2 = fmul2(p2[c * 16 + (kk >> 1)], t2);
+            float d0, d1;
+            unpk2(d2, d0, d1);
+            ds[kk >> 1] = pack_bf16(d0, d1);               // (the 1/sqrt(d) factor is applied to dK at the end)
+          }
+        }
+        tmem_st_32x16(tlane + 128 + h * 64 + c * 16, ds);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_a(sb + GK_DST_FULL + 8 * h);
+#ifdef GQ_CYCLES
+      c_ds += GQC_NOW() - t0;
+#endif
     }
+#ifdef GQ_CYCLES
+    if (lane == 0 && (warp & 3) == 0) {                    // one warp per group
+      GQC_ADD(40, n_it);
+      GQC_ADD(41, GQC_NOW() - t_begin);
+      GQC_ADD(42, w_bar);
+      GQC_ADD(43, w_st);
+      GQC_ADD(44, c_p);
+      GQC_ADD(45, w_dpt);
+      GQC_ADD(46, c_ds);
+    }
+#endif
     mbar_wait_a(sb + GK_ACC_DONE, 0);
     tc_fence_after();
     const bool live = kv_glob < S;
-    const size_t o = ((static_cast<size_t>(b) * S + kv_glob) * Hkv + hkv) * GQ_T + half * 64;
+    const size_t o = ((static_cast<size_t>(b) * S + kv_glob) * Hkv + hkv) * GQ_T + h * 64;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       uint4* dst = reinterpret_cast<uint4*>((which == 0 ? dv : dk) + o);
+      const float f = which == 0 ? 1.0f : scale;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t r[32];
-        tmem_ld_32x32(tlane + 256 + which * 128 + half * 64 + c * 32, r);
+        tmem_ld_32x32(tlane + 256 + which * 128 + h * 64 + c * 32, r);
         tmem_ld_wait();
         if (live) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 v;
-            v.x = pack_bf16(__uint_as_float(r[8 * u]), __uint_as_float(r[8 * u + 1]));
-            v.y = pack_bf16(__uint_as_float(r[8 * u + 2]), __uint_as_float(r[8 * u + 3]));
-            v.z = pack_bf16(__uint_as_float(r[8 * u + 4]), __uint_as_float(r[8 * u + 5]));
-            v.w = pack_bf16(__uint_as_float(r[8 * u + 6]), __uint_as_float(r[8 * u + 7]));
+            v.x = pack_bf16(__uint_as_float(r[8 * u]) * f, __uint_as_float(r[8 * u + 1]) * f);
+            v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * f, __uint_as_float(r[8 * u + 3]) * f);
+            v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * f, __uint_as_float(r[8 * u + 5]) * f);
+            v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * f, __uint_as_float(r[8 * u + 7]) * f);
             dst[c * 4 + u] = v;
           }
         }
@@ -704,7 +1061,7 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const void* out,
+int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const void* q, const void* out,
                    const void* d_out, const float* lse, float* dsum_ws, const int* kv_len, void* dq, void* dk, void* dv, int B,
                    int S, int Hq, int Hkv, float scale, cudaStream_t stream) {
   static bool attr_set = false;
@@ -718,10 +1075,11 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(d_out), dsum_ws, B, S, Hq);
   AL_CHECK_CUDA(cudaGetLastError());
   const int nt = (S + GQ_T - 1) / GQ_T;
-  gqa_bwd_dq_kernel<<<dim3(nt, Hq, B), GQ_THREADS, GD_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
-                                                                       reinterpret_cast<__nv_bfloat16*>(dq), S, Hq, Hkv, scale);
+  gqa_bwd_dq_kernel<<<dim3(nt, Hq, B), GD_THREADS, GD_SMEM, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<const __nv_bfloat16*>(d_out), lse, dsum_ws, kv_len,
+      reinterpret_cast<__nv_bfloat16*>(dq), S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
-  gqa_bwd_dkv_kernel<<<dim3(nt, Hkv, B), GQ_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
+  gqa_bwd_dkv_kernel<<<dim3(nt, Hkv, B), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
                                                                          reinterpret_cast<__nv_bfloat16*>(dk),
                                                                          reinterpret_cast<__nv_bfloat16*>(dv), S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
@@ -729,3 +1087,15 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 }
 
 }  // namespace al
+
+#ifdef GQ_CYCLES
+extern "C" int al_debug_gqa_cycles(unsigned long long* out64, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out64, al::gq_cyc, sizeof(al::gq_cyc));
+  if (reset) {
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(al::gq_cyc, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

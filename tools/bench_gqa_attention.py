@@ -63,3 +63,28 @@ t_ob = timeit(ours_fb)
 t_rb = timeit(ref_fb)
 print(f"native  fwd {t_of:.3f} ms ({flops_fwd / t_of / 1e9:.0f} TFLOP/s)   fwd+bwd {t_ob:.3f} ms (bwd alone ~{flops_bwd / max(t_ob - t_of, 1e-6) / 1e9:.0f} TFLOP/s)")
 print(f"SDPA    fwd {t_rf:.3f} ms ({flops_fwd / t_rf / 1e9:.0f} TFLOP/s)   fwd+bwd {t_rb:.3f} ms (bwd alone ~{flops_bwd / max(t_rb - t_rf, 1e-6) / 1e9:.0f} TFLOP/s)")
+
+if os.environ.get("KERNELS"):                      # per-kernel device times of the native path
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            ours_fb()
+        torch.cuda.synchronize()
+    for ev in prof.key_averages():
+        if "gqa_" in ev.key:
+            print(f"  {ev.key[:48]:48s} {ev.device_time_total / ev.count:9.1f} us x {ev.count}")
+
+if os.environ.get("CYCLES"):                       # a -DGQ_CYCLES build (AUDIOLLM_B200_LIB=...): per-role cycle accounts
+    import ctypes
+    lib = ctypes.CDLL(os.environ["AUDIOLLM_B200_LIB"])
+    buf = (ctypes.c_ulonglong * 64)()
+    lib.al_debug_gqa_cycles(buf, 1)
+    ours_fb()
+    lib.al_debug_gqa_cycles(buf, 0)
+    v = list(buf)
+    names = {0: "fwd issuer [total wait_P]", 8: "fwd compute [total wait_S max bar exp wait_O store]", 16: "dq issuer [total issue_SdP wait_dS]",
+             24: "dq compute [total wait_SdP math wait_dQ store]", 32: "dkv issuer [total wait_PT wait_dST]",
+             40: "dkv compute [total bar wait_ST P wait_dPT dS]"}
+    for base, nm in names.items():
+        if v[base]:
+            print(f"  {nm}: n={v[base]}  per-unit cycles: " + " ".join(f"{x / v[base]:.0f}" for x in v[base + 1:base + 8]))
