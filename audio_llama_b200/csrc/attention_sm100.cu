@@ -96,30 +96,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x for a pair, x <= ~9, on the FMA / ALU pipes.
-__device__ __forceinline__ void poly_exp2_pair(unsigned long long x2, float& o0, float& o1) {
-  float x0, x1;
-  unpk2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  const unsigned long long xc = pk2(x0, x1);
-  const unsigned long long MAGIC = pk2(12582912.0f, 12582912.0f);          // 1.5 * 2^23
-  const unsigned long long NMAGIC = pk2(-12582912.0f, -12582912.0f);
-  const unsigned long long NEG1 = pk2(-1.0f, -1.0f);
-  const unsigned long long t = fadd2(xc, MAGIC);                           // low mantissa bits = round(x)
-  const unsigned long long xr = fadd2(t, NMAGIC);
-  const unsigned long long f = ffma2(xr, NEG1, xc);                        // x - round(x) in [-0.5, 0.5]
-  unsigned long long p = ffma2(pk2(0.05508868396282196f, 0.05508868396282196f), f,
-                               pk2(0.24260404706001282f, 0.24260404706001282f));
-  p = ffma2(p, f, pk2(0.6932762265205383f, 0.6932762265205383f));
-  p = ffma2(p, f, pk2(0.9999289512634277f, 0.9999289512634277f));
-  float t0, t1, p0, p1;
-  unpk2(t, t0, t1);
-  unpk2(p, p0, p1);
-  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-
 // Exact attention for ONE query row by one warp (plain loads, online softmax in fp32). Only used for the rows of a CTA in
 // which the fast path flagged a possible overflow of its lagged softmax reference (see the softmax warps below): a
 // score that outgrows the reference by more than 2^100 within two kv tiles. Slow, exact, practically never taken.

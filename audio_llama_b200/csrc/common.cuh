@@ -408,6 +408,39 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
+
+// 2^x for a pair on the FMA / ALU pipes (degree-3 polynomial on the fraction, exponent added as an integer; relative
+// error 7e-5). x < -126 is clamped (result ~ 0). CLAMP_HI: x > 127 is clamped to 127 as well, so that an argument the
+// XU path would turn into +inf comes out as a finite value >= 2^126 instead of a wrapped exponent (callers whose
+// reference can lag behind the scores rely on such terms tripping their overflow guard); callers with x <= ~10 by
+// construction skip that instruction.
+template <bool CLAMP_HI = true>
+__device__ __forceinline__ void poly_exp2_pair(unsigned long long x2, float& o0, float& o1) {
+  float x0, x1;
+  unpk2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  if (CLAMP_HI) {
+    x0 = fminf(x0, 127.0f);
+    x1 = fminf(x1, 127.0f);
+  }
+  const unsigned long long xc = pk2(x0, x1);
+  const unsigned long long MAGIC = pk2(12582912.0f, 12582912.0f);          // 1.5 * 2^23
+  const unsigned long long NMAGIC = pk2(-12582912.0f, -12582912.0f);
+  const unsigned long long NEG1 = pk2(-1.0f, -1.0f);
+  const unsigned long long t = fadd2(xc, MAGIC);                           // low mantissa bits = round(x)
+  const unsigned long long xr = fadd2(t, NMAGIC);
+  const unsigned long long f = ffma2(xr, NEG1, xc);                        // x - round(x) in [-0.5, 0.5]
+  unsigned long long p = ffma2(pk2(0.05508868396282196f, 0.05508868396282196f), f,
+                               pk2(0.24260404706001282f, 0.24260404706001282f));
+  p = ffma2(p, f, pk2(0.6932762265205383f, 0.6932762265205383f));
+  p = ffma2(p, f, pk2(0.9999289512634277f, 0.9999289512634277f));
+  float t0, t1, p0, p1;
+  unpk2(t, t0, t1);
+  unpk2(p, p0, p1);
+  o0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  o1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>

@@ -37,6 +37,10 @@ constexpr int GQ_CW = GQ_T / GQ_SPLIT;         // columns of a 128-wide tile row
 constexpr int GQ_COMPUTE = GQ_T * GQ_SPLIT;    // compute threads
 constexpr int GQ_THREADS = 128 + GQ_COMPUTE;   // warps 0-3 control (TMA, MMA, TMEM allocator, idle), then the compute warps
 constexpr float GQ_TAU = 8.0f;                 // lazy-rescale threshold of the forward, log2 units
+#ifndef GQ_POLY_NUM
+#define GQ_POLY_NUM 1
+#define GQ_POLY_DEN 4
+#endif
 constexpr int GQ_BAR_EXCH = 1;                 // named barrier of the compute threads
 constexpr float LOG2E_GQ = 1.4426950408889634f;
 
@@ -121,9 +125,16 @@ __device__ __forceinline__ void gq_mma_tm(uint32_t d_tmem, uint32_t a_tmem, uint
     umma_ts_lo(d_tmem, a_tmem + k * 8, b_lo + ((2048 * (4 * H + k)) >> 4), IDESC, (k != 0) || accumulate);
 }
 
+// D[tmem 128 x 128] = A[tmem: 128 lanes x 128 bf16 = 64 columns] * B[smem tile, K-major over d]^T
+__device__ __forceinline__ void gq_mma_tk(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo) {
+  constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_ts_lo(d_tmem, a_tmem + k * 8, b_lo + (((k >> 2) * GQ_BOX_BYTES + (k & 3) * 32) >> 4), IDESC, k != 0);
+}
+
 // ============================================================================ forward
-constexpr uint32_t GF_OFF_Q = 0;
-constexpr uint32_t GF_OFF_K = GQ_TILE_BYTES;
+constexpr uint32_t GF_OFF_K = 0;
 constexpr uint32_t GF_OFF_V = GF_OFF_K + 2 * GQ_TILE_BYTES;
 constexpr uint32_t GF_OFF_EXCH = GF_OFF_V + 2 * GQ_TILE_BYTES;       // [2 parities][GQ_SPLIT][128] f32 row maxima, then [GQ_SPLIT][128] sums
 constexpr uint32_t GF_OFF_BARS = GF_OFF_EXCH + 3 * GQ_SPLIT * GQ_T * 4;
@@ -133,23 +144,23 @@ constexpr uint32_t GF_Q_FULL = GF_OFF_BARS, GF_K_FULL = GF_Q_FULL + 8, GF_K_EMPT
 constexpr int GF_SMEM = GF_TMEM_PTR + 16 + 1024;
 
 __global__ void __launch_bounds__(GQ_THREADS, 1)
-gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                const int* __restrict__ kv_len, int S, int Hq, int Hkv, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heavy tiles first: query tile qt visits qt + 1 kv tiles (causal), so the block order runs from the last tile down
-  const int qt = gridDim.x - 1 - blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
+  // heavy tiles first, over the WHOLE grid (blockIdx.z is the slowest index of the launch order): query tile qt visits
+  // qt + 1 kv tiles (causal), so the heaviest work items start first and the tail of the grid is made of the light ones
+  const int qt = gridDim.z - 1 - blockIdx.z, hq = blockIdx.x, b = blockIdx.y;
   const int hkv = hq / (Hq / Hkv);
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
 
   if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init_a(sb + GF_Q_FULL, 1);
+    mbar_init_a(sb + GF_Q_FULL, GQ_COMPUTE);
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GF_K_FULL + 8 * s, 1);
       mbar_init_a(sb + GF_K_EMPTY + 8 * s, 1);
@@ -171,11 +182,11 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GF_TMEM_PTR) : "memory");
-  // TMEM columns: S0 0..127 | S1 128..255 | O 256..383 | P 384..447 (bf16 pairs)
+  // TMEM columns: S0 0..127 | S1 128..255 | O 256..383 | P 384..447 (bf16 pairs) | Q 448..511 (bf16 pairs: the A operand of
+  // every S = Q K_j^T of this CTA, so those products read only K from shared memory)
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
-      gq_load_tile(sb + GF_OFF_Q, &tmQ, sb + GF_Q_FULL, hq, qt * GQ_T, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j & 1;
         if (j >= 2) mbar_wait_a(sb + GF_K_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
@@ -187,14 +198,14 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: S_j one tile ahead of P V_{j-1}
     mbar_wait_a(sb + GF_Q_FULL, 0);
-    const uint32_t q_lo = gq_desc_kmajor(sb + GF_OFF_Q), k_lo = gq_desc_kmajor(sb + GF_OFF_K), v_lo = gq_desc_mnmajor(sb + GF_OFF_V);
+    const uint32_t k_lo = gq_desc_kmajor(sb + GF_OFF_K), v_lo = gq_desc_mnmajor(sb + GF_OFF_V);
     auto issue_qk = [&](int j) {
       const int s = j & 1;
       mbar_wait_a(sb + GF_K_FULL + 8 * s, (j >> 1) & 1);
       if (j >= 2) mbar_wait_a(sb + GF_S_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        gq_mma_kk<128, 0>(tmem_base + s * 128, q_lo, k_lo + s * (GQ_TILE_BYTES >> 4), false);
+        gq_mma_tk(tmem_base + s * 128, tmem_base + 448, k_lo + s * (GQ_TILE_BYTES >> 4));
         umma_commit_a(sb + GF_K_EMPTY + 8 * s);
         umma_commit_a(sb + GF_S_FULL + 8 * s);
       }
@@ -238,6 +249,27 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const int q_glob = qt * GQ_T + static_cast<int>(row);
     constexpr uint32_t EX_STRIDE = GQ_T * 4, EX_SET = GQ_SPLIT * GQ_T * 4;   // one part's slots | one parity's set
     const uint32_t ex_row = sb + GF_OFF_EXCH + row * 4;
+    {   // this thread's GQ_CW columns of the Q row -> TMEM (bf16 pairs are already the A-operand layout)
+      const bool live = q_glob < S;
+      const uint4* src = reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * S + (live ? q_glob : 0)) * Hq + hq) * GQ_T +
+                                                        part * GQ_CW);
+#pragma unroll
+      for (int c = 0; c < GQ_CW / 32; ++c) {
+        uint32_t r[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint4 v = live ? __ldg(src + 4 * c + u) : make_uint4(0, 0, 0, 0);
+          r[4 * u] = v.x;
+          r[4 * u + 1] = v.y;
+          r[4 * u + 2] = v.z;
+          r[4 * u + 3] = v.w;
+        }
+        tmem_st_32x16(tlane + 448 + part * (GQ_CW / 2) + 16 * c, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive_a(sb + GF_Q_FULL);
+    }
     float m_ref = -INFINITY, l = 0.f;
 #ifdef GQ_CYCLES
     long long w_s = 0, w_bar = 0, w_o = 0, c_a = 0, c_b = 0, c_c = 0, t_begin = GQC_NOW(), t0, t1;
@@ -301,9 +333,15 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int k = 0; k < GQ_CW; k += 2) {
         const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), c2, nm2);
-        float x0, x1;
-        unpk2(x2, x0, x1);
-        const float p0 = ex2f(x0), p1 = ex2f(x1);
+        float p0, p1;
+        if (((k >> 1) % GQ_POLY_DEN) < GQ_POLY_NUM) {       // this share of the exponentials on the FMA pipe (the XU is the
+          poly_exp2_pair<false>(x2, p0, p1);                // narrower one: 16 ex2 / cycle / SM against 16384 per tile)
+        } else {
+          float x0, x1;
+          unpk2(x2, x0, x1);
+          p0 = ex2f(x0);
+          p1 = ex2f(x1);
+        }
         if ((k >> 1) & 1) l2b = fadd2(l2b, pk2(p0, p1));
         else l2a = fadd2(l2a, pk2(p0, p1));
         pk[k >> 1] = pack_bf16(p0, p1);
@@ -398,15 +436,15 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_gqa_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
+int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
                    const int* kv_len, int B, int S, int Hq, int Hkv, float scale, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(gqa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM));
     attr_set = true;
   }
-  dim3 grid((S + GQ_T - 1) / GQ_T, Hq, B);
-  gqa_fwd_kernel<<<grid, GQ_THREADS, GF_SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, kv_len, S, Hq,
+  dim3 grid(Hq, B, (S + GQ_T - 1) / GQ_T);
+  gqa_fwd_kernel<<<grid, GQ_THREADS, GF_SMEM, stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, kv_len, S, Hq,
                                                         Hkv, scale * 1.4426950408889634f);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -462,14 +500,6 @@ constexpr int GD_SMEM = GD_TMEM_PTR + 16 + 1024;
 static_assert(GD_CW == 32, "the dQ kernel's compute loop handles one 32-column chunk per thread");
 constexpr uint32_t GD_TM_S = 0, GD_TM_DP = 128, GD_TM_DQ = 256, GD_TM_Q = 384, GD_TM_DO = 448;
 
-// D[tmem 128 x 128] = A[tmem: 128 lanes x 128 bf16 = 64 columns] * B[smem tile, K-major over d]^T
-__device__ __forceinline__ void gq_mma_tk(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo) {
-  constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T);
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    umma_ts_lo(d_tmem, a_tmem + k * 8, b_lo + (((k >> 2) * GQ_BOX_BYTES + (k & 3) * 32) >> 4), IDESC, k != 0);
-}
-
 __global__ void __launch_bounds__(GD_THREADS, 1)
 gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __nv_bfloat16* __restrict__ d_out,
@@ -478,8 +508,9 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heavy tiles first: query tile qt visits qt + 1 kv tiles (causal), so the block order runs from the last tile down
-  const int qt = gridDim.x - 1 - blockIdx.x, hq = blockIdx.y, b = blockIdx.z;
+  // heavy tiles first, over the WHOLE grid (blockIdx.z is the slowest index of the launch order): query tile qt visits
+  // qt + 1 kv tiles (causal), so the heaviest work items start first and the tail of the grid is made of the light ones
+  const int qt = gridDim.z - 1 - blockIdx.z, hq = blockIdx.x, b = blockIdx.y;
   const int hkv = hq / (Hq / Hkv);
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
@@ -752,7 +783,7 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.x, hkv = blockIdx.y, b = blockIdx.z;
+  const int kt = blockIdx.z, hkv = blockIdx.x, b = blockIdx.y;   // kv tile 0 meets every query tile: heaviest first
   const int G = Hq / Hkv;
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int nq = (S + GQ_T - 1) / GQ_T;
@@ -1075,11 +1106,11 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(d_out), dsum_ws, B, S, Hq);
   AL_CHECK_CUDA(cudaGetLastError());
   const int nt = (S + GQ_T - 1) / GQ_T;
-  gqa_bwd_dq_kernel<<<dim3(nt, Hq, B), GD_THREADS, GD_SMEM, stream>>>(
+  gqa_bwd_dq_kernel<<<dim3(Hq, B, nt), GD_THREADS, GD_SMEM, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<const __nv_bfloat16*>(d_out), lse, dsum_ws, kv_len,
       reinterpret_cast<__nv_bfloat16*>(dq), S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
-  gqa_bwd_dkv_kernel<<<dim3(nt, Hkv, B), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
+  gqa_bwd_dkv_kernel<<<dim3(Hkv, B, nt), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
                                                                          reinterpret_cast<__nv_bfloat16*>(dk),
                                                                          reinterpret_cast<__nv_bfloat16*>(dv), S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
