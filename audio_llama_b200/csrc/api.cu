@@ -1018,10 +1018,26 @@ int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_o
 }
 
 // ----------------------------------------------------------------------------- LoRA linear
+int al_linear_add_bf16(const void* x, int rows, int in_dim, int out_dim, const void* W, const float* bias, const void* addend,
+                       void* out, al_stream_t stream) {
+  AL_REQUIRE(x && W && out && addend, "al_linear_add_bf16: NULL argument");
+  AL_REQUIRE(rows > 0 && in_dim % 8 == 0 && out_dim % 8 == 0, "al_linear_add_bf16: bad shape rows=%d in=%d out=%d", rows, in_dim, out_dim);
+  return gemm_plain(x, in_dim, rows, W, in_dim, out_dim, in_dim, bias, out, out_dim, EPI_ADD_BF16, addend, out_dim, 0,
+                    (cudaStream_t)stream);
+}
+
 int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W, const float* bias,
                            const void* lora_A, const void* lora_B_scaled, void* t_ws, void* out, int out_dtype,
                            al_stream_t stream) {
+  return al_lora_linear_forward_ex(x, rows, in_dim, out_dim, rank, W, bias, lora_A, lora_B_scaled, t_ws, nullptr, out, out_dtype,
+                                   stream);
+}
+int al_lora_linear_forward_ex(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W, const float* bias,
+                              const void* lora_A, const void* lora_B_scaled, void* t_ws, const void* addend, void* out,
+                              int out_dtype, al_stream_t stream) {
   AL_REQUIRE(x && W && lora_A && lora_B_scaled && t_ws && out, "al_lora_linear_forward: NULL argument");
+  AL_REQUIRE(addend == nullptr || (out_dtype == 0 && out_dim % 8 == 0),
+             "al_lora_linear_forward_ex: an addend needs a bf16 output and out_dim %% 8 == 0 (out_dim=%d)", out_dim);
   AL_REQUIRE(rows > 0 && in_dim % 8 == 0 && rank % 8 == 0 && rank > 0 && out_dim > 0,
              "al_lora_linear_forward: bad shape rows=%d in=%d out=%d rank=%d", rows, in_dim, out_dim, rank);
   // 1. T = x A^T  [rows, rank] (bf16)
@@ -1034,12 +1050,14 @@ int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int
   if ((rc = tmap_weight(&tb, W, out_dim, in_dim))) return rc;
   if ((rc = tmap_rows3d(&ta2, t_ws, 2, rank, rows, 1, rank, (uint64_t)rows * rank, 64, 128))) return rc;
   if ((rc = tmap_weight(&tb2, lora_B_scaled, out_dim, rank))) return rc;
-  const int flags = out_dtype == 1 ? AL_EPI_OUT_F32 : 0;
+  const int flags = out_dtype == 1 ? AL_EPI_OUT_F32 : (addend ? EPI_ADD_BF16 : 0);
   if ((rc = tmap_rows3d(&to, out, out_dtype == 1 ? 4 : 2, out_dim, rows, 1, out_dim, (uint64_t)rows * out_dim,
                         gemm_out_box_cols(flags), 128)))
     return rc;
   GemmParams p{};
   p.m_per_batch = rows; p.batch = 1; p.N = out_dim; p.K = in_dim; p.K2 = rank; p.bias = bias;
+  p.grad_in = reinterpret_cast<const __nv_bfloat16*>(addend);
+  p.grad_ld = out_dim;
   rc = launch_gemm2(ta, tb, to, ta2, tb2, p, flags, num_sms(), (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
@@ -1064,6 +1082,12 @@ size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim
 int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
                             const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace, void* dx,
                             float* dA, float* dB_raw, al_stream_t stream) {
+  return al_lora_linear_backward_ex(x, dy, rows, in_dim, out_dim, rank, W_T, lora_A, lora_B_scaled, t_saved, workspace, nullptr, dx,
+                                    dA, dB_raw, stream);
+}
+int al_lora_linear_backward_ex(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
+                               const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace,
+                               const void* dx_addend, void* dx, float* dA, float* dB_raw, al_stream_t stream) {
   AL_REQUIRE(x && dy && lora_A && lora_B_scaled && t_saved && workspace && dA && dB_raw,
              "al_lora_linear_backward: NULL argument");
   AL_REQUIRE(dx == nullptr || W_T != nullptr, "al_lora_linear_backward: dx needs W_T ([in][out], the frozen weight transposed)");
@@ -1095,7 +1119,9 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
     if ((rc = tmap_rows3d(&to, dx, 2, in_dim, rows, 1, in_dim, (uint64_t)rows * in_dim, gemm_out_box_cols(0), 128))) return rc;
     GemmParams p{};
     p.m_per_batch = rows; p.batch = 1; p.N = in_dim; p.K = out_dim; p.K2 = rank;
-    rc = launch_gemm2(ta, tb, to, ta2, tb2, p, 0, num_sms(), st);
+    p.grad_in = reinterpret_cast<const __nv_bfloat16*>(dx_addend);   // dx = ... + dx_addend (may be dx itself)
+    p.grad_ld = in_dim;
+    rc = launch_gemm2(ta, tb, to, ta2, tb2, p, dx_addend ? EPI_ADD_BF16 : 0, num_sms(), st);
     if (rc) return rc;
     g_launches += 1;
   }
@@ -1110,14 +1136,18 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
 // ----------------------------------------------------------------------------- LLaMA-side row kernels (§8f-1 slice)
 int al_rmsnorm_forward(const void* x, const void* weight, void* y, float* rstd, int rows, int d, float eps, al_stream_t stream) {
   AL_REQUIRE(x && weight && y && rows >= 0, "al_rmsnorm_forward: NULL argument");
-  int rc = launch_rmsnorm(x, weight, y, rstd, nullptr, nullptr, rows, d, eps, false, (cudaStream_t)stream);
+  int rc = launch_rmsnorm(x, weight, y, rstd, nullptr, nullptr, nullptr, rows, d, eps, false, (cudaStream_t)stream);
   if (rc == 0 && rows > 0) g_launches += 1;
   return rc;
 }
 int al_rmsnorm_backward(const void* x, const void* weight, const float* rstd, const void* dy, void* dx, int rows, int d,
                         al_stream_t stream) {
+  return al_rmsnorm_backward_ex(x, weight, rstd, dy, nullptr, dx, rows, d, stream);
+}
+int al_rmsnorm_backward_ex(const void* x, const void* weight, const float* rstd, const void* dy, const void* dx_addend, void* dx,
+                           int rows, int d, al_stream_t stream) {
   AL_REQUIRE(x && weight && rstd && dy && dx && rows >= 0, "al_rmsnorm_backward: NULL argument");
-  int rc = launch_rmsnorm(x, weight, nullptr, const_cast<float*>(rstd), dy, dx, rows, d, 0.f, true, (cudaStream_t)stream);
+  int rc = launch_rmsnorm(x, weight, nullptr, const_cast<float*>(rstd), dy, dx_addend, dx, rows, d, 0.f, true, (cudaStream_t)stream);
   if (rc == 0 && rows > 0) g_launches += 1;
   return rc;
 }

@@ -56,6 +56,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool ROWAUX = (FLAGS & EPI_ROWAUX) != 0;
   constexpr bool RESID = (FLAGS & EPI_RESIDUAL) != 0;
   constexpr bool GELU_GRAD = (FLAGS & EPI_GELU_GRAD) != 0;
+  constexpr bool ADD16 = (FLAGS & EPI_ADD_BF16) != 0;
   constexpr bool TN = (FLAGS & EPI_TN) != 0;     // operands row-major over the contraction: staged MN-major
   constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_ROWS = CTA2 ? 128 : 256;       // weight rows staged by this CTA
@@ -263,6 +264,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < CH; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
         }
+        if constexpr (ADD16) {
+          // + a bf16 addend with the output's shape (possibly the output buffer itself: this CTA is the only reader and
+          // writer of the tile and reads it before its own TMA store -> plain coherent loads)
+          const __nv_bfloat16* ap = p.grad_in + (static_cast<size_t>(b) * p.m_per_batch + grow) * p.grad_ld + col0;
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            if (fullc) {
+              const uint4 g = *reinterpret_cast<const uint4*>(ap + j);
+              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[j + 2 * q] += __uint_as_float(gw[q] << 16);
+                v[j + 2 * q + 1] += __uint_as_float(gw[q] & 0xffff0000u);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                if (col0 + j + q < p.N) v[j + q] += __bfloat162float(ap[j + q]);
+            }
+          }
+        }
         if constexpr (GELU_GRAD) {
           // backward of h = gelu(a): v holds the recomputed pre-activation a = x W1^T + b1; out = dh * gelu'(a),
           // gelu'(a) = Phi(a) + a phi(a). dh is a bf16 [M][N] matrix read row-wise (128 B per thread).
@@ -433,6 +455,8 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
       return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_GELU_GRAD:
       return launch_mode<EPI_GELU_GRAD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case EPI_ADD_BF16:
+      return launch_mode<EPI_ADD_BF16>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     case EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD:
       return launch_mode<EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
     default:

@@ -156,6 +156,9 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
   const int hkv = hq / (Hq / Hkv);
   const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
+#ifdef GQ_CYCLES
+  const long long t_entry = GQC_NOW();
+#endif
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmK);
@@ -390,6 +393,9 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
     }
 #ifdef GQ_CYCLES
     if (lane == 0 && warp == 4) {
+      GQC_ADD(48, 1);                                      // per CTA: entry -> loop start, loop, (epilogue added below)
+      GQC_ADD(49, t_begin - t_entry);
+      GQC_ADD(50, GQC_NOW() - t_begin);
       GQC_ADD(8, n_tiles);
       GQC_ADD(9, GQC_NOW() - t_begin);
       GQC_ADD(10, w_s);
@@ -430,10 +436,16 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
         }
       }
     }
+#ifdef GQ_CYCLES
+    if (lane == 0 && warp == 4) GQC_ADD(51, GQC_NOW() - t_entry);
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
+#ifdef GQ_CYCLES
+  if (threadIdx.x == 0) GQC_ADD(52, GQC_NOW() - t_entry);
+#endif
 }
 
 int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,

@@ -16,6 +16,8 @@ enum GemmEpilogue : int {
   EPI_RESIDUAL = 16,    // + resid[batch][row][col] (fp32, may alias out: in-place residual add, no atomics)
   EPI_GELU_GRAD = 32,   // out = grad_in[row][col] * gelu'(acc + bias)  (backward of a Linear+GELU, recomputed)
   EPI_TN = 64,          // operand layout, not an epilogue: out = A_src^T W_src with A_src [K][M], W_src [K][N] row-major
+  EPI_ADD_BF16 = 128,   // + addend[row][col] (bf16 rows of grad_ld elements through grad_in; may alias a bf16 out: residual
+                        //   adds and gradient accumulation of the LLaMA layers without a separate elementwise pass)
                         // (contraction over the ROWS: weight gradients); both operands are staged MN-major
 };
 
@@ -117,8 +119,8 @@ int launch_mel(const float* wave, const int* n_samples, int B, long long wave_st
 int launch_mel_finalize(float* out, const unsigned int* clip_max_bits, int B, int n_mels, cudaStream_t stream);
 
 // ------------------------------------------------------------------ LLaMA-side row kernels (llama_rows.cu)
-int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const void* dy, void* dx, int rows, int d, float eps,
-                   bool backward, cudaStream_t st);
+int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const void* dy, const void* addend, void* dx, int rows, int d,
+                   float eps, bool backward, cudaStream_t st);
 int launch_swiglu(const void* gate, const void* up, const void* dh, void* out0, void* out1, long long n, bool backward,
                   int num_sms, cudaStream_t st);
 int launch_rope(const void* x, const void* cs, const void* sn, void* out, int B, int S, int H, int hd, int cos_batch,

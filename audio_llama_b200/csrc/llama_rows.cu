@@ -67,11 +67,12 @@ rmsnorm_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, uin
   }
 }
 
-// dx = rstd * (g - xhat * mean(g * xhat)), g = dy * w, xhat = x * rstd (the weight is frozen: no dw).
+// dx = rstd * (g - xhat * mean(g * xhat)), g = dy * w, xhat = x * rstd (the weight is frozen: no dw), + addend when given
+// (the gradient that reaches x through the residual connection: one pass instead of autograd's separate add).
 template <int MAXV>
 __global__ void __launch_bounds__(256, (MAXV <= 12) ? 3 : 2)
 rmsnorm_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, const float* __restrict__ rstd_in,
-                   const uint4* __restrict__ dy, uint4* __restrict__ dx, int rows, int nvec, float inv_d) {
+                   const uint4* __restrict__ dy, const uint4* addend, uint4* dx, int rows, int nvec, float inv_d) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -107,14 +108,20 @@ rmsnorm_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ w, con
       unpack8(__ldg(w + c), wf);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = rstd * (df[k] * wf[k] - xf[k] * rstd * dot);
+      if (addend != nullptr) {                 // (may be dx itself: each element is read and written by this lane only)
+        float af[8];
+        unpack8(addend[base + c], af);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] += af[k];
+      }
       dx[base + c] = pack8(o);
     }
   }
 }
 
 template <int MAXV>
-static int rmsnorm_launch(const void* x, const void* w, void* y, float* rstd, const void* dy, void* dx, int rows, int d, float eps,
-                          bool backward, cudaStream_t st) {
+static int rmsnorm_launch(const void* x, const void* w, void* y, float* rstd, const void* dy, const void* addend, void* dx, int rows,
+                          int d, float eps, bool backward, cudaStream_t st) {
   const int nvec = d / 8;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   if (!backward)
@@ -122,20 +129,20 @@ static int rmsnorm_launch(const void* x, const void* w, void* y, float* rstd, co
                                                     reinterpret_cast<uint4*>(y), rstd, rows, nvec, 1.0f / d, eps);
   else
     rmsnorm_bwd_kernel<MAXV><<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(w), rstd,
-                                                    reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), rows, nvec,
-                                                    1.0f / d);
+                                                    reinterpret_cast<const uint4*>(dy), reinterpret_cast<const uint4*>(addend),
+                                                    reinterpret_cast<uint4*>(dx), rows, nvec, 1.0f / d);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const void* dy, void* dx, int rows, int d, float eps,
-                   bool backward, cudaStream_t st) {
+int launch_rmsnorm(const void* x, const void* w, void* y, float* rstd, const void* dy, const void* addend, void* dx, int rows, int d,
+                   float eps, bool backward, cudaStream_t st) {
   AL_REQUIRE(d % 8 == 0 && d <= 8192, "rmsnorm: d=%d must be a multiple of 8 and <= 8192", d);
   if (rows == 0) return 0;
-  if (d <= 2048) return rmsnorm_launch<8>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
-  if (d <= 3072) return rmsnorm_launch<12>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);   // fewer registers: 4 CTAs / SM
-  if (d <= 4096) return rmsnorm_launch<16>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
-  return rmsnorm_launch<32>(x, w, y, rstd, dy, dx, rows, d, eps, backward, st);
+  if (d <= 2048) return rmsnorm_launch<8>(x, w, y, rstd, dy, addend, dx, rows, d, eps, backward, st);
+  if (d <= 3072) return rmsnorm_launch<12>(x, w, y, rstd, dy, addend, dx, rows, d, eps, backward, st);   // fewer registers: 4 CTAs / SM
+  if (d <= 4096) return rmsnorm_launch<16>(x, w, y, rstd, dy, addend, dx, rows, d, eps, backward, st);
+  return rmsnorm_launch<32>(x, w, y, rstd, dy, addend, dx, rows, d, eps, backward, st);
 }
 
 // ----------------------------------------------------------------------------- SwiGLU

@@ -18,6 +18,7 @@ There is no CPU fallback: inputs that are not bf16 CUDA tensors go to the module
 """
 from __future__ import annotations
 
+import os
 import types
 
 import torch
@@ -56,6 +57,41 @@ class _RMSNormFn(torch.autograd.Function):
 
 def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
     return _RMSNormFn.apply(x, weight, eps)
+
+
+class _ResidualRMSNormFn(torch.autograd.Function):
+    """(x, rmsnorm(x)): the residual stream and its normalised copy from one node, so that the backward receives both
+    gradients (the one arriving over the residual connection and the one through the norm) and adds them inside the
+    rmsnorm backward kernel (`al_rmsnorm_backward_ex`) — autograd would otherwise run a separate elementwise add."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        xc = x.contiguous()
+        d = xc.shape[-1]
+        rows = xc.numel() // d
+        y = torch.empty_like(xc)
+        rstd = torch.empty(rows, dtype=torch.float32, device=xc.device)
+        check(lib().al_rmsnorm_forward(ptr(xc), ptr(weight), ptr(y), ptr(rstd), rows, d, float(eps), stream_ptr()),
+              "al_rmsnorm_forward")
+        ctx.save_for_backward(xc, weight, rstd)
+        return xc.view_as(xc), y
+
+    @staticmethod
+    def backward(ctx, g_x, g_y):
+        xc, weight, rstd = ctx.saved_tensors
+        if g_y is None:
+            return g_x, None, None
+        d = xc.shape[-1]
+        dyc = g_y.contiguous()
+        add = g_x.contiguous() if g_x is not None else None
+        dx = torch.empty_like(xc)
+        check(lib().al_rmsnorm_backward_ex(ptr(xc), ptr(weight), ptr(rstd), ptr(dyc), ptr(add), ptr(dx), xc.numel() // d, d,
+                                           stream_ptr()), "al_rmsnorm_backward_ex")
+        return dx, None, None
+
+
+def residual_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float):
+    return _ResidualRMSNormFn.apply(x, weight, eps)
 
 
 # ----------------------------------------------------------------------------- SwiGLU
@@ -145,6 +181,42 @@ class _FrozenLinearFn(torch.autograd.Function):
 
 def frozen_linear(x, weight, bias=None):
     return _FrozenLinearFn.apply(x, weight, bias)
+
+
+class _FrozenLinearAddFn(torch.autograd.Function):
+    """y = addend + x W^T (+ b), W frozen, the add in the GEMM epilogue (`al_linear_add_bf16`): o_proj and the residual
+    connection around the attention block. d addend = dy (the same tensor, no copy)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, addend):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        out_dim, in_dim = weight.shape
+        b = bias.detach().float().contiguous() if bias is not None else None
+        a2 = addend.reshape(-1, out_dim).contiguous()
+        y = torch.empty(x2.shape[0], out_dim, dtype=torch.bfloat16, device=x.device)
+        check(lib().al_linear_add_bf16(ptr(x2), x2.shape[0], in_dim, out_dim, ptr(weight), ptr(b), ptr(a2), ptr(y), stream_ptr()),
+              "al_linear_add_bf16")
+        ctx.save_for_backward(weight)
+        ctx.in_shape = x.shape
+        return y.reshape(*x.shape[:-1], out_dim)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (weight,) = ctx.saved_tensors
+        out_dim, in_dim = weight.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dy2 = dy.reshape(-1, out_dim).contiguous()
+            wt = _weight_t(weight)                  # [in, out]
+            dx = torch.empty(dy2.shape[0], in_dim, dtype=torch.bfloat16, device=dy.device)
+            check(lib().al_gemm_bf16(ptr(dy2), out_dim, dy2.numel(), dy2.shape[0], 1, ptr(wt), in_dim, out_dim, None, ptr(dx),
+                                     in_dim, dx.numel(), 0, None, 0, None, stream_ptr()), "al_gemm_bf16")
+            dx = dx.reshape(ctx.in_shape)
+        return dx, None, None, (dy if ctx.needs_input_grad[3] else None)
+
+
+def frozen_linear_add(x, weight, bias, addend):
+    return _FrozenLinearAddFn.apply(x, weight, bias, addend)
 
 
 # ----------------------------------------------------------------------------- rotary embedding
@@ -347,12 +419,64 @@ def _attention_forward(m, hidden_states, position_embeddings=None, attention_mas
     return m.o_proj(out.reshape(B, S, -1)), None
 
 
+def _layer_forward(layer, hidden_states, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
+                   position_embeddings=None, _orig=None, **kwargs):
+    """LlamaDecoderLayer.forward with nothing left to elementwise kernels or to autograd's gradient accumulation:
+      x, h   = residual_rmsnorm(x)                      backward: d x(residual) + rmsnorm' in one kernel
+      q,k,v  = fused_lora_multi(h)                      backward: dh summed in the dgrad GEMMs' epilogues
+      x      = x + o_proj(attention(rope(q), rope(k), v))    the add in o_proj's epilogue
+      x, h   = residual_rmsnorm(x);  g, u = fused_lora_multi(h)
+      x      = x + down_proj(swiglu(g, u))              the add in down_proj's (fused LoRA) epilogue
+    Taken when the native attention is planned for this forward and q/k/v/gate/up/down carry LoRA layers while o_proj
+    does not (the reference's default target list); everything else goes through HF's forward over the patched
+    sub-modules (same arithmetic, separate add kernels)."""
+    st = _ATTN_STATE
+    lo = getattr(layer, "_al_lora", None)
+    attn, mlp = layer.self_attn, layer.mlp
+    if not (st["active"] and lo is not None and past_key_values is None and _ok(hidden_states)
+            and position_embeddings is not None and attn.head_dim == 128 and mlp.config.hidden_act == "silu"
+            and attn.q_proj.weight.dtype == torch.bfloat16 and hidden_states.shape[-1] % 8 == 0):
+        return _orig(layer, hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+                     past_key_values=past_key_values, use_cache=use_cache, position_embeddings=position_embeddings, **kwargs)
+    from .models.lora import fused_lora_forward_add, fused_lora_multi
+    hd = attn.head_dim
+    B, S, _ = hidden_states.shape
+    x, h = residual_rmsnorm(hidden_states, layer.input_layernorm.weight, layer.input_layernorm.variance_epsilon)
+    q, k, v = fused_lora_multi(h, [(attn.q_proj, lo["q_proj"]), (attn.k_proj, lo["k_proj"]), (attn.v_proj, lo["v_proj"])])
+    cos, sin = position_embeddings
+    cc, ss = cos.contiguous(), sin.contiguous()
+    q = _RoPEFn.apply(q.view(B, S, -1, hd), cc, ss)
+    k = _RoPEFn.apply(k.view(B, S, -1, hd), cc, ss)
+    a = gqa_attention(q, k, v.view(B, S, -1, hd), st["kv_len"], attn.scaling)
+    x = frozen_linear_add(a.reshape(B, S, -1), attn.o_proj.weight, attn.o_proj.bias, x)
+    x, h = residual_rmsnorm(x, layer.post_attention_layernorm.weight, layer.post_attention_layernorm.variance_epsilon)
+    g, u = fused_lora_multi(h, [(mlp.gate_proj, lo["gate_proj"]), (mlp.up_proj, lo["up_proj"])])
+    return fused_lora_forward_add(mlp.down_proj, lo["down_proj"], swiglu(g, u), x)
+
+
+def _layer_lora_table(audio_llm, llama, layer):
+    """{projection: LoRALayer} of one decoder layer when it has the reference's default LoRA layout, else None."""
+    names = {id(m): n for n, m in llama.named_modules()}
+    lora = getattr(audio_llm, "lora_layers", None) or {}
+    table = {}
+    for proj, mod in (("q_proj", layer.self_attn.q_proj), ("k_proj", layer.self_attn.k_proj), ("v_proj", layer.self_attn.v_proj),
+                      ("gate_proj", layer.mlp.gate_proj), ("up_proj", layer.mlp.up_proj), ("down_proj", layer.mlp.down_proj)):
+        ll = lora.get(names.get(id(mod)))
+        if ll is None or mod.weight.requires_grad or mod.weight.shape[0] % 8 or mod.weight.shape[1] % 8:
+            return None
+        table[proj] = ll
+    o = layer.self_attn.o_proj
+    if names.get(id(o)) in lora or o.weight.requires_grad or o.weight.shape[0] % 8:
+        return None
+    return table
+
+
 # ----------------------------------------------------------------------------- wiring
 _ORIG = {}
 
 
 def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_only=True, frozen_linears=True,
-           attention=True):
+           attention=True, fused_layers=True):
     """Patch the HF LLaMA inside `audio_llm` (an audio_llama_b200.models.allm.AudioLLM) to the native ops."""
     from transformers.models.llama import modeling_llama as ML
     llama = audio_llm.llama.model
@@ -387,6 +511,17 @@ def enable(audio_llm, rmsnorm_=True, mlp=True, rope=True, fused_ce=True, causal_
                     return m.down_proj(swiglu(m.gate_proj(x), m.up_proj(x)))
                 return _orig(m, x)
             mod.forward = types.MethodType(mlp_fwd, mod)
+    if fused_layers and attention and rmsnorm_ and mlp and frozen_linears and getattr(audio_llm, "fused_lora", False) \
+            and os.environ.get("AUDIOLLM_B200_FUSED_LAYERS", "1") != "0":
+        for mod in llama.modules():
+            if isinstance(mod, ML.LlamaDecoderLayer):
+                mod._al_lora = _layer_lora_table(audio_llm, llama, mod)
+
+                def layer_fwd(m, hidden_states, attention_mask=None, position_ids=None, past_key_values=None, use_cache=False,
+                              position_embeddings=None, _orig=type(mod).forward, **kw):
+                    return _layer_forward(m, hidden_states, attention_mask, position_ids, past_key_values, use_cache,
+                                          position_embeddings, _orig=_orig, **kw)
+                mod.forward = types.MethodType(layer_fwd, mod)
     if rope and "rope" not in _ORIG:
         _ORIG["rope"] = ML.apply_rotary_pos_emb
         ML.apply_rotary_pos_emb = apply_rotary_pos_emb

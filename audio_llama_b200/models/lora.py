@@ -103,3 +103,91 @@ def fused_lora_forward(module: nn.Linear, lora_layer: LoRALayer, x: torch.Tensor
     """Replacement for `module(x)` + lora_forward_hook when x / W are bf16 CUDA tensors."""
     return _FusedLoRALinearFn.apply(x, module.weight, module.bias, lora_layer.lora_A, lora_layer.lora_B,
                                     lora_layer.scaling)
+
+
+class _FusedLoRALinearAddFn(torch.autograd.Function):
+    """y = addend + x W^T + b + s (x A^T) B^T: _FusedLoRALinearFn with the residual connection folded into the GEMM
+    epilogue (`al_lora_linear_forward_ex`). The addend's gradient is dy itself."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, lora_A, lora_B, scaling, addend):
+        from .. import ops
+        y, (a_pad, b_pad, t) = ops.lora_linear(x.contiguous(), weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype,
+                                              return_saved=True, packed=_packed_operands(lora_A, lora_B, scaling),
+                                              addend=addend)
+        ctx.save_for_backward(x, weight, a_pad, b_pad, t)
+        ctx.scaling = scaling
+        ctx.rank = lora_A.shape[0]
+        ctx.dtypes = (lora_A.dtype, lora_B.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from .. import ops
+        x, weight, a_pad, b_pad, t = ctx.saved_tensors
+        need_dx = ctx.needs_input_grad[0]
+        dyb = dy.to(torch.bfloat16)
+        dx, dA, dB_raw = ops.lora_linear_backward(x.contiguous(), dyb, _frozen_weight_t(weight) if need_dx else None,
+                                                  a_pad, b_pad, t, ctx.rank, need_dx=need_dx)
+        return dx, None, None, dA.to(ctx.dtypes[0]), (dB_raw * ctx.scaling).to(ctx.dtypes[1]), None, \
+            (dy if ctx.needs_input_grad[6] else None)
+
+
+def fused_lora_forward_add(module: nn.Linear, lora_layer: LoRALayer, x: torch.Tensor, addend: torch.Tensor) -> torch.Tensor:
+    """addend + module(x) + lora(x) in one GEMM (down_proj and the residual connection around the MLP)."""
+    return _FusedLoRALinearAddFn.apply(x, module.weight, module.bias, lora_layer.lora_A, lora_layer.lora_B,
+                                       lora_layer.scaling, addend)
+
+
+class _FusedLoRAMultiFn(torch.autograd.Function):
+    """Several LoRA-carrying projections of ONE input (q / k / v, gate / up): forward = one fused GEMM each; backward sums
+    their input gradients inside the GEMM epilogues (dx = dy_0 W_0 + ...; the next product adds into the same buffer,
+    `al_lora_linear_backward_ex`) instead of leaving the sum to autograd's elementwise adds.
+    Arguments: x, then (weight, bias, lora_A, lora_B, scaling) per projection."""
+
+    @staticmethod
+    def forward(ctx, x, *args):
+        from .. import ops
+        n = len(args) // 5
+        xc = x.contiguous()
+        outs, saved, meta = [], [xc], []
+        for i in range(n):
+            weight, bias, lora_A, lora_B, scaling = args[5 * i:5 * i + 5]
+            y, (a_pad, b_pad, t) = ops.lora_linear(xc, weight, bias, lora_A, lora_B, scaling, out_dtype=x.dtype,
+                                                  return_saved=True, packed=_packed_operands(lora_A, lora_B, scaling))
+            outs.append(y)
+            saved += [weight, a_pad, b_pad, t]
+            meta.append((scaling, lora_A.shape[0], lora_A.dtype, lora_B.dtype))
+        ctx.save_for_backward(*saved)
+        ctx.meta = meta
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        from .. import ops
+        saved = ctx.saved_tensors
+        x = saved[0]
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        grads = []
+        for i, dy in enumerate(dys):
+            weight, a_pad, b_pad, t = saved[1 + 4 * i:5 + 4 * i]
+            scaling, rank, dt_a, dt_b = ctx.meta[i]
+            if dy is None:
+                grads += [None, None, None, None, None]
+                continue
+            dxi, dA, dB_raw = ops.lora_linear_backward(x, dy.to(torch.bfloat16), _frozen_weight_t(weight) if need_dx else None,
+                                                       a_pad, b_pad, t, rank, need_dx=need_dx, dx_accumulate=dx)
+            if need_dx:
+                dx = dxi
+            grads += [None, None, dA.to(dt_a), (dB_raw * scaling).to(dt_b), None]
+        return (dx, *grads)
+
+
+def fused_lora_multi(x: torch.Tensor, pairs):
+    """pairs: [(nn.Linear, LoRALayer), ...] sharing the input x -> tuple of outputs."""
+    args = []
+    for module, lora_layer in pairs:
+        args += [module.weight, module.bias, lora_layer.lora_A, lora_layer.lora_B, lora_layer.scaling]
+    return _FusedLoRAMultiFn.apply(x, *args)
+

@@ -260,11 +260,12 @@ def pack_lora(lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float):
 
 def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], lora_a: torch.Tensor,
                 lora_b: torch.Tensor, scaling: float, out_dtype=torch.bfloat16, return_saved: bool = False,
-                packed=None):
+                packed=None, addend: Optional[torch.Tensor] = None):
     """Frozen linear + LoRA (L1): x [..., in] bf16, w [out, in] bf16, lora_a [r, in], lora_b [out, r] (any float dtype).
     out = x w^T + bias + scaling * (x a^T) b^T with the rank-r product accumulated inside the frozen GEMM.
     `packed` = pack_lora(lora_a, lora_b, scaling) when the caller keeps it across calls (the parameters only change at
-    optimizer steps); return_saved=True also returns (a_pad, b_scaled_pad, t) for lora_linear_backward."""
+    optimizer steps); return_saved=True also returns (a_pad, b_scaled_pad, t) for lora_linear_backward. `addend`
+    (bf16, the output's shape) is added in the GEMM epilogue (the residual connection around down_proj)."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
     out_dim, in_dim = w.shape
@@ -276,19 +277,26 @@ def lora_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     out = torch.empty(*x.shape[:-1], out_dim, dtype=out_dtype, device=x.device)
     if bias is not None:
         bias = _req(bias.detach().float().contiguous(), torch.float32, "bias")
-    check(lib().al_lora_linear_forward(ptr(x2), rows, in_dim, out_dim, r_pad, ptr(w), ptr(bias), ptr(a), ptr(b),
-                                       ptr(t_ws), ptr(out), 1 if out_dtype == torch.float32 else 0, stream_ptr()),
-          "al_lora_linear_forward")
+    if addend is not None:
+        if out_dtype != torch.bfloat16 or addend.shape != out.shape:
+            raise ValueError("lora_linear: an addend needs a bf16 output of the same shape")
+        addend = _req(addend.contiguous(), torch.bfloat16, "addend")
+    check(lib().al_lora_linear_forward_ex(ptr(x2), rows, in_dim, out_dim, r_pad, ptr(w), ptr(bias), ptr(a), ptr(b),
+                                          ptr(t_ws), ptr(addend), ptr(out), 1 if out_dtype == torch.float32 else 0,
+                                          stream_ptr()), "al_lora_linear_forward")
     if return_saved:
         return out, (a, b, t_ws)
     return out
 
 
 def lora_linear_backward(x: torch.Tensor, dy: torch.Tensor, w_t: Optional[torch.Tensor], a_pad: torch.Tensor,
-                         b_scaled_pad: torch.Tensor, t_saved: torch.Tensor, rank: int, need_dx: bool = True):
+                         b_scaled_pad: torch.Tensor, t_saved: torch.Tensor, rank: int, need_dx: bool = True,
+                         dx_accumulate: Optional[torch.Tensor] = None):
     """Backward of lora_linear with the weight frozen. x [..., in], dy [..., out] bf16; w_t = w.t().contiguous()
     ([in, out] bf16, needed only for dx). Returns (dx or None, dA [rank, in] f32, dB_raw [out, rank] f32) where the
-    gradient of the unscaled lora_B is scaling * dB_raw (dA already carries the scaling)."""
+    gradient of the unscaled lora_B is scaling * dB_raw (dA already carries the scaling). `dx_accumulate` (bf16,
+    x's shape, contiguous): dx is added INTO it in the GEMM epilogue and it is returned as dx (several projections of one
+    input: their input gradients sum without separate add passes)."""
     _req(x, torch.bfloat16, "x")
     dy = _req(dy.contiguous(), torch.bfloat16, "dy")
     r_pad, in_dim = a_pad.shape
@@ -300,14 +308,21 @@ def lora_linear_backward(x: torch.Tensor, dy: torch.Tensor, w_t: Optional[torch.
     ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
     off = (-ws.data_ptr()) % 1024
     ws = ws[off:off + nbytes]
-    dx = torch.empty_like(x2) if need_dx else None
+    dx = None
     if need_dx:
         _req(w_t, torch.bfloat16, "w_t")
+        if dx_accumulate is not None:
+            if not dx_accumulate.is_contiguous() or dx_accumulate.numel() != x2.numel():
+                raise ValueError("lora_linear_backward: dx_accumulate must be contiguous with x's element count")
+            dx = _req(dx_accumulate, torch.bfloat16, "dx_accumulate").view(rows, in_dim)
+        else:
+            dx = torch.empty_like(x2)
     dA = torch.empty(r_pad, in_dim, dtype=torch.float32, device=x.device)
     dB = torch.empty(out_dim, r_pad, dtype=torch.float32, device=x.device)
-    check(lib().al_lora_linear_backward(ptr(x2), ptr(dy2), rows, in_dim, out_dim, r_pad, ptr(w_t) if need_dx else None,
-                                        ptr(a_pad), ptr(b_scaled_pad), ptr(t_saved), ptr(ws), ptr(dx), ptr(dA), ptr(dB),
-                                        stream_ptr()), "al_lora_linear_backward")
+    check(lib().al_lora_linear_backward_ex(ptr(x2), ptr(dy2), rows, in_dim, out_dim, r_pad, ptr(w_t) if need_dx else None,
+                                           ptr(a_pad), ptr(b_scaled_pad), ptr(t_saved), ptr(ws),
+                                           ptr(dx) if (need_dx and dx_accumulate is not None) else None, ptr(dx), ptr(dA),
+                                           ptr(dB), stream_ptr()), "al_lora_linear_backward")
     return (dx.view_as(x) if need_dx else None), dA[:rank], dB[:, :rank]
 
 

@@ -200,6 +200,20 @@ int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int
  * gradient of the UNSCALED lora_B is scaling * dB_raw, and dA already carries the scaling through U.
  * W_T is the frozen weight transposed, [in][out] bf16 (transposed once by the caller, it never changes). */
 size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim, int rank);
+/* The _ex forms fold an elementwise add into the GEMM epilogue (what HF's LlamaDecoderLayer.forward writes as
+ * `residual + hidden_states`, and what autograd does when several projections share one input):
+ *   al_lora_linear_forward_ex   out = x W^T + b + (x A^T)(sB)^T + addend      addend [rows][out_dim] bf16 or NULL
+ *   al_lora_linear_backward_ex  dx  = dy W + U A + dx_addend                  dx_addend [rows][in_dim] bf16 or NULL
+ *   al_linear_add_bf16          out = x W^T + b + addend                      (a frozen linear without LoRA: o_proj)
+ * The addend may be the output buffer itself (accumulate in place). */
+int al_lora_linear_forward_ex(const void* x, int rows, int in_dim, int out_dim, int rank, const void* W,
+                              const float* bias, const void* lora_A, const void* lora_B_scaled, void* t_ws,
+                              const void* addend, void* out, int out_dtype, al_stream_t stream);
+int al_lora_linear_backward_ex(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
+                               const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace,
+                               const void* dx_addend, void* dx, float* dA, float* dB_raw, al_stream_t stream);
+int al_linear_add_bf16(const void* x, int rows, int in_dim, int out_dim, const void* W, const float* bias,
+                       const void* addend, void* out, al_stream_t stream);
 int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim, int out_dim, int rank, const void* W_T,
                             const void* lora_A, const void* lora_B_scaled, const void* t_saved, void* workspace,
                             void* dx, float* dA, float* dB_raw, al_stream_t stream);
@@ -220,6 +234,10 @@ int al_lora_linear_backward(const void* x, const void* dy, int rows, int in_dim,
 int al_rmsnorm_forward(const void* x, const void* weight, void* y, float* rstd, int rows, int d, float eps, al_stream_t stream);
 int al_rmsnorm_backward(const void* x, const void* weight, const float* rstd, const void* dy, void* dx, int rows, int d,
                         al_stream_t stream);
+/* dx = rmsnorm backward + dx_addend (bf16 [rows][d] or NULL; may be dx itself): the gradient arriving over the residual
+ * connection joins in the same pass. */
+int al_rmsnorm_backward_ex(const void* x, const void* weight, const float* rstd, const void* dy, const void* dx_addend,
+                           void* dx, int rows, int d, al_stream_t stream);
 int al_swiglu_forward(const void* gate, const void* up, void* h, long long n, al_stream_t stream);
 int al_swiglu_backward(const void* gate, const void* up, const void* dh, void* dgate, void* dup, long long n, al_stream_t stream);
 int al_rope(const void* x, const void* cos, const void* sin, void* out, int B, int S, int H, int head_dim, int cos_batch,

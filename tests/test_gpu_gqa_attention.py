@@ -92,7 +92,7 @@ def test_native_attention_inside_audio_llm_matches_hf_with_padding():
     mask[0, 150:] = 0                                        # right padding; its labels stay token ids
     mask[1, :] = 1
 
-    def run(attention, m=mask):
+    def run(attention, m=mask, fused_layers=True):
         with patch.object(Bm, "load_base_models", fake), patch.dict(os.environ, {"AUDIOLLM_B200_NATIVE": "0"}):
             mdl = AudioLLM("x", "y", lora_rank=8).to("cuda")
         g = torch.Generator().manual_seed(3)
@@ -101,8 +101,10 @@ def test_native_attention_inside_audio_llm_matches_hf_with_padding():
                 l.lora_A.copy_(torch.randn(l.lora_A.shape, generator=g) * 0.05)
                 l.lora_B.copy_(torch.randn(l.lora_B.shape, generator=g) * 0.05)
         mdl.enable_fused_lora()
-        mdl.enable_native_llama_ops(attention=attention)
+        mdl.enable_native_llama_ops(attention=attention, fused_layers=fused_layers)
         assert mdl.native_attention == attention
+        # the fused decoder-layer forward (adds in the GEMM / rmsnorm-backward epilogues) is armed with the native attention
+        assert (getattr(mdl.llama.model.model.layers[0], "_al_lora", None) is not None) == (attention and fused_layers)
         out = mdl(input_ids=ids, attention_mask=m, labels=labels)
         out.loss.backward()
         l0 = mdl.lora_layers["model.layers.0.self_attn.q_proj"]
@@ -113,6 +115,10 @@ def test_native_attention_inside_audio_llm_matches_hf_with_padding():
         a, b = run(False), run(True)
         assert abs(a[0] - b[0]) <= 2e-2 * abs(a[0]), (a[0], b[0])
         assert rel(b[1], a[1]) <= 8e-2 and rel(b[2], a[2]) <= 8e-2, (rel(b[1], a[1]), rel(b[2], a[2]))
+        # same kernels with autograd's own adds instead of the epilogue adds: only the rounding points differ
+        u = run(True, fused_layers=False)
+        assert abs(u[0] - b[0]) <= 5e-3 * abs(u[0]), (u[0], b[0])
+        assert rel(b[1], u[1]) <= 3e-2 and rel(b[2], u[2]) <= 3e-2, (rel(b[1], u[1]), rel(b[2], u[2]))
         left = mask.clone()
         left[0] = 0
         left[0, 50:] = 1                                     # left padding: not a kv_len mask -> stock path, still finite

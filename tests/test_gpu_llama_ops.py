@@ -46,6 +46,40 @@ def test_rmsnorm(rows, d):
     assert rel(xn.grad, xr.grad) <= 1e-2
 
 
+def test_residual_rmsnorm_and_linear_add():
+    """The fused decoder layer's pieces: residual_rmsnorm returns (x, rmsnorm(x)) and its backward adds the gradient of
+    the pass-through output inside the rmsnorm backward kernel; frozen_linear_add folds the residual add into the GEMM."""
+    g = torch.Generator().manual_seed(11)
+    rows, d, out_dim = 517, 3072, 1024
+    x = torch.randn(rows, d, generator=g).bfloat16().cuda().requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).bfloat16().cuda()
+    gx = torch.randn(rows, d, generator=g).bfloat16().cuda()
+    gy = torch.randn(rows, d, generator=g).bfloat16().cuda()
+    xa, y = LN.residual_rmsnorm(x, w, 1e-5)
+    assert torch.equal(xa, x.detach()) and torch.equal(y, LN.rmsnorm(x.detach(), w, 1e-5))
+    torch.autograd.backward([xa, y], [gx, gy])
+    x2 = x.detach().clone().requires_grad_(True)
+    LN.rmsnorm(x2, w, 1e-5).backward(gy)
+    ref = x2.grad.float() + gx.float()
+    assert (x.grad.float() - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
+    # pass-through only / norm only
+    x3 = x.detach().clone().requires_grad_(True)
+    xa3, _ = LN.residual_rmsnorm(x3, w, 1e-5)
+    xa3.backward(gx)
+    assert torch.equal(x3.grad, gx)
+    # o_proj + residual
+    W = (torch.randn(out_dim, d, generator=g) * 0.02).bfloat16().cuda()
+    r = torch.randn(rows, out_dim, generator=g).bfloat16().cuda().requires_grad_(True)
+    a = torch.randn(rows, d, generator=g).bfloat16().cuda().requires_grad_(True)
+    dy = torch.randn(rows, out_dim, generator=g).bfloat16().cuda()
+    out = LN.frozen_linear_add(a, W, None, r)
+    ref = (a.detach().float() @ W.float().t()) + r.detach().float()
+    assert O.rel_l2(out.float().cpu(), ref.cpu()) <= 4e-3
+    out.backward(dy)
+    assert torch.equal(r.grad, dy)
+    assert O.rel_l2(a.grad.float().cpu(), (dy.float() @ W.float()).cpu()) <= 6e-3
+
+
 def test_swiglu():
     g = torch.Generator().manual_seed(1)
     a = (torch.randn(300, 8192, generator=g) * 2).bfloat16().cuda()

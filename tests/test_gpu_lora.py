@@ -115,6 +115,34 @@ def test_lora_linear_backward(in_dim, out_dim, rank, rows):
     assert dx2 is None and O.rel_l2(dA2.cpu(), dA.cpu()) <= 1e-5      # (split-K reduce-add: not bit-reproducible)
 
 
+@pytest.mark.parametrize("in_dim,out_dim,rank,rows", [(3072, 1024, 64, 2014), (256, 512, 8, 77)])
+def test_lora_linear_epilogue_adds(in_dim, out_dim, rank, rows):
+    """The _ex forms: forward with an addend == forward + addend; backward accumulating into an existing dx (in place)
+    == the sum of the separate input gradients. One rounding to bf16 instead of two: compared in fp32 at bf16 tolerance."""
+    g = torch.Generator().manual_seed(in_dim + out_dim)
+    x = torch.randn(rows, in_dim, generator=g).bfloat16().cuda()
+    W = (torch.randn(out_dim, in_dim, generator=g) * 0.02).bfloat16().cuda()
+    A = (torch.randn(rank, in_dim, generator=g) * 0.05).cuda()
+    B = (torch.randn(out_dim, rank, generator=g) * 0.05).cuda()
+    r = torch.randn(rows, out_dim, generator=g).bfloat16().cuda()
+    dy = torch.randn(rows, out_dim, generator=g).bfloat16().cuda()
+    scaling = 16 / rank
+    y0, (a_pad, b_pad, t) = ops.lora_linear(x, W, None, A, B, scaling, return_saved=True)
+    y1 = ops.lora_linear(x, W, None, A, B, scaling, addend=r)
+    ref = y0.float() + r.float()
+    assert (y1.float() - ref).abs().max().item() <= 2 ** -7 * max(1.0, ref.abs().max().item())
+    assert O.rel_l2(y1.float().cpu(), ref.cpu()) <= 4e-3
+    wt = W.t().contiguous()
+    dx_a, dA_a, _ = ops.lora_linear_backward(x, dy, wt, a_pad, b_pad, t, rank)
+    dx_b, _, _ = ops.lora_linear_backward(x, dy * 0.5, wt, a_pad, b_pad, t, rank)
+    acc = dx_a.clone()
+    out, dA_c, _ = ops.lora_linear_backward(x, dy * 0.5, wt, a_pad, b_pad, t, rank, dx_accumulate=acc)
+    assert out.data_ptr() == acc.data_ptr()                 # accumulated in place
+    ref = dx_a.float() + dx_b.float()
+    assert O.rel_l2(out.float().cpu(), ref.cpu()) <= 6e-3
+    assert O.rel_l2(dA_c.cpu(), 0.5 * dA_a.cpu()) <= 1e-2
+
+
 def test_fused_and_native_paths_are_the_default_for_bf16_cuda():
     """AudioLLM.to("cuda") with bf16 LLaMA weights switches to the fused frozen+LoRA GEMMs and the native row kernels
     by itself; fp32 weights keep the reference-style hooks. Loss of the default path == loss of the hook path."""

@@ -84,7 +84,8 @@ if os.environ.get("CYCLES"):                       # a -DGQ_CYCLES build (AUDIOL
     v = list(buf)
     names = {0: "fwd issuer [total wait_P]", 8: "fwd compute [total wait_S max bar exp wait_O store]", 16: "dq issuer [total issue_SdP wait_dS]",
              24: "dq compute [total wait_SdP math wait_dQ store]", 32: "dkv issuer [total wait_PT wait_dST]",
-             40: "dkv compute [total bar wait_ST P wait_dPT dS]"}
+             40: "dkv compute [total bar wait_ST P wait_dPT dS]",
+             48: "fwd per CTA [entry->loop, loop, entry->stores done, entry->exit]"}
     for base, nm in names.items():
         if v[base]:
             print(f"  {nm}: n={v[base]}  per-unit cycles: " + " ".join(f"{x / v[base]:.0f}" for x in v[base + 1:base + 8]))
