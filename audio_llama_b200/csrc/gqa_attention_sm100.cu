@@ -20,6 +20,7 @@
 //                       P^T / dS^T overwrite the first 64 columns of S^T / dP^T (the next tile's S^T is issued after the
 //                       products that read them: tensor-core operations of one thread execute in issue order).
 // D = rowsum(dO * O) comes from gqa_rowdot_kernel. Scores are recomputed in the backward (nothing but O and lse is saved).
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -143,22 +144,43 @@ constexpr uint32_t GF_Q_FULL = GF_OFF_BARS, GF_K_FULL = GF_Q_FULL + 8, GF_K_EMPT
                    GF_O_FULL = GF_P_FULL + 8, GF_TMEM_PTR = GF_O_FULL + 8;
 constexpr int GF_SMEM = GF_TMEM_PTR + 16 + 1024;
 
+// Work items = (query tile, query head, batch), heaviest (largest query tile: most kv tiles under the causal mask) first.
+// The kernels are PERSISTENT: one CTA per SM walks the item list in a serpentine order (round r gives CTA c item
+// r G + c, the next round r G + (G - 1 - c)), which on a descending list is within ~1 % of a dynamic longest-first
+// schedule, and the TMEM allocation, barrier set-up, launch latency and pipeline fill are paid once per SM instead of
+// once per item (measured before: ~10 000 of ~27 000 cycles per item went to those, with nothing to overlap them).
+struct GqItem {
+  int qt, hq, b;
+};
+__device__ __forceinline__ bool gq_item(int round, int nq, int Hq, int B, GqItem& it) {
+  const int G = static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
+  const int idx = round * G + ((round & 1) ? (G - 1 - c) : c);
+  const int per = Hq * B;
+  if (idx >= nq * per) return false;
+  it.qt = nq - 1 - idx / per;
+  const int rem = idx % per;
+  it.b = rem / Hq;
+  it.hq = rem % Hq;
+  return true;
+}
+__device__ __forceinline__ int gq_rounds(int nq, int Hq, int B) {
+  return (nq * Hq * B + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+}
+
 __global__ void __launch_bounds__(GQ_THREADS, 1)
 gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
-               const int* __restrict__ kv_len, int S, int Hq, int Hkv, float scale_log2) {
+               const int* __restrict__ kv_len, int B, int S, int Hq, int Hkv, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heavy tiles first, over the WHOLE grid (blockIdx.z is the slowest index of the launch order): query tile qt visits
-  // qt + 1 kv tiles (causal), so the heaviest work items start first and the tail of the grid is made of the light ones
-  const int qt = gridDim.z - 1 - blockIdx.z, hq = blockIdx.x, b = blockIdx.y;
-  const int hkv = hq / (Hq / Hkv);
-  const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
-  const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
-#ifdef GQ_CYCLES
-  const long long t_entry = GQC_NOW();
-#endif
+  const int nq = (S + GQ_T - 1) / GQ_T;
+  const int rounds = gq_rounds(nq, Hq, B);
+  const int G_heads = Hq / Hkv;
+  auto tiles_of = [&](const GqItem& it) {
+    const int kvl = max(1, min(S, kv_len ? kv_len[it.b] : S));
+    return min(it.qt + 1, (kvl + GQ_T - 1) / GQ_T);
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmK);
@@ -186,26 +208,33 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GF_TMEM_PTR) : "memory");
   // TMEM columns: S0 0..127 | S1 128..255 | O 256..383 | P 384..447 (bf16 pairs) | Q 448..511 (bf16 pairs: the A operand of
-  // every S = Q K_j^T of this CTA, so those products read only K from shared memory)
+  // every S = Q K_j^T of an item, so those products read only K from shared memory)
+  // Every ring / hand-off below is indexed by g, the number of (item, kv tile) steps this CTA has taken so far: stages
+  // and mbarrier phases run on across item boundaries.
 
   if (warp == 0) {
-    if (elect_one()) {                                     // ---------------- TMA producer
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait_a(sb + GF_K_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
-        gq_load_tile(sb + GF_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GF_K_FULL + 8 * s, hkv, j * GQ_T, b);
-        if (j >= 2) mbar_wait_a(sb + GF_V_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
-        gq_load_tile(sb + GF_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GF_V_FULL + 8 * s, hkv, j * GQ_T, b);
+    if (elect_one()) {                                     // ---------------- TMA producer (runs ahead into the next item)
+      int g = 0;
+      for (int r = 0; r < rounds; ++r) {
+        GqItem it;
+        if (!gq_item(r, nq, Hq, B, it)) continue;
+        const int n_tiles = tiles_of(it), hkv = it.hq / G_heads;
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int s = g & 1;
+          if (g >= 2) mbar_wait_a(sb + GF_K_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
+          gq_load_tile(sb + GF_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GF_K_FULL + 8 * s, hkv, j * GQ_T, it.b);
+          if (g >= 2) mbar_wait_a(sb + GF_V_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
+          gq_load_tile(sb + GF_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GF_V_FULL + 8 * s, hkv, j * GQ_T, it.b);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer: S_j one tile ahead of P V_{j-1}
-    mbar_wait_a(sb + GF_Q_FULL, 0);
     const uint32_t k_lo = gq_desc_kmajor(sb + GF_OFF_K), v_lo = gq_desc_mnmajor(sb + GF_OFF_V);
-    auto issue_qk = [&](int j) {
-      const int s = j & 1;
-      mbar_wait_a(sb + GF_K_FULL + 8 * s, (j >> 1) & 1);
-      if (j >= 2) mbar_wait_a(sb + GF_S_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
+    auto issue_qk = [&](int g) {
+      const int s = g & 1;
+      mbar_wait_a(sb + GF_K_FULL + 8 * s, (g >> 1) & 1);
+      if (g >= 2) mbar_wait_a(sb + GF_S_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         gq_mma_tk(tmem_base + s * 128, tmem_base + 448, k_lo + s * (GQ_TILE_BYTES >> 4));
@@ -214,238 +243,220 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
       }
       __syncwarp();
     };
-    issue_qk(0);
-#ifdef GQ_CYCLES
-    long long w_p = 0, t_begin = GQC_NOW(), t0;
-#endif
-    for (int j = 0; j < n_tiles; ++j) {
-      if (j + 1 < n_tiles) issue_qk(j + 1);
-      const int s = j & 1;
-      mbar_wait_a(sb + GF_V_FULL + 8 * s, (j >> 1) & 1);
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GF_P_FULL, j & 1);
-#ifdef GQ_CYCLES
-      w_p += GQC_NOW() - t0;
-#endif
-      tc_fence_after();
-      if (elect_one()) {
-        gq_mma_tm<8, 0>(tmem_base + 256, tmem_base + 384, v_lo + s * (GQ_TILE_BYTES >> 4), j != 0);
-        umma_commit_a(sb + GF_V_EMPTY + 8 * s);
-        umma_commit_a(sb + GF_O_FULL);
+    int g = 0, n_item = 0;
+    for (int r = 0; r < rounds; ++r) {
+      GqItem it;
+      if (!gq_item(r, nq, Hq, B, it)) continue;
+      const int n_tiles = tiles_of(it);
+      mbar_wait_a(sb + GF_Q_FULL, n_item & 1);             // this item's Q rows are in TMEM
+      ++n_item;
+      issue_qk(g);
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        if (j + 1 < n_tiles) issue_qk(g + 1);
+        const int s = g & 1;
+        mbar_wait_a(sb + GF_V_FULL + 8 * s, (g >> 1) & 1);
+        mbar_wait_a(sb + GF_P_FULL, g & 1);                // (for j = 0 this also says: the previous item's O has been read)
+        tc_fence_after();
+        if (elect_one()) {
+          gq_mma_tm<8, 0>(tmem_base + 256, tmem_base + 384, v_lo + s * (GQ_TILE_BYTES >> 4), j != 0);
+          umma_commit_a(sb + GF_V_EMPTY + 8 * s);
+          umma_commit_a(sb + GF_O_FULL);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-#ifdef GQ_CYCLES
-    if (lane == 0) {
-      GQC_ADD(0, n_tiles);
-      GQC_ADD(1, GQC_NOW() - t_begin);
-      GQC_ADD(2, w_p);
-    }
-#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax: GQ_SPLIT threads per query row
     const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
-    const int q_glob = qt * GQ_T + static_cast<int>(row);
     constexpr uint32_t EX_STRIDE = GQ_T * 4, EX_SET = GQ_SPLIT * GQ_T * 4;   // one part's slots | one parity's set
     const uint32_t ex_row = sb + GF_OFF_EXCH + row * 4;
-    {   // this thread's GQ_CW columns of the Q row -> TMEM (bf16 pairs are already the A-operand layout)
-      const bool live = q_glob < S;
-      const uint4* src = reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(b) * S + (live ? q_glob : 0)) * Hq + hq) * GQ_T +
+    // this thread's GQ_CW columns of an item's Q row (bf16 pairs are already the A-operand layout of the TS product)
+    auto load_q = [&](const GqItem& it, uint32_t (&r)[GQ_CW / 2]) {
+      const int qg = it.qt * GQ_T + static_cast<int>(row);
+      const bool live = qg < S;
+      const uint4* src = reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(it.b) * S + (live ? qg : 0)) * Hq + it.hq) * GQ_T +
                                                         part * GQ_CW);
 #pragma unroll
-      for (int c = 0; c < GQ_CW / 32; ++c) {
-        uint32_t r[16];
+      for (int u = 0; u < GQ_CW / 8; ++u) {
+        const uint4 v = live ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
+        r[4 * u] = v.x;
+        r[4 * u + 1] = v.y;
+        r[4 * u + 2] = v.z;
+        r[4 * u + 3] = v.w;
+      }
+    };
+    auto store_q = [&](const uint32_t (&r)[GQ_CW / 2]) {    // (only after the last S of the previous item has been produced)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint4 v = live ? __ldg(src + 4 * c + u) : make_uint4(0, 0, 0, 0);
-          r[4 * u] = v.x;
-          r[4 * u + 1] = v.y;
-          r[4 * u + 2] = v.z;
-          r[4 * u + 3] = v.w;
-        }
-        tmem_st_32x16(tlane + 448 + part * (GQ_CW / 2) + 16 * c, r);
+      for (int c = 0; c < GQ_CW / 32; ++c) {
+        const uint32_t(&rc)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&r[16 * c]);
+        tmem_st_32x16(tlane + 448 + part * (GQ_CW / 2) + 16 * c, rc);
       }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GF_Q_FULL);
-    }
-    float m_ref = -INFINITY, l = 0.f;
-#ifdef GQ_CYCLES
-    long long w_s = 0, w_bar = 0, w_o = 0, c_a = 0, c_b = 0, c_c = 0, t_begin = GQC_NOW(), t0, t1;
-#endif
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sbuf = j & 1;
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GF_S_FULL + 8 * sbuf, (j >> 1) & 1);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      w_s += t1 - t0;
-#endif
+    };
+    int g = 0;
+    bool first = true;
+    for (int r = 0; r < rounds; ++r) {
+      GqItem it;
+      if (!gq_item(r, nq, Hq, B, it)) continue;
+      const int qt = it.qt, hq = it.hq, b = it.b;
+      const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
+      const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
+      const int q_glob = qt * GQ_T + static_cast<int>(row);
+      if (first) {                                         // (later items: stored at the end of the previous one)
+        uint32_t qr[GQ_CW / 2];
+        load_q(it, qr);
+        store_q(qr);
+        first = false;
+      }
+      float m_ref = -INFINITY, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        const int sbuf = g & 1;
+        mbar_wait_a(sb + GF_S_FULL + 8 * sbuf, (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t s[GQ_CW];
+#pragma unroll
+        for (int c = 0; c < GQ_CW / 32; ++c) {
+          uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]);
+          tmem_ld_32x32(tlane + sbuf * 128 + part * GQ_CW + 32 * c, sc);
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive_a(sb + GF_S_EMPTY + 8 * sbuf);
+        const int col0 = j * GQ_T + part * GQ_CW;
+        if (j == qt || col0 + GQ_CW > kvl) {               // diagonal tile or the tile holding the padding boundary
+#pragma unroll
+          for (int k = 0; k < GQ_CW; ++k)
+            if (col0 + k > q_glob || col0 + k >= kvl) s[k] = 0xff800000u;
+        }
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+#pragma unroll
+        for (int k = 2; k < GQ_CW; k += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
+          if (k + 2 < GQ_CW) mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
+        }
+        sts_f32(ex_row + sbuf * EX_SET + part * EX_STRIDE, fmaxf(mx0, mx1));
+        named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
+        float tile_max = lds_f32(ex_row + sbuf * EX_SET);
+#pragma unroll
+        for (int qq = 1; qq < GQ_SPLIT; ++qq) tile_max = fmaxf(tile_max, lds_f32(ex_row + sbuf * EX_SET + qq * EX_STRIDE));
+        tile_max *= scale_log2;
+        float alpha = 1.0f;
+        const bool rescale = __any_sync(0xffffffffu, tile_max > m_ref + GQ_TAU);
+        if (rescale && tile_max > m_ref + GQ_TAU) {        // (per row; the TMEM traffic below stays warp-uniform)
+          alpha = ex2f(m_ref - tile_max);                  // 0 on the first tile
+          m_ref = tile_max;
+          l *= alpha;
+        }
+        const unsigned long long c2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_ref, -m_ref);
+        unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);
+        uint32_t pk[GQ_CW / 2];
+#pragma unroll
+        for (int k = 0; k < GQ_CW; k += 2) {
+          const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), c2, nm2);
+          float p0, p1;
+          if (((k >> 1) % GQ_POLY_DEN) < GQ_POLY_NUM) {     // this share of the exponentials on the FMA pipe (the XU is the
+            poly_exp2_pair<false>(x2, p0, p1);              // narrower one: 16 ex2 / cycle / SM against 16384 per tile)
+          } else {
+            float x0, x1;
+            unpk2(x2, x0, x1);
+            p0 = ex2f(x0);
+            p1 = ex2f(x1);
+          }
+          if ((k >> 1) & 1) l2b = fadd2(l2b, pk2(p0, p1));
+          else l2a = fadd2(l2a, pk2(p0, p1));
+          pk[k >> 1] = pack_bf16(p0, p1);
+        }
+        {
+          float a, c, e, f;
+          unpk2(l2a, a, c);
+          unpk2(l2b, e, f);
+          l += (a + c) + (e + f);
+        }
+        if (j > 0) {                                       // the previous P V has read P and finished its part of O
+          mbar_wait_a(sb + GF_O_FULL, (g - 1) & 1);
+          tc_fence_after();
+          if (rescale) {
+#pragma unroll
+            for (int c = 0; c < GQ_CW / 32; ++c) {
+              uint32_t rr[32];
+              tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, rr);
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 32; ++k) rr[k] = __float_as_uint(__uint_as_float(rr[k]) * alpha);
+              tmem_st_32x32(tlane + 256 + part * GQ_CW + c * 32, rr);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < GQ_CW / 32; ++c) {
+          uint32_t(&pc)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16 * c]);
+          tmem_st_32x16(tlane + 384 + part * (GQ_CW / 2) + 16 * c, pc);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_a(sb + GF_P_FULL);
+      }
+      // The next item's Q rows: requested now, stored once this item's sums are exchanged (every S of this item has been
+      // produced, so no product reads the Q columns any more); the issuer then starts the next item's first S under
+      // this item's epilogue.
+      GqItem nx;
+      bool has_next = false;
+      for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
+      uint32_t qn[GQ_CW / 2];
+      if (has_next) load_q(nx, qn);
+      // row sum of all parts, normalise, store O (this part's columns) and the log-sum-exp
+      sts_f32(ex_row + 2 * EX_SET + part * EX_STRIDE, l);
+      named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
+      float l_tot = lds_f32(ex_row + 2 * EX_SET);
+#pragma unroll
+      for (int qq = 1; qq < GQ_SPLIT; ++qq) l_tot += lds_f32(ex_row + 2 * EX_SET + qq * EX_STRIDE);
+      const float inv_l = 1.0f / l_tot;
+      if (has_next) store_q(qn);
+      mbar_wait_a(sb + GF_O_FULL, (g - 1) & 1);
       tc_fence_after();
-      uint32_t s[GQ_CW];
+      if (q_glob < S) {
+        if (part == 0) lse[(static_cast<size_t>(b) * Hq + hq) * S + q_glob] = m_ref + log2f(l_tot);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GQ_CW);
 #pragma unroll
       for (int c = 0; c < GQ_CW / 32; ++c) {
-        uint32_t(&sc)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32 * c]);
-        tmem_ld_32x32(tlane + sbuf * 128 + part * GQ_CW + 32 * c, sc);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_a(sb + GF_S_EMPTY + 8 * sbuf);
-      const int col0 = j * GQ_T + part * GQ_CW;
-      if (j == qt || col0 + GQ_CW > kvl) {                 // diagonal tile or the tile holding the padding boundary
+        uint32_t rr[32];
+        tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, rr);
+        tmem_ld_wait();
+        if (q_glob < S) {
 #pragma unroll
-        for (int k = 0; k < GQ_CW; ++k)
-          if (col0 + k > q_glob || col0 + k >= kvl) s[k] = 0xff800000u;
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-#pragma unroll
-      for (int k = 2; k < GQ_CW; k += 4) {
-        mx0 = fmax3(mx0, __uint_as_float(s[k]), __uint_as_float(s[k + 1]));
-        if (k + 2 < GQ_CW) mx1 = fmax3(mx1, __uint_as_float(s[k + 2]), __uint_as_float(s[k + 3]));
-      }
-      sts_f32(ex_row + sbuf * EX_SET + part * EX_STRIDE, fmaxf(mx0, mx1));
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-      c_a += t0 - t1;
-#endif
-      named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      w_bar += t1 - t0;
-#endif
-      float tile_max = lds_f32(ex_row + sbuf * EX_SET);
-#pragma unroll
-      for (int q = 1; q < GQ_SPLIT; ++q) tile_max = fmaxf(tile_max, lds_f32(ex_row + sbuf * EX_SET + q * EX_STRIDE));
-      tile_max *= scale_log2;
-      float alpha = 1.0f;
-      const bool rescale = __any_sync(0xffffffffu, tile_max > m_ref + GQ_TAU);
-      if (rescale && tile_max > m_ref + GQ_TAU) {          // (per row; the TMEM traffic below stays warp-uniform)
-        alpha = ex2f(m_ref - tile_max);                    // 0 on the first tile
-        m_ref = tile_max;
-        l *= alpha;
-      }
-      const unsigned long long c2 = pk2(scale_log2, scale_log2), nm2 = pk2(-m_ref, -m_ref);
-      unsigned long long l2a = pk2(0.f, 0.f), l2b = pk2(0.f, 0.f);
-      uint32_t pk[GQ_CW / 2];
-#pragma unroll
-      for (int k = 0; k < GQ_CW; k += 2) {
-        const unsigned long long x2 = ffma2(pk2(__uint_as_float(s[k]), __uint_as_float(s[k + 1])), c2, nm2);
-        float p0, p1;
-        if (((k >> 1) % GQ_POLY_DEN) < GQ_POLY_NUM) {       // this share of the exponentials on the FMA pipe (the XU is the
-          poly_exp2_pair<false>(x2, p0, p1);                // narrower one: 16 ex2 / cycle / SM against 16384 per tile)
-        } else {
-          float x0, x1;
-          unpk2(x2, x0, x1);
-          p0 = ex2f(x0);
-          p1 = ex2f(x1);
-        }
-        if ((k >> 1) & 1) l2b = fadd2(l2b, pk2(p0, p1));
-        else l2a = fadd2(l2a, pk2(p0, p1));
-        pk[k >> 1] = pack_bf16(p0, p1);
-      }
-      {
-        float a, c, e, f;
-        unpk2(l2a, a, c);
-        unpk2(l2b, e, f);
-        l += (a + c) + (e + f);
-      }
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-      c_b += t0 - t1;
-#endif
-      if (j > 0) {                                         // the previous P V has read P and finished its part of O
-        mbar_wait_a(sb + GF_O_FULL, (j - 1) & 1);
-#ifdef GQ_CYCLES
-        t1 = GQC_NOW();
-        w_o += t1 - t0;
-        t0 = t1;
-#endif
-        tc_fence_after();
-        if (rescale) {
-#pragma unroll
-          for (int c = 0; c < GQ_CW / 32; ++c) {
-            uint32_t r[32];
-            tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(__uint_as_float(r[k]) * alpha);
-            tmem_st_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(rr[8 * u]) * inv_l, __uint_as_float(rr[8 * u + 1]) * inv_l);
+            v.y = pack_bf16(__uint_as_float(rr[8 * u + 2]) * inv_l, __uint_as_float(rr[8 * u + 3]) * inv_l);
+            v.z = pack_bf16(__uint_as_float(rr[8 * u + 4]) * inv_l, __uint_as_float(rr[8 * u + 5]) * inv_l);
+            v.w = pack_bf16(__uint_as_float(rr[8 * u + 6]) * inv_l, __uint_as_float(rr[8 * u + 7]) * inv_l);
+            dst[c * 4 + u] = v;
           }
         }
       }
-#pragma unroll
-      for (int c = 0; c < GQ_CW / 32; ++c) {
-        uint32_t(&pc)[16] = *reinterpret_cast<uint32_t(*)[16]>(&pk[16 * c]);
-        tmem_st_32x16(tlane + 384 + part * (GQ_CW / 2) + 16 * c, pc);
-      }
-      tmem_st_wait();
+      // (the O columns are free again once every compute thread has passed this point: the next item's first P V is
+      //  issued only after all of them have delivered its P, i.e. after their epilogue)
       tc_fence_before();
-      mbar_arrive_a(sb + GF_P_FULL);
-#ifdef GQ_CYCLES
-      c_c += GQC_NOW() - t0;
-#endif
     }
-#ifdef GQ_CYCLES
-    if (lane == 0 && warp == 4) {
-      GQC_ADD(48, 1);                                      // per CTA: entry -> loop start, loop, (epilogue added below)
-      GQC_ADD(49, t_begin - t_entry);
-      GQC_ADD(50, GQC_NOW() - t_begin);
-      GQC_ADD(8, n_tiles);
-      GQC_ADD(9, GQC_NOW() - t_begin);
-      GQC_ADD(10, w_s);
-      GQC_ADD(11, c_a);
-      GQC_ADD(12, w_bar);
-      GQC_ADD(13, c_b);
-      GQC_ADD(14, w_o);
-      GQC_ADD(15, c_c);
-    }
-#endif
-    // row sum of all parts, normalise, store O (this part's columns) and the log-sum-exp
-    sts_f32(ex_row + 2 * EX_SET + part * EX_STRIDE, l);
-    named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
-    float l_tot = lds_f32(ex_row + 2 * EX_SET);
-#pragma unroll
-    for (int q = 1; q < GQ_SPLIT; ++q) l_tot += lds_f32(ex_row + 2 * EX_SET + q * EX_STRIDE);
-    const float inv_l = 1.0f / l_tot;
-    mbar_wait_a(sb + GF_O_FULL, (n_tiles - 1) & 1);
-    tc_fence_after();
-    if (q_glob < S) {
-      if (part == 0) lse[(static_cast<size_t>(b) * Hq + hq) * S + q_glob] = m_ref + log2f(l_tot);
-    }
-    uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GQ_CW);
-#pragma unroll
-    for (int c = 0; c < GQ_CW / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, r);
-      tmem_ld_wait();
-      if (q_glob < S) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[8 * u]) * inv_l, __uint_as_float(r[8 * u + 1]) * inv_l);
-          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * inv_l, __uint_as_float(r[8 * u + 3]) * inv_l);
-          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * inv_l, __uint_as_float(r[8 * u + 5]) * inv_l);
-          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * inv_l, __uint_as_float(r[8 * u + 7]) * inv_l);
-          dst[c * 4 + u] = v;
-        }
-      }
-    }
-#ifdef GQ_CYCLES
-    if (lane == 0 && warp == 4) GQC_ADD(51, GQC_NOW() - t_entry);
-#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
-#ifdef GQ_CYCLES
-  if (threadIdx.x == 0) GQC_ADD(52, GQC_NOW() - t_entry);
-#endif
+}
+
+static int gq_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
 }
 
 int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
@@ -455,9 +466,10 @@ int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, 
     AL_CHECK_CUDA(cudaFuncSetAttribute(gqa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM));
     attr_set = true;
   }
-  dim3 grid(Hq, B, (S + GQ_T - 1) / GQ_T);
-  gqa_fwd_kernel<<<grid, GQ_THREADS, GF_SMEM, stream>>>(reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, kv_len, S, Hq,
-                                                        Hkv, scale * 1.4426950408889634f);
+  const int items = ((S + GQ_T - 1) / GQ_T) * Hq * B;
+  gqa_fwd_kernel<<<std::min(items, gq_num_sms()), GQ_THREADS, GF_SMEM, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, kv_len, B, S, Hq, Hkv,
+      scale * 1.4426950408889634f);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
