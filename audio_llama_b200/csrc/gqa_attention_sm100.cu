@@ -528,17 +528,18 @@ __global__ void __launch_bounds__(GD_THREADS, 1)
 gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __nv_bfloat16* __restrict__ d_out,
                   const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_len,
-                  __nv_bfloat16* __restrict__ dq, int S, int Hq, int Hkv, float scale) {
+                  __nv_bfloat16* __restrict__ dq, int B, int S, int Hq, int Hkv, float scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // heavy tiles first, over the WHOLE grid (blockIdx.z is the slowest index of the launch order): query tile qt visits
-  // qt + 1 kv tiles (causal), so the heaviest work items start first and the tail of the grid is made of the light ones
-  const int qt = gridDim.z - 1 - blockIdx.z, hq = blockIdx.x, b = blockIdx.y;
-  const int hkv = hq / (Hq / Hkv);
-  const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
-  const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
+  const int nq = (S + GQ_T - 1) / GQ_T;
+  const int rounds = gq_rounds(nq, Hq, B);               // persistent CTAs over the heavy-first item list (see the forward)
+  const int G_heads = Hq / Hkv;
   const float scale_log2 = scale * LOG2E_GQ;
+  auto tiles_of = [&](const GqItem& it) {
+    const int kvl = max(1, min(S, kv_len ? kv_len[it.b] : S));
+    return min(it.qt + 1, (kvl + GQ_T - 1) / GQ_T);
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmK);
@@ -566,219 +567,205 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GD_TMEM_PTR) : "memory");
   // TMEM columns: S 0..127 | dP 128..255 (each thread's dS, bf16 pairs, over the first half of its own dP columns)
   //               | dQ 256..383 | Q 384..447 | dO 448..511 (bf16 pairs, A operands)
+  // g = (item, kv tile) steps taken by this CTA so far: ring stages and mbarrier phases run on across items.
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait_a(sb + GD_KV_EMPTY + 8 * s, ((j >> 1) - 1) & 1);
-#ifdef GQ_HACK_NOTMA   // timing experiment only (wrong results): tiles after the first two are not loaded
-        if (j >= 2) {
-          mbar_arrive_a(sb + GD_KV_FULL + 8 * s);
-          continue;
+      int g = 0;
+      for (int r = 0; r < rounds; ++r) {
+        GqItem it;
+        if (!gq_item(r, nq, Hq, B, it)) continue;
+        const int n_tiles = tiles_of(it), hkv = it.hq / G_heads;
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int s = g & 1;
+          if (g >= 2) mbar_wait_a(sb + GD_KV_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
+          mbar_arrive_expect_tx_a(sb + GD_KV_FULL + 8 * s, 2 * GQ_TILE_BYTES);
+          gq_issue_tile(sb + GD_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, it.b);
+          gq_issue_tile(sb + GD_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, it.b);
         }
-#endif
-        mbar_arrive_expect_tx_a(sb + GD_KV_FULL + 8 * s, 2 * GQ_TILE_BYTES);
-        gq_issue_tile(sb + GD_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, b);
-        gq_issue_tile(sb + GD_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, b);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // Order: S_{j+1} as soon as S_j is in registers; dQ_j when dS_j is written; dP_{j+1} behind dQ_j (dS_j lives in
+    // Order: S_{g+1} as soon as S_g is in registers; dQ_g when dS_g is written; dP_{g+1} behind dQ_g (dS_g lives in
     // the dP columns; tensor-core operations of one thread execute in issue order).
     const uint32_t k_lo = gq_desc_kmajor(sb + GD_OFF_K), v_lo = gq_desc_kmajor(sb + GD_OFF_V), kmn_lo = gq_desc_mnmajor(sb + GD_OFF_K);
     constexpr uint32_t STAGE = GQ_TILE_BYTES >> 4;
-    mbar_wait_a(sb + GD_QDO_FULL, 0);
-    mbar_wait_a(sb + GD_KV_FULL, 0);
-    tc_fence_after();
-    if (elect_one()) {
-      gq_mma_tk(tmem_base + GD_TM_S, tmem_base + GD_TM_Q, k_lo);
-      umma_commit_a(sb + GD_S_FULL);
-      gq_mma_tk(tmem_base + GD_TM_DP, tmem_base + GD_TM_DO, v_lo);
-      umma_commit_a(sb + GD_DP_FULL);
-    }
-    __syncwarp();
-#ifdef GQ_CYCLES
-    long long w_ds = 0, w_se = 0, t_begin = GQC_NOW(), t0;
-#endif
-    for (int j = 0; j < n_tiles; ++j) {
-      const int s1 = (j + 1) & 1;
-      if (j + 1 < n_tiles) {
-        mbar_wait_a(sb + GD_KV_FULL + 8 * s1, ((j + 1) >> 1) & 1);
-#ifdef GQ_CYCLES
-        t0 = GQC_NOW();
-#endif
-        mbar_wait_a(sb + GD_S_EMPTY, j & 1);
-#ifdef GQ_CYCLES
-        w_se += GQC_NOW() - t0;
-#endif
-        tc_fence_after();
-        if (elect_one()) {
-          gq_mma_tk(tmem_base + GD_TM_S, tmem_base + GD_TM_Q, k_lo + s1 * STAGE);
-          umma_commit_a(sb + GD_S_FULL);
-        }
-        __syncwarp();
-      }
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GD_DS_FULL, j & 1);
-#ifdef GQ_CYCLES
-      w_ds += GQC_NOW() - t0;
-#endif
+    auto issue_s = [&](int g) {                            // needs K_g in shared memory and S_{g-1} in registers
+      const int s = g & 1;
+      mbar_wait_a(sb + GD_KV_FULL + 8 * s, (g >> 1) & 1);
+      if (g >= 1) mbar_wait_a(sb + GD_S_EMPTY, (g - 1) & 1);
       tc_fence_after();
-      if (elect_one()) {                                   // dQ += dS K_j: k-step k = keys 16 k .., from the part that owns them
-        constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T, 0, 1);
-        const uint32_t b_lo = kmn_lo + (j & 1) * STAGE;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ts_lo(tmem_base + GD_TM_DQ, tmem_base + GD_TM_DP + (16 * k / GD_CW) * GD_CW + ((16 * k % GD_CW) >> 1),
-                     b_lo + ((2048 * k) >> 4), IDESC, (k != 0) || (j != 0));
-        umma_commit_a(sb + GD_KV_EMPTY + 8 * (j & 1));
-        if (j + 1 < n_tiles) {
-          gq_mma_tk(tmem_base + GD_TM_DP, tmem_base + GD_TM_DO, v_lo + s1 * STAGE);
-          umma_commit_a(sb + GD_DP_FULL);
-        } else {
-          umma_commit_a(sb + GD_DQ_DONE);
-        }
+      if (elect_one()) {
+        gq_mma_tk(tmem_base + GD_TM_S, tmem_base + GD_TM_Q, k_lo + s * STAGE);
+        umma_commit_a(sb + GD_S_FULL);
       }
       __syncwarp();
+    };
+    auto issue_dp = [&](int g) {                           // (behind dQ_{g-1} in issue order)
+      if (elect_one()) {
+        gq_mma_tk(tmem_base + GD_TM_DP, tmem_base + GD_TM_DO, v_lo + (g & 1) * STAGE);
+        umma_commit_a(sb + GD_DP_FULL);
+      }
+      __syncwarp();
+    };
+    int g = 0, n_item = 0;
+    for (int r = 0; r < rounds; ++r) {
+      GqItem it;
+      if (!gq_item(r, nq, Hq, B, it)) continue;
+      const int n_tiles = tiles_of(it);
+      mbar_wait_a(sb + GD_QDO_FULL, n_item & 1);           // this item's Q and dO rows are in TMEM
+      ++n_item;
+      issue_s(g);
+      issue_dp(g);
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        if (j + 1 < n_tiles) issue_s(g + 1);
+        mbar_wait_a(sb + GD_DS_FULL, g & 1);
+        tc_fence_after();
+        if (elect_one()) {                                 // dQ += dS K_g: k-step k = keys 16 k .., from the part that owns them
+          constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T, 0, 1);
+          const uint32_t b_lo = kmn_lo + (g & 1) * STAGE;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ts_lo(tmem_base + GD_TM_DQ, tmem_base + GD_TM_DP + (16 * k / GD_CW) * GD_CW + ((16 * k % GD_CW) >> 1),
+                       b_lo + ((2048 * k) >> 4), IDESC, (k != 0) || (j != 0));
+          umma_commit_a(sb + GD_KV_EMPTY + 8 * (g & 1));
+          if (j + 1 == n_tiles) umma_commit_a(sb + GD_DQ_DONE);
+        }
+        __syncwarp();
+        if (j + 1 < n_tiles) issue_dp(g + 1);
+      }
     }
-#ifdef GQ_CYCLES
-    if (lane == 0) {
-      GQC_ADD(16, n_tiles);
-      GQC_ADD(17, GQC_NOW() - t_begin);
-      GQC_ADD(18, w_se);
-      GQC_ADD(19, w_ds);
-    }
-#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ dS: GD_SPLIT threads per query row
     const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
-    const int q_glob = qt * GQ_T + static_cast<int>(row);
-    const bool live = q_glob < S;
-    {   // this thread's GD_CW columns of the Q and dO rows -> TMEM (bf16 pairs are already the A-operand layout)
-      const size_t g = ((static_cast<size_t>(b) * S + (live ? q_glob : 0)) * Hq + hq) * GQ_T + part * GD_CW;
+    // this thread's GD_CW columns of an item's Q and dO rows (bf16 pairs are already the A-operand layout) and the row's
+    // -lse and -D
+    auto load_rows = [&](const GqItem& it, uint32_t (&rq)[GD_CW / 2], uint32_t (&rd)[GD_CW / 2], float& neg_lse, float& neg_d) {
+      const int qg = it.qt * GQ_T + static_cast<int>(row);
+      const bool live = qg < S;
+      const size_t g0 = ((static_cast<size_t>(it.b) * S + (live ? qg : 0)) * Hq + it.hq) * GQ_T + part * GD_CW;
+      const uint4* sq = reinterpret_cast<const uint4*>(q + g0);
+      const uint4* sd = reinterpret_cast<const uint4*>(d_out + g0);
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint4* src = reinterpret_cast<const uint4*>((which == 0 ? q : d_out) + g);
-        uint32_t r[GD_CW / 2];
-#pragma unroll
-        for (int u = 0; u < GD_CW / 8; ++u) {
-          const uint4 v = live ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
-          r[4 * u] = v.x;
-          r[4 * u + 1] = v.y;
-          r[4 * u + 2] = v.z;
-          r[4 * u + 3] = v.w;
-        }
-        tmem_st_32x16(tlane + (which == 0 ? GD_TM_Q : GD_TM_DO) + part * (GD_CW / 2), r);
+      for (int u = 0; u < GD_CW / 8; ++u) {
+        const uint4 v = live ? __ldg(sq + u) : make_uint4(0, 0, 0, 0);
+        const uint4 w = live ? __ldg(sd + u) : make_uint4(0, 0, 0, 0);
+        rq[4 * u] = v.x; rq[4 * u + 1] = v.y; rq[4 * u + 2] = v.z; rq[4 * u + 3] = v.w;
+        rd[4 * u] = w.x; rd[4 * u + 1] = w.y; rd[4 * u + 2] = w.z; rd[4 * u + 3] = w.w;
       }
+      const size_t stat = (static_cast<size_t>(it.b) * Hq + it.hq) * S + (live ? qg : 0);
+      neg_lse = live ? -lse[stat] : -INFINITY;             // rows past S: p = 0
+      neg_d = live ? -dsum[stat] : 0.f;
+    };
+    auto store_rows = [&](const uint32_t (&rq)[GD_CW / 2], const uint32_t (&rd)[GD_CW / 2]) {
+      tmem_st_32x16(tlane + GD_TM_Q + part * (GD_CW / 2), rq);
+      tmem_st_32x16(tlane + GD_TM_DO + part * (GD_CW / 2), rd);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GD_QDO_FULL);
-    }
-    const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + (live ? q_glob : 0);
-    const float neg_lse = live ? -lse[stat] : -INFINITY;   // rows past S: p = 0
-    const float neg_d = live ? -dsum[stat] : 0.f;
-    const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse), nd2 = pk2(neg_d, neg_d);
-#ifdef GQ_CYCLES
-    long long w_s = 0, w_dp = 0, c_a = 0, c_b = 0, t_begin = GQC_NOW(), t0, t1;
-#endif
-    for (int j = 0; j < n_tiles; ++j) {
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GD_S_FULL, j & 1);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      w_s += t1 - t0;
-#endif
-      tc_fence_after();
-      const int col0 = j * GQ_T + part * GD_CW;
-      float pf[GD_CW];                                     // this thread's probabilities
-      {
-        uint32_t sv[32];
-        tmem_ld_32x32(tlane + GD_TM_S + part * GD_CW, sv);
-        tmem_ld_wait();
+    };
+    int g = 0, n_item = 0;
+    float neg_lse = 0.f, neg_d = 0.f;
+    bool first = true;
+    for (int r = 0; r < rounds; ++r) {
+      GqItem it;
+      if (!gq_item(r, nq, Hq, B, it)) continue;
+      const int qt = it.qt, hq = it.hq, b = it.b;
+      const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
+      const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
+      const int q_glob = qt * GQ_T + static_cast<int>(row);
+      const bool live = q_glob < S;
+      if (first) {                                         // (later items: stored at the end of the previous one)
+        uint32_t rq[GD_CW / 2], rd[GD_CW / 2];
+        load_rows(it, rq, rd, neg_lse, neg_d);
+        store_rows(rq, rd);
+        first = false;
+      }
+      const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse), nd2 = pk2(neg_d, neg_d);
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        mbar_wait_a(sb + GD_S_FULL, g & 1);
+        tc_fence_after();
+        const int col0 = j * GQ_T + part * GD_CW;
+        float pf[GD_CW];                                   // this thread's probabilities
+        {
+          uint32_t sv[32];
+          tmem_ld_32x32(tlane + GD_TM_S + part * GD_CW, sv);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive_a(sb + GD_S_EMPTY);                  // S of this tile is in registers
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2, nl2);
+            if (((k >> 1) % GQ_POLY_DEN) < GQ_POLY_NUM) {
+              poly_exp2_pair<true>(x2, pf[k], pf[k + 1]);  // (x <= 0 up to rounding for live entries; masked ones can be large)
+            } else {
+              float x0, x1;
+              unpk2(x2, x0, x1);
+              pf[k] = ex2f(x0);
+              pf[k + 1] = ex2f(x1);
+            }
+          }
+          if ((j == qt) || (col0 + GD_CW > kvl)) {         // diagonal tile or the tile holding the padding boundary
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (col0 + k > q_glob || col0 + k >= kvl) pf[k] = 0.f;
+          }
+        }
+        mbar_wait_a(sb + GD_DP_FULL, g & 1);
+        tc_fence_after();
+        {
+          uint32_t dp[32], ds[16];
+          tmem_ld_32x32(tlane + GD_TM_DP + part * GD_CW, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[k]), __uint_as_float(dp[k + 1])), nd2);
+            const unsigned long long d2 = fmul2(pk2(pf[k], pf[k + 1]), t2);
+            float d0, d1;
+            unpk2(d2, d0, d1);
+            ds[k >> 1] = pack_bf16(d0, d1);                // (the 1/sqrt(d) factor is applied to dQ at the end)
+          }
+          // dS over the first half of this thread's own dP columns (columns it has read; nobody else touches them)
+          tmem_st_32x16(tlane + GD_TM_DP + part * GD_CW, ds);
+        }
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive_a(sb + GD_S_EMPTY);                    // S of this tile is in registers
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[k]), __uint_as_float(sv[k + 1])), c2, nl2);
-          float x0, x1;
-          unpk2(x2, x0, x1);
-          pf[k] = ex2f(x0);
-          pf[k + 1] = ex2f(x1);
-        }
-        if ((j == qt) || (col0 + GD_CW > kvl)) {           // diagonal tile or the tile holding the padding boundary
-#pragma unroll
-          for (int k = 0; k < 32; ++k)
-            if (col0 + k > q_glob || col0 + k >= kvl) pf[k] = 0.f;
-        }
+        mbar_arrive_a(sb + GD_DS_FULL);
       }
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-      c_a += t0 - t1;
-#endif
-      mbar_wait_a(sb + GD_DP_FULL, j & 1);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      w_dp += t1 - t0;
-#endif
+      // Next item's rows: every S and dP of this item has been produced (this thread has seen the last DP_FULL), so the Q
+      // and dO columns are free; the issuer starts the next item's first products under this item's epilogue.
+      GqItem nx;
+      bool has_next = false;
+      for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
+      if (has_next) {
+        uint32_t rq[GD_CW / 2], rd[GD_CW / 2];
+        load_rows(nx, rq, rd, neg_lse, neg_d);
+        store_rows(rq, rd);
+      }
+      mbar_wait_a(sb + GD_DQ_DONE, n_item & 1);
+      ++n_item;
       tc_fence_after();
+      uint4* dst = reinterpret_cast<uint4*>(dq + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GD_CW);
       {
-        uint32_t dp[32], ds[16];
-        tmem_ld_32x32(tlane + GD_TM_DP + part * GD_CW, dp);
+        uint32_t rr[32];
+        tmem_ld_32x32(tlane + GD_TM_DQ + part * GD_CW, rr);
         tmem_ld_wait();
+        if (live) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[k]), __uint_as_float(dp[k + 1])), nd2);
-          const unsigned long long d2 = fmul2(pk2(pf[k], pf[k + 1]), t2);
-          float d0, d1;
-          unpk2(d2, d0, d1);
-          ds[k >> 1] = pack_bf16(d0, d1);                  // (the 1/sqrt(d) factor is applied to dQ at the end)
+          for (int u = 0; u < 4; ++u) {
+            uint4 v;
+            v.x = pack_bf16(__uint_as_float(rr[8 * u]) * scale, __uint_as_float(rr[8 * u + 1]) * scale);
+            v.y = pack_bf16(__uint_as_float(rr[8 * u + 2]) * scale, __uint_as_float(rr[8 * u + 3]) * scale);
+            v.z = pack_bf16(__uint_as_float(rr[8 * u + 4]) * scale, __uint_as_float(rr[8 * u + 5]) * scale);
+            v.w = pack_bf16(__uint_as_float(rr[8 * u + 6]) * scale, __uint_as_float(rr[8 * u + 7]) * scale);
+            dst[u] = v;
+          }
         }
-        // dS over the first half of this thread's own dP columns (columns it has read; nobody else touches them)
-        tmem_st_32x16(tlane + GD_TM_DP + part * GD_CW, ds);
       }
-      tmem_st_wait();
       tc_fence_before();
-      mbar_arrive_a(sb + GD_DS_FULL);
-#ifdef GQ_CYCLES
-      c_b += GQC_NOW() - t1;
-#endif
-    }
-#ifdef GQ_CYCLES
-    if (lane == 0 && warp == 4) {
-      GQC_ADD(24, n_tiles);
-      GQC_ADD(25, GQC_NOW() - t_begin);
-      GQC_ADD(26, w_s);
-      GQC_ADD(27, c_a);
-      GQC_ADD(28, w_dp);
-      GQC_ADD(29, c_b);
-    }
-#endif
-    mbar_wait_a(sb + GD_DQ_DONE, 0);
-    tc_fence_after();
-    uint4* dst = reinterpret_cast<uint4*>(dq + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GD_CW);
-    {
-      uint32_t r[32];
-      tmem_ld_32x32(tlane + GD_TM_DQ + part * GD_CW, r);
-      tmem_ld_wait();
-      if (live) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[8 * u]) * scale, __uint_as_float(r[8 * u + 1]) * scale);
-          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * scale, __uint_as_float(r[8 * u + 3]) * scale);
-          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * scale, __uint_as_float(r[8 * u + 5]) * scale);
-          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * scale, __uint_as_float(r[8 * u + 7]) * scale);
-          dst[u] = v;
-        }
-      }
     }
   }
   tc_fence_before();
@@ -1130,9 +1117,9 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(d_out), dsum_ws, B, S, Hq);
   AL_CHECK_CUDA(cudaGetLastError());
   const int nt = (S + GQ_T - 1) / GQ_T;
-  gqa_bwd_dq_kernel<<<dim3(Hq, B, nt), GD_THREADS, GD_SMEM, stream>>>(
+  gqa_bwd_dq_kernel<<<std::min(nt * Hq * B, gq_num_sms()), GD_THREADS, GD_SMEM, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<const __nv_bfloat16*>(d_out), lse, dsum_ws, kv_len,
-      reinterpret_cast<__nv_bfloat16*>(dq), S, Hq, Hkv, scale);
+      reinterpret_cast<__nv_bfloat16*>(dq), B, S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
   gqa_bwd_dkv_kernel<<<dim3(Hkv, B, nt), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
                                                                          reinterpret_cast<__nv_bfloat16*>(dk),
