@@ -611,13 +611,14 @@ int al_gqa_attention_backward(const void* q, const void* k, const void* v, const
   AL_REQUIRE(q && k && v && out && lse && d_out && dq && dk && dv && dsum_ws, "al_gqa_attention_backward: NULL argument");
   AL_REQUIRE(head_dim == 128, "al_gqa_attention_backward: head_dim must be 128, got %d", head_dim);
   AL_REQUIRE(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "al_gqa_attention_backward: bad shape B=%d S=%d Hq=%d Hkv=%d", B, S, Hq, Hkv);
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, tdq;
   int rc;
   if ((rc = tmap_bshd(&tq, q, B, S, Hq))) return rc;
   if ((rc = tmap_bshd(&tk, k, B, S, Hkv))) return rc;
   if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
   if ((rc = tmap_bshd(&tdo, d_out, B, S, Hq))) return rc;
-  rc = launch_gqa_bwd(tq, tk, tv, tdo, q, out, d_out, lse, dsum_ws, kv_len, dq, dk, dv, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
+  if ((rc = tmap_bshd(&tdq, dq, B, S, Hq))) return rc;
+  rc = launch_gqa_bwd(tq, tk, tv, tdo, tdq, out, d_out, lse, dsum_ws, kv_len, dq, dk, dv, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
   if (rc == 0) g_launches += 3;
   return rc;
 }

@@ -63,6 +63,16 @@ __device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d_a(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// Byte offset, inside a [128 rows][128 bf16] tile staged as two SW128 boxes, of the 16-byte chunk `chunk` (0..15) of row
+// `row`: box = chunk / 8, the chunk's position inside the 128-byte row is XORed with row % 8.
+__device__ __forceinline__ uint32_t gq_tile_chunk(uint32_t row, uint32_t chunk) {
+  return (chunk >> 3) * GQ_BOX_BYTES + row * 128 + (((chunk & 7) ^ (row & 7)) << 4);
+}
 __device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -515,20 +525,23 @@ constexpr int GD_CW = GQ_T / GD_SPLIT;         // 32 columns per thread
 constexpr int GD_COMPUTE = GQ_T * GD_SPLIT;
 constexpr int GD_THREADS = 128 + GD_COMPUTE;   // warps 0-3 control, then the compute warps
 constexpr uint32_t GD_OFF_K = 0, GD_OFF_V = 2 * GQ_TILE_BYTES;
-constexpr uint32_t GD_OFF_BARS = 4 * GQ_TILE_BYTES;
+constexpr uint32_t GD_OFF_STG = 4 * GQ_TILE_BYTES;                   // two tiles: the next item's Q | dO rows on their way to TMEM
+                                                                     // (TMA in), then the finished dQ tile in the first (TMA out)
+constexpr uint32_t GD_OFF_BARS = 6 * GQ_TILE_BYTES;
+constexpr uint32_t GD_STG_FULL = GD_OFF_BARS + 128, GD_STG_EMPTY = GD_STG_FULL + 8;
 constexpr uint32_t GD_QDO_FULL = GD_OFF_BARS, GD_KV_FULL = GD_QDO_FULL + 8, GD_KV_EMPTY = GD_KV_FULL + 16, GD_S_FULL = GD_KV_EMPTY + 16,
                    GD_S_EMPTY = GD_S_FULL + 8, GD_DP_FULL = GD_S_EMPTY + 8, GD_DS_FULL = GD_DP_FULL + 8, GD_DQ_DONE = GD_DS_FULL + 8,
                    GD_TMEM_PTR = GD_DQ_DONE + 8;
-constexpr int GD_SMEM = GD_TMEM_PTR + 16 + 1024;
+constexpr int GD_SMEM = GD_OFF_BARS + 256 + 1024;
 // TMEM columns
 static_assert(GD_CW == 32, "the dQ kernel's compute loop handles one 32-column chunk per thread");
 constexpr uint32_t GD_TM_S = 0, GD_TM_DP = 128, GD_TM_DQ = 256, GD_TM_Q = 384, GD_TM_DO = 448;
 
 __global__ void __launch_bounds__(GD_THREADS, 1)
-gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __nv_bfloat16* __restrict__ d_out,
-                  const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_len,
-                  __nv_bfloat16* __restrict__ dq, int B, int S, int Hq, int Hkv, float scale) {
+gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                  const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse, const float* __restrict__ dsum,
+                  const int* __restrict__ kv_len, int B, int S, int Hq, int Hkv, float scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -544,6 +557,11 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
+    mbar_init_a(sb + GD_STG_FULL, 1);
+    mbar_init_a(sb + GD_STG_EMPTY, 1);
     mbar_init_a(sb + GD_QDO_FULL, GD_COMPUTE);
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GD_KV_FULL + 8 * s, 1);
@@ -571,10 +589,16 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
-      int g = 0;
+      auto load_rows = [&](const GqItem& it) {             // an item's Q and dO tiles into the staging pair
+        mbar_arrive_expect_tx_a(sb + GD_STG_FULL, 2 * GQ_TILE_BYTES);
+        gq_issue_tile(sb + GD_OFF_STG, &tmQ, sb + GD_STG_FULL, it.hq, it.qt * GQ_T, it.b);
+        gq_issue_tile(sb + GD_OFF_STG + GQ_TILE_BYTES, &tmDO, sb + GD_STG_FULL, it.hq, it.qt * GQ_T, it.b);
+      };
+      int g = 0, n_item = 0;
       for (int r = 0; r < rounds; ++r) {
         GqItem it;
         if (!gq_item(r, nq, Hq, B, it)) continue;
+        if (n_item == 0) load_rows(it);
         const int n_tiles = tiles_of(it), hkv = it.hq / G_heads;
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int s = g & 1;
@@ -583,6 +607,16 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
           gq_issue_tile(sb + GD_OFF_K + s * GQ_TILE_BYTES, &tmK, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, it.b);
           gq_issue_tile(sb + GD_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GD_KV_FULL + 8 * s, hkv, j * GQ_T, it.b);
         }
+        // the NEXT item's rows, as soon as the staging pair is free (this item's rows are in TMEM and the previous
+        // item's dQ tile has left): about two kv tiles ahead of the moment the compute threads ask for them
+        GqItem nx;
+        bool has_next = false;
+        for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
+        if (has_next) {
+          mbar_wait_a(sb + GD_STG_EMPTY, n_item & 1);
+          load_rows(nx);
+        }
+        ++n_item;
       }
     }
   } else if (warp == 1) {
@@ -641,28 +675,28 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
     const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
-    // this thread's GD_CW columns of an item's Q and dO rows (bf16 pairs are already the A-operand layout) and the row's
-    // -lse and -D
-    auto load_rows = [&](const GqItem& it, uint32_t (&rq)[GD_CW / 2], uint32_t (&rd)[GD_CW / 2], float& neg_lse, float& neg_d) {
+    // An item's Q and dO rows: staged by TMA as two swizzled tiles; this thread moves its GD_CW columns of both rows into
+    // TMEM (bf16 pairs are already the A-operand layout) and fetches the row's -lse and -D.
+    int n_rows = 0;                                        // staged row sets consumed so far (STG_FULL phase)
+    auto take_rows = [&](const GqItem& it, float& neg_lse, float& neg_d) {
       const int qg = it.qt * GQ_T + static_cast<int>(row);
       const bool live = qg < S;
-      const size_t g0 = ((static_cast<size_t>(it.b) * S + (live ? qg : 0)) * Hq + it.hq) * GQ_T + part * GD_CW;
-      const uint4* sq = reinterpret_cast<const uint4*>(q + g0);
-      const uint4* sd = reinterpret_cast<const uint4*>(d_out + g0);
-#pragma unroll
-      for (int u = 0; u < GD_CW / 8; ++u) {
-        const uint4 v = live ? __ldg(sq + u) : make_uint4(0, 0, 0, 0);
-        const uint4 w = live ? __ldg(sd + u) : make_uint4(0, 0, 0, 0);
-        rq[4 * u] = v.x; rq[4 * u + 1] = v.y; rq[4 * u + 2] = v.z; rq[4 * u + 3] = v.w;
-        rd[4 * u] = w.x; rd[4 * u + 1] = w.y; rd[4 * u + 2] = w.z; rd[4 * u + 3] = w.w;
-      }
       const size_t stat = (static_cast<size_t>(it.b) * Hq + it.hq) * S + (live ? qg : 0);
-      neg_lse = live ? -lse[stat] : -INFINITY;             // rows past S: p = 0
+      neg_lse = live ? -lse[stat] : -INFINITY;             // rows past S: p = 0 (their Q / dO rows arrive as zeros)
       neg_d = live ? -dsum[stat] : 0.f;
-    };
-    auto store_rows = [&](const uint32_t (&rq)[GD_CW / 2], const uint32_t (&rd)[GD_CW / 2]) {
-      tmem_st_32x16(tlane + GD_TM_Q + part * (GD_CW / 2), rq);
-      tmem_st_32x16(tlane + GD_TM_DO + part * (GD_CW / 2), rd);
+      mbar_wait_a(sb + GD_STG_FULL, n_rows & 1);
+      ++n_rows;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        uint32_t rr[GD_CW / 2];
+#pragma unroll
+        for (int u = 0; u < GD_CW / 8; ++u) {
+          const uint32_t a = sb + GD_OFF_STG + which * GQ_TILE_BYTES + gq_tile_chunk(row, part * (GD_CW / 8) + u);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rr[4 * u]), "=r"(rr[4 * u + 1]), "=r"(rr[4 * u + 2]), "=r"(rr[4 * u + 3]) : "r"(a));
+        }
+        tmem_st_32x16(tlane + (which == 0 ? GD_TM_Q : GD_TM_DO) + part * (GD_CW / 2), rr);
+      }
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_a(sb + GD_QDO_FULL);
@@ -677,11 +711,10 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
       const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
       const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
       const int q_glob = qt * GQ_T + static_cast<int>(row);
-      const bool live = q_glob < S;
-      if (first) {                                         // (later items: stored at the end of the previous one)
-        uint32_t rq[GD_CW / 2], rd[GD_CW / 2];
-        load_rows(it, rq, rd, neg_lse, neg_d);
-        store_rows(rq, rd);
+      if (first) {                                         // (later items: taken at the end of the previous one)
+        take_rows(it, neg_lse, neg_d);
+        named_bar_sync(GQ_BAR_EXCH, GD_COMPUTE);           // every thread has read the staged rows
+        if (warp == 4 && elect_one()) mbar_arrive_a(sb + GD_STG_EMPTY);
         first = false;
       }
       const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse), nd2 = pk2(neg_d, neg_d);
@@ -736,32 +769,41 @@ gqa_bwd_dq_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ C
         mbar_arrive_a(sb + GD_DS_FULL);
       }
       // Next item's rows: every S and dP of this item has been produced (this thread has seen the last DP_FULL), so the Q
-      // and dO columns are free; the issuer starts the next item's first products under this item's epilogue.
+      // and dO columns of TMEM are free; the issuer starts the next item's first products under this item's epilogue.
       GqItem nx;
       bool has_next = false;
       for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
-      if (has_next) {
-        uint32_t rq[GD_CW / 2], rd[GD_CW / 2];
-        load_rows(nx, rq, rd, neg_lse, neg_d);
-        store_rows(rq, rd);
-      }
+      if (has_next) take_rows(nx, neg_lse, neg_d);
       mbar_wait_a(sb + GD_DQ_DONE, n_item & 1);
       ++n_item;
       tc_fence_after();
-      uint4* dst = reinterpret_cast<uint4*>(dq + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GD_CW);
+      // epilogue: dQ tile -> first staging tile (swizzled) -> one TMA store (rows past S are clipped by the tensor map)
       {
         uint32_t rr[32];
         tmem_ld_32x32(tlane + GD_TM_DQ + part * GD_CW, rr);
         tmem_ld_wait();
-        if (live) {
+        named_bar_sync(GQ_BAR_EXCH, GD_COMPUTE);           // every thread has read the staged rows of the next item
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(rr[8 * u]) * scale, __uint_as_float(rr[8 * u + 1]) * scale);
-            v.y = pack_bf16(__uint_as_float(rr[8 * u + 2]) * scale, __uint_as_float(rr[8 * u + 3]) * scale);
-            v.z = pack_bf16(__uint_as_float(rr[8 * u + 4]) * scale, __uint_as_float(rr[8 * u + 5]) * scale);
-            v.w = pack_bf16(__uint_as_float(rr[8 * u + 6]) * scale, __uint_as_float(rr[8 * u + 7]) * scale);
-            dst[u] = v;
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t v0 = pack_bf16(__uint_as_float(rr[8 * u]) * scale, __uint_as_float(rr[8 * u + 1]) * scale);
+          const uint32_t v1 = pack_bf16(__uint_as_float(rr[8 * u + 2]) * scale, __uint_as_float(rr[8 * u + 3]) * scale);
+          const uint32_t v2 = pack_bf16(__uint_as_float(rr[8 * u + 4]) * scale, __uint_as_float(rr[8 * u + 5]) * scale);
+          const uint32_t v3 = pack_bf16(__uint_as_float(rr[8 * u + 6]) * scale, __uint_as_float(rr[8 * u + 7]) * scale);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(sb + GD_OFF_STG + gq_tile_chunk(row, part * (GD_CW / 8) + u)), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(GQ_BAR_EXCH, GD_COMPUTE);
+        if (warp == 4 && elect_one()) {
+          tma_store_4d_a(&tmDQ, sb + GD_OFF_STG, 0, hq, qt * GQ_T, b);
+          tma_store_4d_a(&tmDQ, sb + GD_OFF_STG + GQ_BOX_BYTES, 64, hq, qt * GQ_T, b);
+          tma_commit_group();
+          if (has_next) {
+            tma_wait_group_read<0>();                      // the tile has left shared memory: the staging pair is free
+            mbar_arrive_a(sb + GD_STG_EMPTY);
+          } else {
+            tma_wait_group<0>();
           }
         }
       }
@@ -1103,7 +1145,8 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const void* q, const void* out,
+int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdq,
+                   const void* out,
                    const void* d_out, const float* lse, float* dsum_ws, const int* kv_len, void* dq, void* dk, void* dv, int B,
                    int S, int Hq, int Hkv, float scale, cudaStream_t stream) {
   static bool attr_set = false;
@@ -1117,9 +1160,8 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(d_out), dsum_ws, B, S, Hq);
   AL_CHECK_CUDA(cudaGetLastError());
   const int nt = (S + GQ_T - 1) / GQ_T;
-  gqa_bwd_dq_kernel<<<std::min(nt * Hq * B, gq_num_sms()), GD_THREADS, GD_SMEM, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<const __nv_bfloat16*>(d_out), lse, dsum_ws, kv_len,
-      reinterpret_cast<__nv_bfloat16*>(dq), B, S, Hq, Hkv, scale);
+  gqa_bwd_dq_kernel<<<std::min(nt * Hq * B, gq_num_sms()), GD_THREADS, GD_SMEM, stream>>>(tq, tk, tv, tdo, tdq, lse, dsum_ws, kv_len,
+                                                                                          B, S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
   gqa_bwd_dkv_kernel<<<dim3(Hkv, B, nt), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
                                                                          reinterpret_cast<__nv_bfloat16*>(dk),

@@ -58,7 +58,8 @@ int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int 
 int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
                    const int* kv_len, int B, int S, int Hq, int Hkv, float scale, cudaStream_t stream);
 // dsum_ws: [B][Hq][S] f32 scratch (rowsum(dO * O)); dq / dk / dv in the layouts of q / k / v.
-int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const void* q, const void* out,
+int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdq,
+                   const void* out,
                    const void* d_out, const float* lse, float* dsum_ws, const int* kv_len, void* dq, void* dk, void* dv, int B,
                    int S, int Hq, int Hkv, float scale, cudaStream_t stream);
 
