@@ -596,11 +596,13 @@ int al_gqa_attention_forward(const void* q, const void* k, const void* v, void* 
   AL_REQUIRE(q && k && v && out && lse, "al_gqa_attention_forward: NULL argument");
   AL_REQUIRE(head_dim == 128, "al_gqa_attention_forward: head_dim must be 128, got %d", head_dim);
   AL_REQUIRE(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "al_gqa_attention_forward: bad shape B=%d S=%d Hq=%d Hkv=%d", B, S, Hq, Hkv);
-  CUtensorMap tk, tv;
+  CUtensorMap tq, tk, tv, to;
   int rc;
+  if ((rc = tmap_bshd(&tq, q, B, S, Hq))) return rc;
   if ((rc = tmap_bshd(&tk, k, B, S, Hkv))) return rc;
   if ((rc = tmap_bshd(&tv, v, B, S, Hkv))) return rc;
-  rc = launch_gqa_fwd(q, tk, tv, out, lse, kv_len, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
+  if ((rc = tmap_bshd(&to, out, B, S, Hq))) return rc;
+  rc = launch_gqa_fwd(tq, tk, tv, to, lse, kv_len, B, S, Hq, Hkv, scale, (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }

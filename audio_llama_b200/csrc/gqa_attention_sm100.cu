@@ -147,12 +147,15 @@ __device__ __forceinline__ void gq_mma_tk(uint32_t d_tmem, uint32_t a_tmem, uint
 // ============================================================================ forward
 constexpr uint32_t GF_OFF_K = 0;
 constexpr uint32_t GF_OFF_V = GF_OFF_K + 2 * GQ_TILE_BYTES;
-constexpr uint32_t GF_OFF_EXCH = GF_OFF_V + 2 * GQ_TILE_BYTES;       // [2 parities][GQ_SPLIT][128] f32 row maxima, then [GQ_SPLIT][128] sums
+constexpr uint32_t GF_OFF_STG = GF_OFF_V + 2 * GQ_TILE_BYTES;        // one tile: the next item's Q rows on their way to TMEM (TMA in),
+                                                                     // then the finished O tile (TMA out)
+constexpr uint32_t GF_OFF_EXCH = GF_OFF_STG + GQ_TILE_BYTES;         // [2 parities][GQ_SPLIT][128] f32 row maxima, then [GQ_SPLIT][128] sums
 constexpr uint32_t GF_OFF_BARS = GF_OFF_EXCH + 3 * GQ_SPLIT * GQ_T * 4;
+constexpr uint32_t GF_STG_FULL = GF_OFF_BARS + 128, GF_STG_EMPTY = GF_STG_FULL + 8;
 constexpr uint32_t GF_Q_FULL = GF_OFF_BARS, GF_K_FULL = GF_Q_FULL + 8, GF_K_EMPTY = GF_K_FULL + 16, GF_V_FULL = GF_K_EMPTY + 16,
                    GF_V_EMPTY = GF_V_FULL + 16, GF_S_FULL = GF_V_EMPTY + 16, GF_S_EMPTY = GF_S_FULL + 16, GF_P_FULL = GF_S_EMPTY + 16,
                    GF_O_FULL = GF_P_FULL + 8, GF_TMEM_PTR = GF_O_FULL + 8;
-constexpr int GF_SMEM = GF_TMEM_PTR + 16 + 1024;
+constexpr int GF_SMEM = GF_OFF_BARS + 256 + 1024;
 
 // Work items = (query tile, query head, batch), heaviest (largest query tile: most kv tiles under the causal mask) first.
 // The kernels are PERSISTENT: one CTA per SM walks the item list in a serpentine order (round r gives CTA c item
@@ -178,8 +181,8 @@ __device__ __forceinline__ int gq_rounds(int nq, int Hq, int B) {
 }
 
 __global__ void __launch_bounds__(GQ_THREADS, 1)
-gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, float* __restrict__ lse,
                const int* __restrict__ kv_len, int B, int S, int Hq, int Hkv, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
@@ -195,6 +198,10 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmO);
+    mbar_init_a(sb + GF_STG_FULL, 1);
+    mbar_init_a(sb + GF_STG_EMPTY, 1);
     mbar_init_a(sb + GF_Q_FULL, GQ_COMPUTE);
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GF_K_FULL + 8 * s, 1);
@@ -224,10 +231,11 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer (runs ahead into the next item)
-      int g = 0;
+      int g = 0, n_item = 0;
       for (int r = 0; r < rounds; ++r) {
         GqItem it;
         if (!gq_item(r, nq, Hq, B, it)) continue;
+        if (n_item == 0) gq_load_tile(sb + GF_OFF_STG, &tmQ, sb + GF_STG_FULL, it.hq, it.qt * GQ_T, it.b);
         const int n_tiles = tiles_of(it), hkv = it.hq / G_heads;
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int s = g & 1;
@@ -236,6 +244,16 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
           if (g >= 2) mbar_wait_a(sb + GF_V_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
           gq_load_tile(sb + GF_OFF_V + s * GQ_TILE_BYTES, &tmV, sb + GF_V_FULL + 8 * s, hkv, j * GQ_T, it.b);
         }
+        // the NEXT item's Q tile, as soon as the staging tile is free (this item's rows are in TMEM and the previous
+        // item's O tile has left)
+        GqItem nx;
+        bool has_next = false;
+        for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
+        if (has_next) {
+          mbar_wait_a(sb + GF_STG_EMPTY, n_item & 1);
+          gq_load_tile(sb + GF_OFF_STG, &tmQ, sb + GF_STG_FULL, nx.hq, nx.qt * GQ_T, nx.b);
+        }
+        ++n_item;
       }
     }
   } else if (warp == 1) {
@@ -282,26 +300,22 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
     constexpr uint32_t EX_STRIDE = GQ_T * 4, EX_SET = GQ_SPLIT * GQ_T * 4;   // one part's slots | one parity's set
     const uint32_t ex_row = sb + GF_OFF_EXCH + row * 4;
-    // this thread's GQ_CW columns of an item's Q row (bf16 pairs are already the A-operand layout of the TS product)
-    auto load_q = [&](const GqItem& it, uint32_t (&r)[GQ_CW / 2]) {
-      const int qg = it.qt * GQ_T + static_cast<int>(row);
-      const bool live = qg < S;
-      const uint4* src = reinterpret_cast<const uint4*>(q + ((static_cast<size_t>(it.b) * S + (live ? qg : 0)) * Hq + it.hq) * GQ_T +
-                                                        part * GQ_CW);
-#pragma unroll
-      for (int u = 0; u < GQ_CW / 8; ++u) {
-        const uint4 v = live ? __ldg(src + u) : make_uint4(0, 0, 0, 0);
-        r[4 * u] = v.x;
-        r[4 * u + 1] = v.y;
-        r[4 * u + 2] = v.z;
-        r[4 * u + 3] = v.w;
-      }
-    };
-    auto store_q = [&](const uint32_t (&r)[GQ_CW / 2]) {    // (only after the last S of the previous item has been produced)
+    // An item's Q rows: staged by TMA as a swizzled tile; this thread moves its GQ_CW columns into TMEM (bf16 pairs are
+    // already the A-operand layout of the TS product). Only after the last S of the previous item has been produced.
+    int n_rows = 0;                                        // staged tiles consumed so far (STG_FULL phase)
+    auto take_q = [&]() {
+      mbar_wait_a(sb + GF_STG_FULL, n_rows & 1);
+      ++n_rows;
 #pragma unroll
       for (int c = 0; c < GQ_CW / 32; ++c) {
-        const uint32_t(&rc)[16] = *reinterpret_cast<const uint32_t(*)[16]>(&r[16 * c]);
-        tmem_st_32x16(tlane + 448 + part * (GQ_CW / 2) + 16 * c, rc);
+        uint32_t rr[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t a = sb + GF_OFF_STG + gq_tile_chunk(row, part * (GQ_CW / 8) + 4 * c + u);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rr[4 * u]), "=r"(rr[4 * u + 1]), "=r"(rr[4 * u + 2]), "=r"(rr[4 * u + 3]) : "r"(a));
+        }
+        tmem_st_32x16(tlane + 448 + part * (GQ_CW / 2) + 16 * c, rr);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -316,10 +330,10 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
       const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
       const int n_tiles = min(qt + 1, (kvl + GQ_T - 1) / GQ_T);
       const int q_glob = qt * GQ_T + static_cast<int>(row);
-      if (first) {                                         // (later items: stored at the end of the previous one)
-        uint32_t qr[GQ_CW / 2];
-        load_q(it, qr);
-        store_q(qr);
+      if (first) {                                         // (later items: taken at the end of the previous one)
+        take_q();
+        named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);           // every thread has read the staged tile
+        if (warp == 4 && elect_one()) mbar_arrive_a(sb + GF_STG_EMPTY);
         first = false;
       }
       float m_ref = -INFINITY, l = 0.f;
@@ -410,48 +424,56 @@ gqa_fwd_kernel(const __nv_bfloat16* __restrict__ q, const __grid_constant__ CUte
         tc_fence_before();
         mbar_arrive_a(sb + GF_P_FULL);
       }
-      // The next item's Q rows: requested now, stored once this item's sums are exchanged (every S of this item has been
-      // produced, so no product reads the Q columns any more); the issuer then starts the next item's first S under
-      // this item's epilogue.
+      // row sum of all parts; then the next item's Q rows into TMEM (every S of this item has been produced, so no product
+      // reads the Q columns any more): the issuer starts the next item's first S under this item's epilogue
       GqItem nx;
       bool has_next = false;
       for (int r2 = r + 1; r2 < rounds && !has_next; ++r2) has_next = gq_item(r2, nq, Hq, B, nx);
-      uint32_t qn[GQ_CW / 2];
-      if (has_next) load_q(nx, qn);
-      // row sum of all parts, normalise, store O (this part's columns) and the log-sum-exp
       sts_f32(ex_row + 2 * EX_SET + part * EX_STRIDE, l);
       named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
       float l_tot = lds_f32(ex_row + 2 * EX_SET);
 #pragma unroll
       for (int qq = 1; qq < GQ_SPLIT; ++qq) l_tot += lds_f32(ex_row + 2 * EX_SET + qq * EX_STRIDE);
       const float inv_l = 1.0f / l_tot;
-      if (has_next) store_q(qn);
+      if (has_next) take_q();
       mbar_wait_a(sb + GF_O_FULL, (g - 1) & 1);
       tc_fence_after();
       if (q_glob < S) {
         if (part == 0) lse[(static_cast<size_t>(b) * Hq + hq) * S + q_glob] = m_ref + log2f(l_tot);
       }
-      uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * S + q_glob) * Hq + hq) * GQ_T + part * GQ_CW);
+      // epilogue: normalised O tile -> staging tile (swizzled) -> one TMA store (rows past S are clipped by the tensor map)
+      uint32_t ov[GQ_CW / 2];
 #pragma unroll
       for (int c = 0; c < GQ_CW / 32; ++c) {
         uint32_t rr[32];
         tmem_ld_32x32(tlane + 256 + part * GQ_CW + c * 32, rr);
         tmem_ld_wait();
-        if (q_glob < S) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 v;
-            v.x = pack_bf16(__uint_as_float(rr[8 * u]) * inv_l, __uint_as_float(rr[8 * u + 1]) * inv_l);
-            v.y = pack_bf16(__uint_as_float(rr[8 * u + 2]) * inv_l, __uint_as_float(rr[8 * u + 3]) * inv_l);
-            v.z = pack_bf16(__uint_as_float(rr[8 * u + 4]) * inv_l, __uint_as_float(rr[8 * u + 5]) * inv_l);
-            v.w = pack_bf16(__uint_as_float(rr[8 * u + 6]) * inv_l, __uint_as_float(rr[8 * u + 7]) * inv_l);
-            dst[c * 4 + u] = v;
-          }
+        for (int k = 0; k < 16; ++k)
+          ov[16 * c + k] = pack_bf16(__uint_as_float(rr[2 * k]) * inv_l, __uint_as_float(rr[2 * k + 1]) * inv_l);
+      }
+      tc_fence_before();
+      named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);             // every thread has read the staged Q tile of the next item
+      // (and has read its O columns: the next item's first P V is issued only after all of them have delivered its P)
+#pragma unroll
+      for (int u = 0; u < GQ_CW / 8; ++u)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(sb + GF_OFF_STG + gq_tile_chunk(row, part * (GQ_CW / 8) + u)), "r"(ov[4 * u]), "r"(ov[4 * u + 1]),
+                       "r"(ov[4 * u + 2]), "r"(ov[4 * u + 3])
+                     : "memory");
+      fence_proxy_async_smem();
+      named_bar_sync(GQ_BAR_EXCH, GQ_COMPUTE);
+      if (warp == 4 && elect_one()) {
+        tma_store_4d_a(&tmO, sb + GF_OFF_STG, 0, hq, qt * GQ_T, b);
+        tma_store_4d_a(&tmO, sb + GF_OFF_STG + GQ_BOX_BYTES, 64, hq, qt * GQ_T, b);
+        tma_commit_group();
+        if (has_next) {
+          tma_wait_group_read<0>();                        // the tile has left shared memory: the staging tile is free
+          mbar_arrive_a(sb + GF_STG_EMPTY);
+        } else {
+          tma_wait_group<0>();
         }
       }
-      // (the O columns are free again once every compute thread has passed this point: the next item's first P V is
-      //  issued only after all of them have delivered its P, i.e. after their epilogue)
-      tc_fence_before();
     }
   }
   tc_fence_before();
@@ -469,7 +491,7 @@ static int gq_num_sms() {
   return n;
 }
 
-int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
+int launch_gqa_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
                    const int* kv_len, int B, int S, int Hq, int Hkv, float scale, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -477,9 +499,8 @@ int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, 
     attr_set = true;
   }
   const int items = ((S + GQ_T - 1) / GQ_T) * Hq * B;
-  gqa_fwd_kernel<<<std::min(items, gq_num_sms()), GQ_THREADS, GF_SMEM, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), tk, tv, reinterpret_cast<__nv_bfloat16*>(out), lse, kv_len, B, S, Hq, Hkv,
-      scale * 1.4426950408889634f);
+  gqa_fwd_kernel<<<std::min(items, gq_num_sms()), GQ_THREADS, GF_SMEM, stream>>>(tq, tk, tv, to, lse, kv_len, B, S, Hq, Hkv,
+                                                                                 scale * 1.4426950408889634f);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

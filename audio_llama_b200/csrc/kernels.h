@@ -55,7 +55,7 @@ int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int 
 
 // ------------------------------------------------------------------ causal GQA attention, head_dim 128 (gqa_attention_sm100.cu)
 // Tensor maps: rank 4 over [B][S][H][128] bf16, box {64, 1, 128, 1}, SW128 (see api.cu tmap_bshd).
-int launch_gqa_fwd(const void* q, const CUtensorMap& tk, const CUtensorMap& tv, void* out, float* lse,
+int launch_gqa_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
                    const int* kv_len, int B, int S, int Hq, int Hkv, float scale, cudaStream_t stream);
 // dsum_ws: [B][Hq][S] f32 scratch (rowsum(dO * O)); dq / dk / dv in the layouts of q / k / v.
 int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& tdq,
