@@ -1,6 +1,9 @@
 // TMEM read-port probe: NW warps each loop tcgen05.ld 32x32b.x32 (4 KB per warp-instruction), optionally while one thread
 // streams SS / TS products; prints bytes per cycle per SM for the loads and cycles per product.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../audio_llama_b200/csrc tmem_rate.cu -o tmem_rate
+// WARNING kept from the first version of this probe: it consumed the loaded values through a run-time register index
+// (`acc ^= v[r & 31]`), which put the destination array in LOCAL memory — every load was followed by 32 spill stores and
+// the 'TMEM port' read 50 B / cycle / SM. Check `-Xptxas -v` for a zero stack frame before believing a number from here.
 #include <stdio.h>
 #include "common.cuh"
 using namespace al;
