@@ -8,18 +8,20 @@
 //   v  [B][S][Hkv][128] bf16                   kv_len [B] int32 or NULL: keys >= kv_len[b] are masked (right padding)
 // Mask = causal AND key < kv_len[b]; query head h reads kv head h / (Hq / Hkv).
 //
-// Three kernels, one (128-row tile, head, batch) work item per CTA, one CTA per SM (192 KB of shared memory):
-//   gqa_fwd_kernel      S = Q K_j^T (SS MMA, double-buffered in TMEM) -> online softmax, two threads per query row
-//                       (exact row maximum exchanged through shared memory, lazy rescale of O) -> P bf16 in TMEM ->
-//                       O += P V_j (A from TMEM, V MN-major). Writes O and the row log-sum-exp.
-//   gqa_bwd_dq_kernel   per query tile, over kv tiles j <= i: S and dP = dO V_j^T (two SS MMAs), P = 2^(S c - lse),
-//                       dS = P (dP - D) scale -> bf16 in TMEM -> dQ += dS K_j (A from TMEM, K MN-major).
-//   gqa_bwd_dkv_kernel  per kv tile, over the group's query heads and query tiles i >= j, everything TRANSPOSED so that
-//                       the products that contract over queries take their A operand from TMEM: S^T = K_j Q_i^T,
-//                       dP^T = V_j dO_i^T, then dV += P^T dO_i and dK += dS^T Q_i (dO / Q as MN-major B operands).
-//                       P^T / dS^T overwrite the first 64 columns of S^T / dP^T (the next tile's S^T is issued after the
-//                       products that read them: tensor-core operations of one thread execute in issue order).
-// D = rowsum(dO * O) comes from gqa_rowdot_kernel. Scores are recomputed in the backward (nothing but O and lse is saved).
+// Three persistent kernels (one CTA per SM, 512 TMEM columns and ~195 KB of shared memory each) that walk a list of work
+// items, heaviest first, in a serpentine order over the SMs; plus a row-dot kernel for D = rowsum(dO * O):
+//   gqa_fwd_kernel      item = (128-query tile, query head, sample). Q rows in TMEM, S = Q K_j^T as a TS product
+//                       double-buffered in TMEM -> online softmax, four threads per query row (exact row maximum exchanged
+//                       through shared memory, lazy rescale of O, 1/4 of the exponentials on the FMA pipe) -> P bf16 in
+//                       TMEM -> O += P V_j (A from TMEM, V MN-major). Writes O (TMA store) and the row log-sum-exp.
+//   gqa_bwd_dq_kernel   same items. Q and dO rows in TMEM; over kv tiles j <= i: S = Q K_j^T, dP = dO V_j^T (TS products),
+//                       P = 2^(S c - lse), dS = P (dP - D) -> bf16 over the thread's own dP columns -> dQ += dS K_j
+//                       (A from TMEM, K MN-major); dQ * 1/sqrt(d) leaves through a TMA store.
+//   gqa_bwd_dkv_kernel  item = (kv tile, kv head, sample); over the group's query heads and query tiles i >= j, everything
+//                       TRANSPOSED so that the products that contract over queries take their A operand from TMEM:
+//                       S^T = K_j Q_i^T, dP^T = V_j dO_i^T, then dV += P^T dO_i and dK += dS^T Q_i (dO / Q as MN-major B
+//                       operands); the S^T and dP^T chains are staggered on the tensor pipe.
+// Scores are recomputed in the backward (nothing but O and lse is saved). Design notes and measurements: DESIGN.md 11.6 / 11.7.
 #include <algorithm>
 #include <type_traits>
 
@@ -512,26 +514,42 @@ __device__ __forceinline__ void gq_issue_tile(uint32_t dst, const CUtensorMap* m
   tma_load_4d_a(dst + GQ_BOX_BYTES, m, bar, 64, h, s0, b);
 }
 
-// D[b][h][s] = sum_d dO[b][s][h][d] * O[b][s][h][d]   (one warp per row)
+// D[b][h][s] = sum_d dO[b][s][h][d] * O[b][s][h][d]: 16 lanes per 256-byte row (one 16-byte load of each tensor per lane),
+// four rows per thread in flight, grid-stride over groups of 64 rows.
 __global__ void __launch_bounds__(256)
 gqa_rowdot_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ dsum,
                   int B, int S, int H) {
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (row >= static_cast<long long>(B) * S * H) return;
-  const int lane = threadIdx.x & 31;
-  const uint2 a = reinterpret_cast<const uint2*>(o + row * GQ_T)[lane];
-  const uint2 g = reinterpret_cast<const uint2*>(d_o + row * GQ_T)[lane];
-  float acc = __uint_as_float(a.x << 16) * __uint_as_float(g.x << 16);
-  acc = fmaf(__uint_as_float(a.x & 0xffff0000u), __uint_as_float(g.x & 0xffff0000u), acc);
-  acc = fmaf(__uint_as_float(a.y << 16), __uint_as_float(g.y << 16), acc);
-  acc = fmaf(__uint_as_float(a.y & 0xffff0000u), __uint_as_float(g.y & 0xffff0000u), acc);
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const int h = static_cast<int>(row % H);
-    const long long bs = row / H;
-    const int sidx = static_cast<int>(bs % S);
-    const int b = static_cast<int>(bs / S);
-    dsum[(static_cast<long long>(b) * H + h) * S + sidx] = acc;
+  const long long rows = static_cast<long long>(B) * S * H;
+  const int sub = threadIdx.x & 15, rin = threadIdx.x >> 4;   // lane within the row, row within a 16-row slab
+  for (long long base = static_cast<long long>(blockIdx.x) * 64; base < rows; base += static_cast<long long>(gridDim.x) * 64) {
+    uint4 a[4], g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long row = base + u * 16 + rin;
+      const bool ok = row < rows;
+      a[u] = ok ? __ldg(reinterpret_cast<const uint4*>(o + row * GQ_T) + sub) : make_uint4(0, 0, 0, 0);
+      g[u] = ok ? __ldg(reinterpret_cast<const uint4*>(d_o + row * GQ_T) + sub) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, gw[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc = fmaf(__uint_as_float(aw[e] << 16), __uint_as_float(gw[e] << 16), acc);
+        acc = fmaf(__uint_as_float(aw[e] & 0xffff0000u), __uint_as_float(gw[e] & 0xffff0000u), acc);
+      }
+#pragma unroll
+      for (int off = 8; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      const long long row = base + u * 16 + rin;
+      if (sub == 0 && row < rows) {
+        const int h = static_cast<int>(row % H);
+        const long long bs = row / H;
+        const int sidx = static_cast<int>(bs % S);
+        const int b = static_cast<int>(bs / S);
+        dsum[(static_cast<long long>(b) * H + h) * S + sidx] = acc;
+      }
+    }
   }
 }
 
@@ -837,50 +855,60 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------- dK, dV
-// Each 128-query tile is processed as two 64-query halves with their own TMEM regions, barriers and compute group
-// (warps 4-7: half 0, warps 8-11: half 1), so that one half's exponentials run under the other half's products and
-// the tensor pipe always has the next S^T / dP^T half queued behind the dV / dK update of the previous one.
-constexpr int GK_THREADS = 384;
+// Work item = (kv tile, kv head, sample): K_j and V_j stay in shared memory while the group's query heads and the query
+// tiles i >= j stream through a two-stage Q / dO ring. Everything is TRANSPOSED (lane = key, column = query) so that the
+// products that contract over queries take their A operand from TMEM. All 512 TMEM columns are in use (S^T, dP^T, dV, dK),
+// so nothing is double-buffered; instead the two dependency chains of an iteration are staggered on the tensor pipe:
+//     S^T_g -> (P^T) -> dV_g -> S^T_{g+1}          dP^T_g -> (dS^T) -> dK_g -> dP^T_{g+1}
+// dK_{g-1} and dP^T_g run under the exponent phase of iteration g, dV_g and S^T_{g+1} under its dS phase (tensor-core
+// operations of one thread execute in issue order, so a product that overwrites a region is simply issued behind the one
+// that reads it). P^T / dS^T are written by each thread over the first half of its OWN S^T / dP^T columns. Persistent CTAs
+// over the item list, heaviest kv tile (tile 0 meets every query tile) first.
+constexpr int GK_SPLIT = 4;                    // compute threads per key row
+constexpr int GK_CW = GQ_T / GK_SPLIT;         // 32 query columns per thread
+constexpr int GK_COMPUTE = GQ_T * GK_SPLIT;
+constexpr int GK_THREADS = 128 + GK_COMPUTE;
+static_assert(GK_CW == 32, "the dK / dV kernel's compute loop handles one 32-column chunk per thread");
 constexpr uint32_t GK_OFF_K = 0, GK_OFF_V = GQ_TILE_BYTES, GK_OFF_Q = 2 * GQ_TILE_BYTES, GK_OFF_DO = 4 * GQ_TILE_BYTES;
-constexpr uint32_t GK_OFF_STAT = 6 * GQ_TILE_BYTES;                 // [2 halves][2 stages][-lse 64 | -D 64] f32
+constexpr uint32_t GK_OFF_STAT = 6 * GQ_TILE_BYTES;                 // [2 stages][-lse 128 | -D 128] f32
 constexpr uint32_t GK_OFF_BARS = GK_OFF_STAT + 2 * 2 * GQ_T * 4;
-constexpr uint32_t GK_KV_FULL = GK_OFF_BARS, GK_QDO_FULL = GK_KV_FULL + 8, GK_QDO_EMPTY = GK_QDO_FULL + 16, GK_ST_FULL = GK_QDO_EMPTY + 16,
-                   GK_DPT_FULL = GK_ST_FULL + 16, GK_PT_FULL = GK_DPT_FULL + 16, GK_DST_FULL = GK_PT_FULL + 16,
-                   GK_ACC_DONE = GK_DST_FULL + 16, GK_TMEM_PTR = GK_ACC_DONE + 8;
-constexpr int GK_SMEM = GK_TMEM_PTR + 16 + 1024;
+constexpr uint32_t GK_KV_FULL = GK_OFF_BARS, GK_KV_EMPTY = GK_KV_FULL + 8, GK_QDO_FULL = GK_KV_EMPTY + 8, GK_QDO_EMPTY = GK_QDO_FULL + 16,
+                   GK_ST_FULL = GK_QDO_EMPTY + 16, GK_DPT_FULL = GK_ST_FULL + 8, GK_PT_FULL = GK_DPT_FULL + 8, GK_DST_FULL = GK_PT_FULL + 8,
+                   GK_ACC_DONE = GK_DST_FULL + 8, GK_TMEM_PTR = GK_ACC_DONE + 8;
+constexpr int GK_SMEM = GK_OFF_BARS + 256 + 1024;
+
+struct GkItem {
+  int kt, hkv, b;
+};
+__device__ __forceinline__ bool gk_item(int round, int nq, int Hkv, int B, GkItem& it) {
+  const int G = static_cast<int>(gridDim.x), c = static_cast<int>(blockIdx.x);
+  const int idx = round * G + ((round & 1) ? (G - 1 - c) : c);
+  const int per = Hkv * B;
+  if (idx >= nq * per) return false;
+  it.kt = idx / per;                                       // kv tile 0 first: it meets every query tile
+  const int rem = idx % per;
+  it.b = rem / Hkv;
+  it.hkv = rem % Hkv;
+  return true;
+}
 
 __global__ void __launch_bounds__(GK_THREADS, 1)
 gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ dsum, const int* __restrict__ kv_len,
-                   __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int S, int Hq, int Hkv, float scale) {
+                   __nv_bfloat16* __restrict__ dk, __nv_bfloat16* __restrict__ dv, int B, int S, int Hq, int Hkv, float scale) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kt = blockIdx.z, hkv = blockIdx.x, b = blockIdx.y;   // kv tile 0 meets every query tile: heaviest first
   const int G = Hq / Hkv;
-  const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
   const int nq = (S + GQ_T - 1) / GQ_T;
-  const int n_q_local = nq - kt;                           // query tiles i >= kt (causal)
-  const int n_it = G * n_q_local;
+  const int rounds = (nq * Hkv * B + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const float scale_log2 = scale * LOG2E_GQ;
-
-  if (kt * GQ_T >= kvl) {                                  // every key of this tile is padding: zero gradients
-    if (warp >= 4) {
-      const int half = (warp - 4) >> 2;
-      const int kv_glob = kt * GQ_T + (warp & 3) * 32 + lane;
-      if (kv_glob < S) {
-        const size_t o = ((static_cast<size_t>(b) * S + kv_glob) * Hkv + hkv) * GQ_T + half * 64;
-        const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          reinterpret_cast<uint4*>(dk + o)[u] = z;
-          reinterpret_cast<uint4*>(dv + o)[u] = z;
-        }
-      }
-    }
-    return;
-  }
+  // iterations of an item: the group's G query heads x the query tiles i >= kt; 0 when every key of the tile is padding
+  auto iters_of = [&](const GkItem& it) {
+    const int kvl = max(1, min(S, kv_len ? kv_len[it.b] : S));
+    return (it.kt * GQ_T >= kvl) ? 0 : G * (nq - it.kt);
+  };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmQ);
@@ -888,14 +916,15 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmV);
     tma_prefetch_desc(&tmDO);
     mbar_init_a(sb + GK_KV_FULL, 1);
+    mbar_init_a(sb + GK_KV_EMPTY, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init_a(sb + GK_QDO_FULL + 8 * s, 1);
       mbar_init_a(sb + GK_QDO_EMPTY + 8 * s, 1);
-      mbar_init_a(sb + GK_ST_FULL + 8 * s, 1);
-      mbar_init_a(sb + GK_DPT_FULL + 8 * s, 1);
-      mbar_init_a(sb + GK_PT_FULL + 8 * s, 128);
-      mbar_init_a(sb + GK_DST_FULL + 8 * s, 128);
     }
+    mbar_init_a(sb + GK_ST_FULL, 1);
+    mbar_init_a(sb + GK_DPT_FULL, 1);
+    mbar_init_a(sb + GK_PT_FULL, GK_COMPUTE);
+    mbar_init_a(sb + GK_DST_FULL, GK_COMPUTE);
     mbar_init_a(sb + GK_ACC_DONE, 1);
     fence_barrier_init();
   }
@@ -908,257 +937,232 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sb + GK_TMEM_PTR) : "memory");
-  // TMEM columns: S^T 0..127 (query half h at 64 h; its P^T bf16 over the first 32 of them) | dP^T 128..255 (dS^T alike)
-  //               | dV 256..383 | dK 384..511
+  // TMEM columns: S^T 0..127 | dP^T 128..255 | dV 256..383 | dK 384..511; thread (key row, part p) owns columns 32 p .. 32 p + 31
+  // of S^T and dP^T and writes its 32 P^T / dS^T values (bf16 pairs) over the first 16 of them.
+  // g = iterations taken by this CTA so far, nl = items with work so far: stages and mbarrier phases run on across items.
 
   if (warp == 0) {
     if (elect_one()) {                                     // ---------------- TMA producer
-      mbar_arrive_expect_tx_a(sb + GK_KV_FULL, 2 * GQ_TILE_BYTES);
-      gq_issue_tile(sb + GK_OFF_K, &tmK, sb + GK_KV_FULL, hkv, kt * GQ_T, b);
-      gq_issue_tile(sb + GK_OFF_V, &tmV, sb + GK_KV_FULL, hkv, kt * GQ_T, b);
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it & 1;
-        const int hq = hkv * G + it / n_q_local, i = kt + it % n_q_local;
-        if (it >= 2) mbar_wait_a(sb + GK_QDO_EMPTY + 8 * s, ((it >> 1) - 1) & 1);
-        mbar_arrive_expect_tx_a(sb + GK_QDO_FULL + 8 * s, 2 * GQ_TILE_BYTES);
-        gq_issue_tile(sb + GK_OFF_Q + s * GQ_TILE_BYTES, &tmQ, sb + GK_QDO_FULL + 8 * s, hq, i * GQ_T, b);
-        gq_issue_tile(sb + GK_OFF_DO + s * GQ_TILE_BYTES, &tmDO, sb + GK_QDO_FULL + 8 * s, hq, i * GQ_T, b);
+      int g = 0, nl = 0;
+      for (int r = 0; r < rounds; ++r) {
+        GkItem it;
+        if (!gk_item(r, nq, Hkv, B, it)) continue;
+        const int n_it = iters_of(it);
+        if (n_it == 0) continue;
+        const int n_q_local = nq - it.kt;
+        if (nl >= 1) mbar_wait_a(sb + GK_KV_EMPTY, (nl - 1) & 1);   // the previous item's last S^T / dP^T have read K / V
+        mbar_arrive_expect_tx_a(sb + GK_KV_FULL, 2 * GQ_TILE_BYTES);
+        gq_issue_tile(sb + GK_OFF_K, &tmK, sb + GK_KV_FULL, it.hkv, it.kt * GQ_T, it.b);
+        gq_issue_tile(sb + GK_OFF_V, &tmV, sb + GK_KV_FULL, it.hkv, it.kt * GQ_T, it.b);
+        for (int t = 0; t < n_it; ++t, ++g) {
+          const int s = g & 1;
+          const int hq = it.hkv * G + t / n_q_local, i = it.kt + t % n_q_local;
+          if (g >= 2) mbar_wait_a(sb + GK_QDO_EMPTY + 8 * s, ((g >> 1) - 1) & 1);
+          mbar_arrive_expect_tx_a(sb + GK_QDO_FULL + 8 * s, 2 * GQ_TILE_BYTES);
+          gq_issue_tile(sb + GK_OFF_Q + s * GQ_TILE_BYTES, &tmQ, sb + GK_QDO_FULL + 8 * s, hq, i * GQ_T, it.b);
+          gq_issue_tile(sb + GK_OFF_DO + s * GQ_TILE_BYTES, &tmDO, sb + GK_QDO_FULL + 8 * s, hq, i * GQ_T, it.b);
+        }
+        ++nl;
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    mbar_wait_a(sb + GK_KV_FULL, 0);
-    // Per query half h the chain is  S^T -> (P^T) -> dV -> next S^T   and   dP^T -> (dS^T) -> dK -> next dP^T : the
-    // products that overwrite a region are issued behind the ones that read it (tensor-core operations of one thread
-    // execute in issue order), and the two halves' chains interleave on the tensor pipe.
     const uint32_t k_lo = gq_desc_kmajor(sb + GK_OFF_K), v_lo = gq_desc_kmajor(sb + GK_OFF_V), q_lo = gq_desc_kmajor(sb + GK_OFF_Q),
                    do_lo = gq_desc_kmajor(sb + GK_OFF_DO), qmn_lo = gq_desc_mnmajor(sb + GK_OFF_Q),
                    domn_lo = gq_desc_mnmajor(sb + GK_OFF_DO);
     constexpr uint32_t STAGE = GQ_TILE_BYTES >> 4;
-    auto issue_s = [&](int it, auto hc) {                  // S^T = K Q^T for query half h of tile it
-      constexpr int h = decltype(hc)::value;
-      const int s = it & 1;
-      if (h == 0) mbar_wait_a(sb + GK_QDO_FULL + 8 * s, (it >> 1) & 1);
+    auto issue_s = [&](int g) {                            // S^T = K Q^T (behind dV_{g-1}, which reads P^T_{g-1} from the same columns)
+      const int s = g & 1;
+      mbar_wait_a(sb + GK_QDO_FULL + 8 * s, (g >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        gq_mma_kk<64, h>(tmem_base + h * 64, k_lo, q_lo + s * STAGE, false);
-        umma_commit_a(sb + GK_ST_FULL + 8 * h);
+        gq_mma_kk<128, 0>(tmem_base, k_lo, q_lo + s * STAGE, false);
+        umma_commit_a(sb + GK_ST_FULL);
       }
       __syncwarp();
     };
-    auto issue_dp = [&](int it, auto hc) {                 // dP^T = V dO^T
-      constexpr int h = decltype(hc)::value;
-      const int s = it & 1;
+    auto issue_dp = [&](int g, bool last_of_item) {        // dP^T = V dO^T (behind dK_{g-1})
+      const int s = g & 1;
       if (elect_one()) {
-        gq_mma_kk<64, h>(tmem_base + 128 + h * 64, v_lo, do_lo + s * STAGE, false);
-        umma_commit_a(sb + GK_DPT_FULL + 8 * h);
+        gq_mma_kk<128, 0>(tmem_base + 128, v_lo, do_lo + s * STAGE, false);
+        umma_commit_a(sb + GK_DPT_FULL);
+        if (last_of_item) umma_commit_a(sb + GK_KV_EMPTY); // no later product of this item reads K / V from shared memory
       }
       __syncwarp();
     };
-    using H0 = std::integral_constant<int, 0>;
-    using H1 = std::integral_constant<int, 1>;
-    issue_s(0, H0{});
-    issue_dp(0, H0{});
-    issue_s(0, H1{});
-    issue_dp(0, H1{});
-#ifdef GQ_CYCLES
-    long long w_pt = 0, w_dst = 0, t_begin = GQC_NOW(), t0;
-#endif
-    auto half_step = [&](int it, auto hc) {
-      constexpr int h = decltype(hc)::value;
-      const int s = it & 1;
-      const bool first = (it == 0) && (h == 0), last = (it == n_it - 1) && (h == 1);
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GK_PT_FULL + 8 * h, it & 1);
-#ifdef GQ_CYCLES
-      w_pt += GQC_NOW() - t0;
-#endif
-      tc_fence_after();
-      if (elect_one())                                     // dV += P^T dO over this half's 64 queries
-        gq_mma_tm<4, h>(tmem_base + 256, tmem_base + h * 64, domn_lo + s * STAGE, !first);
-      __syncwarp();
-      if (it + 1 < n_it) issue_s(it + 1, hc);
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      mbar_wait_a(sb + GK_DST_FULL + 8 * h, it & 1);
-#ifdef GQ_CYCLES
-      w_dst += GQC_NOW() - t0;
-#endif
-      tc_fence_after();
-      if (elect_one()) {                                   // dK += dS^T Q
-        gq_mma_tm<4, h>(tmem_base + 384, tmem_base + 128 + h * 64, qmn_lo + s * STAGE, !first);
-        if (h == 1) umma_commit_a(sb + GK_QDO_EMPTY + 8 * s);
-        if (last) umma_commit_a(sb + GK_ACC_DONE);
-      }
-      __syncwarp();
-      if (it + 1 < n_it) issue_dp(it + 1, hc);
+    // D[tmem 128 x 128] (+)= A[tmem: this iteration's P^T or dS^T, 16 queries = 8 columns per k-step, in the owner's columns]
+    //                        * B[smem tile, 128 query rows = contraction, MN-major]
+    auto issue_acc = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_lo, bool accumulate) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(GQ_T, GQ_T, 0, 1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_ts_lo(d_tmem, a_base + (16 * k / GK_CW) * GK_CW + ((16 * k % GK_CW) >> 1), b_lo + ((2048 * k) >> 4), IDESC,
+                   (k != 0) || accumulate);
     };
-    for (int it = 0; it < n_it; ++it) {
-      half_step(it, H0{});
-      half_step(it, H1{});
+    int g = 0, nl = 0;
+    for (int r = 0; r < rounds; ++r) {
+      GkItem it;
+      if (!gk_item(r, nq, Hkv, B, it)) continue;
+      const int n_it = iters_of(it);
+      if (n_it == 0) continue;
+      mbar_wait_a(sb + GK_KV_FULL, nl & 1);
+      issue_s(g);
+      issue_dp(g, n_it == 1);
+      for (int t = 0; t < n_it; ++t, ++g) {
+        const int s = g & 1;
+        const bool more = t + 1 < n_it;
+        mbar_wait_a(sb + GK_PT_FULL, g & 1);               // (t = 0: also says the previous item's accumulators have been read)
+        tc_fence_after();
+        if (elect_one()) issue_acc(tmem_base + 256, tmem_base, domn_lo + s * STAGE, t != 0);          // dV += P^T dO
+        __syncwarp();
+        if (more) issue_s(g + 1);
+        mbar_wait_a(sb + GK_DST_FULL, g & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_acc(tmem_base + 384, tmem_base + 128, qmn_lo + s * STAGE, t != 0);                     // dK += dS^T Q
+          umma_commit_a(sb + GK_QDO_EMPTY + 8 * s);
+          if (!more) umma_commit_a(sb + GK_ACC_DONE);
+        }
+        __syncwarp();
+        if (more) issue_dp(g + 1, t + 2 == n_it);
+      }
+      ++nl;
     }
-#ifdef GQ_CYCLES
-    if (lane == 0) {
-      GQC_ADD(32, 2 * n_it);
-      GQC_ADD(33, GQC_NOW() - t_begin);
-      GQC_ADD(34, w_pt);
-      GQC_ADD(35, w_dst);
-    }
-#endif
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ P^T, dS^T: lane = key row, columns = queries
-    const int h = (warp - 4) >> 2;                         // this group's query half
+    const int part = (warp - 4) >> 2;
     const uint32_t row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem_base + ((row & ~31u) << 16);
-    const int kv_glob = kt * GQ_T + static_cast<int>(row);
-    const bool key_ok = kv_glob < kvl;
-    const int tg = threadIdx.x - 128 - 128 * h;            // 0..127 inside the group
+    const int tid_c = threadIdx.x - 128;
     const unsigned long long c2 = pk2(scale_log2, scale_log2);
-    const uint32_t stat_base = sb + GK_OFF_STAT + h * (2 * GQ_T * 4);
-    auto load_stat = [&](int it) -> float {                // -lse (threads 0..63) / -D (64..127) of this half's queries
-      const int hq = hkv * G + it / n_q_local, i = kt + it % n_q_local;
-      const int qi = i * GQ_T + 64 * h + (tg & 63);
-      const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + min(qi, S - 1);
-      float v = (tg < 64) ? -lse[stat] : -dsum[stat];
-      if (qi >= S) v = (tg < 64) ? -INFINITY : 0.f;        // rows past S: p = 2^(-inf) = 0
-      return v;
-    };
-    float stat_next = load_stat(0);
-#ifdef GQ_CYCLES
-    long long w_bar = 0, w_st = 0, w_dpt = 0, c_p = 0, c_ds = 0, t_begin = GQC_NOW(), t0, t1;
-#endif
-    for (int it = 0; it < n_it; ++it) {
-      const int s = it & 1;
-      const int i = kt + it % n_q_local;
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-#endif
-      sts_f32(stat_base + s * (GQ_T * 4) + tg * 4, stat_next);
-      if (it + 1 < n_it) stat_next = load_stat(it + 1);
-      named_bar_sync(GQ_BAR_EXCH + h, 128);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      w_bar += t1 - t0;
-#endif
-      mbar_wait_a(sb + GK_ST_FULL + 8 * h, it & 1);
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-      w_st += t0 - t1;
-#endif
-      tc_fence_after();
-      const int q0 = i * GQ_T + 64 * h;                    // first query column of this half
-      const bool edge = (i == kt);                         // diagonal tile: query < key is masked
-      const uint32_t st_nl = stat_base + s * (GQ_T * 4), st_nd = st_nl + 64 * 4;
-      unsigned long long p2[32];                           // this row's 64 probabilities, fp32 pairs
+    int g = 0, nl = 0;
+    for (int r = 0; r < rounds; ++r) {
+      GkItem item;
+      if (!gk_item(r, nq, Hkv, B, item)) continue;
+      const int kt = item.kt, hkv = item.hkv, b = item.b;
+      const int kvl = max(1, min(S, kv_len ? kv_len[b] : S));
+      const int kv_glob = kt * GQ_T + static_cast<int>(row);
+      const size_t o = ((static_cast<size_t>(b) * S + kv_glob) * Hkv + hkv) * GQ_T + part * GK_CW;
+      const int n_it = iters_of(item);
+      if (n_it == 0) {                                     // every key of this tile is padding: zero gradients
+        if (kv_glob < S) {
+          const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sv[32], pt[16];
-        tmem_ld_32x32(tlane + h * 64 + c * 32, sv);
-        tmem_ld_wait();
+          for (int u = 0; u < GK_CW / 8; ++u) {
+            reinterpret_cast<uint4*>(dk + o)[u] = z;
+            reinterpret_cast<uint4*>(dv + o)[u] = z;
+          }
+        }
+        continue;
+      }
+      const int n_q_local = nq - kt;
+      const bool key_ok = kv_glob < kvl;
+      auto load_stat = [&](int t) -> float {               // -lse (threads 0..127) / -D (128..255) of iteration t's queries
+        const int hq = hkv * G + t / n_q_local, i = kt + t % n_q_local;
+        const int qi = i * GQ_T + (tid_c & 127);
+        const size_t stat = (static_cast<size_t>(b) * Hq + hq) * S + min(qi, S - 1);
+        float v = (tid_c < 128) ? -lse[stat] : -dsum[stat];
+        if (qi >= S) v = (tid_c < 128) ? -INFINITY : 0.f;  // rows past S: p = 2^(-inf) = 0
+        return v;
+      };
+      float stat_next = (tid_c < 256) ? load_stat(0) : 0.f;
+      for (int t = 0; t < n_it; ++t, ++g) {
+        const int s = g & 1;
+        const int i = kt + t % n_q_local;
+        if (tid_c < 256) {
+          sts_f32(sb + GK_OFF_STAT + s * (2 * GQ_T * 4) + tid_c * 4, stat_next);
+          if (t + 1 < n_it) stat_next = load_stat(t + 1);
+        }
+        named_bar_sync(GQ_BAR_EXCH, GK_COMPUTE);
+        const int q0 = i * GQ_T + part * GK_CW;            // first query column of this thread
+        const uint32_t st_nl = sb + GK_OFF_STAT + s * (2 * GQ_T * 4) + part * (GK_CW * 4), st_nd = st_nl + GQ_T * 4;
+        float pf[GK_CW];                                   // this thread's probabilities
+        mbar_wait_a(sb + GK_ST_FULL, g & 1);
+        tc_fence_after();
+        {
+          uint32_t sv[32], pt[16];
+          tmem_ld_32x32(tlane + part * GK_CW, sv);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          unsigned long long nl_a, nl_b;
-          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nl_a), "=l"(nl_b) : "r"(st_nl + (c * 32 + k) * 4));
+          for (int k = 0; k < 32; k += 4) {
+            unsigned long long nl_a, nl_b;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nl_a), "=l"(nl_b) : "r"(st_nl + k * 4));
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kk = k + 2 * u;
-            const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[kk]), __uint_as_float(sv[kk + 1])), c2, u ? nl_b : nl_a);
-            float x0, x1;
-            unpk2(x2, x0, x1);
-            float p0 = ex2f(x0), p1 = ex2f(x1);
-            if (edge || !key_ok) {
-              const int qg = q0 + c * 32 + kk;
-              if (qg < kv_glob || !key_ok) p0 = 0.f;
-              if (qg + 1 < kv_glob || !key_ok) p1 = 0.f;
+            for (int u = 0; u < 2; ++u) {
+              const int kk = k + 2 * u;
+              const unsigned long long x2 = ffma2(pk2(__uint_as_float(sv[kk]), __uint_as_float(sv[kk + 1])), c2, u ? nl_b : nl_a);
+              if (((kk >> 1) % GQ_POLY_DEN) < GQ_POLY_NUM) {
+                poly_exp2_pair<true>(x2, pf[kk], pf[kk + 1]);   // (masked entries can be large: clamped, then zeroed below)
+              } else {
+                float x0, x1;
+                unpk2(x2, x0, x1);
+                pf[kk] = ex2f(x0);
+                pf[kk + 1] = ex2f(x1);
+              }
             }
-            pt[kk >> 1] = pack_bf16(p0, p1);
-            p2[c * 16 + (kk >> 1)] = pk2(p0, p1);
           }
+          if (i == kt || !key_ok) {                        // diagonal tile: query < key is masked; padded keys: everything
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (q0 + k < kv_glob || !key_ok) pf[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) pt[k >> 1] = pack_bf16(pf[k], pf[k + 1]);
+          tmem_st_32x16(tlane + part * GK_CW, pt);         // over columns this thread has read; nobody else touches them
         }
-        // P^T overwrites the first 32 columns of this thread's own S^T row half (columns it has already read; no other
-        // thread touches them)
-        tmem_st_32x16(tlane + h * 64 + c * 16, pt);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_a(sb + GK_PT_FULL);
+        mbar_wait_a(sb + GK_DPT_FULL, g & 1);
+        tc_fence_after();
+        {
+          uint32_t dp[32], ds[16];
+          tmem_ld_32x32(tlane + 128 + part * GK_CW, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            unsigned long long nd_a, nd_b;
+            asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nd_a), "=l"(nd_b) : "r"(st_nd + k * 4));
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int kk = k + 2 * u;
+              const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[kk]), __uint_as_float(dp[kk + 1])), u ? nd_b : nd_a);
+              const unsigned long long d2 = fmul2(pk2(pf[kk], pf[kk + 1]), t2);
+              float d0, d1;
+              unpk2(d2, d0, d1);
+              ds[kk >> 1] = pack_bf16(d0, d1);             // (the 1/sqrt(d) factor is applied to dK at the end)
+            }
+          }
+          tmem_st_32x16(tlane + 128 + part * GK_CW, ds);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive_a(sb + GK_DST_FULL);
       }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive_a(sb + GK_PT_FULL + 8 * h);
-#ifdef GQ_CYCLES
-      t1 = GQC_NOW();
-      c_p += t1 - t0;
-#endif
-      mbar_wait_a(sb + GK_DPT_FULL + 8 * h, it & 1);
-#ifdef GQ_CYCLES
-      t0 = GQC_NOW();
-      w_dpt += t0 - t1;
-#endif
+      mbar_wait_a(sb + GK_ACC_DONE, nl & 1);
+      ++nl;
       tc_fence_after();
+      const bool live = kv_glob < S;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t dp[32], ds[16];
-        tmem_ld_32x32(tlane + 128 + h * 64 + c * 32, dp);
-        tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-          unsigned long long nd_a, nd_b;
-          asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(nd_a), "=l"(nd_b) : "r"(st_nd + (c * 32 + k) * 4));
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kk = k + 2 * u;
-            const unsigned long long t2 = fadd2(pk2(__uint_as_float(dp[kk]), __uint_as_float(dp[kk + 1])), u ? nd_b : nd_a);
-            const unsigned long long d2 = fmul2(p2[c * 16 + (kk >> 1)], t2);
-            float d0, d1;
-            unpk2(d2, d0, d1);
-            ds[kk >> 1] = pack_bf16(d0, d1);               // (the 1/sqrt(d) factor is applied to dK at the end)
-          }
-        }
-        tmem_st_32x16(tlane + 128 + h * 64 + c * 16, ds);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive_a(sb + GK_DST_FULL + 8 * h);
-#ifdef GQ_CYCLES
-      c_ds += GQC_NOW() - t0;
-#endif
-    }
-#ifdef GQ_CYCLES
-    if (lane == 0 && (warp & 3) == 0) {                    // one warp per group
-      GQC_ADD(40, n_it);
-      GQC_ADD(41, GQC_NOW() - t_begin);
-      GQC_ADD(42, w_bar);
-      GQC_ADD(43, w_st);
-      GQC_ADD(44, c_p);
-      GQC_ADD(45, w_dpt);
-      GQC_ADD(46, c_ds);
-    }
-#endif
-    mbar_wait_a(sb + GK_ACC_DONE, 0);
-    tc_fence_after();
-    const bool live = kv_glob < S;
-    const size_t o = ((static_cast<size_t>(b) * S + kv_glob) * Hkv + hkv) * GQ_T + h * 64;
-#pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      uint4* dst = reinterpret_cast<uint4*>((which == 0 ? dv : dk) + o);
-      const float f = which == 0 ? 1.0f : scale;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tlane + 256 + which * 128 + h * 64 + c * 32, r);
+      for (int which = 0; which < 2; ++which) {
+        uint4* dst = reinterpret_cast<uint4*>((which == 0 ? dv : dk) + o);
+        const float f = which == 0 ? 1.0f : scale;
+        uint32_t rr[32];
+        tmem_ld_32x32(tlane + 256 + which * 128 + part * GK_CW, rr);
         tmem_ld_wait();
         if (live) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint4 v;
-            v.x = pack_bf16(__uint_as_float(r[8 * u]) * f, __uint_as_float(r[8 * u + 1]) * f);
-            v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * f, __uint_as_float(r[8 * u + 3]) * f);
-            v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * f, __uint_as_float(r[8 * u + 5]) * f);
-            v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * f, __uint_as_float(r[8 * u + 7]) * f);
-            dst[c * 4 + u] = v;
+            v.x = pack_bf16(__uint_as_float(rr[8 * u]) * f, __uint_as_float(rr[8 * u + 1]) * f);
+            v.y = pack_bf16(__uint_as_float(rr[8 * u + 2]) * f, __uint_as_float(rr[8 * u + 3]) * f);
+            v.z = pack_bf16(__uint_as_float(rr[8 * u + 4]) * f, __uint_as_float(rr[8 * u + 5]) * f);
+            v.w = pack_bf16(__uint_as_float(rr[8 * u + 6]) * f, __uint_as_float(rr[8 * u + 7]) * f);
+            dst[u] = v;
           }
         }
       }
+      tc_fence_before();                                   // (the next item's first dV is issued only after every thread's P^T)
     }
   }
   tc_fence_before();
@@ -1177,16 +1181,16 @@ int launch_gqa_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     attr_set = true;
   }
   const long long rows = static_cast<long long>(B) * S * Hq;
-  gqa_rowdot_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+  gqa_rowdot_kernel<<<static_cast<unsigned>(std::min<long long>((rows + 63) / 64, 8LL * gq_num_sms())), 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(d_out), dsum_ws, B, S, Hq);
   AL_CHECK_CUDA(cudaGetLastError());
   const int nt = (S + GQ_T - 1) / GQ_T;
   gqa_bwd_dq_kernel<<<std::min(nt * Hq * B, gq_num_sms()), GD_THREADS, GD_SMEM, stream>>>(tq, tk, tv, tdo, tdq, lse, dsum_ws, kv_len,
                                                                                           B, S, Hq, Hkv, scale);
   AL_CHECK_CUDA(cudaGetLastError());
-  gqa_bwd_dkv_kernel<<<dim3(Hkv, B, nt), GK_THREADS, GK_SMEM, stream>>>(tq, tk, tv, tdo, lse, dsum_ws, kv_len,
-                                                                         reinterpret_cast<__nv_bfloat16*>(dk),
-                                                                         reinterpret_cast<__nv_bfloat16*>(dv), S, Hq, Hkv, scale);
+  gqa_bwd_dkv_kernel<<<std::min(nt * Hkv * B, gq_num_sms()), GK_THREADS, GK_SMEM, stream>>>(
+      tq, tk, tv, tdo, lse, dsum_ws, kv_len, reinterpret_cast<__nv_bfloat16*>(dk), reinterpret_cast<__nv_bfloat16*>(dv), B, S, Hq, Hkv,
+      scale);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,19 +1,22 @@
-"""LLaMA-side native ops (first slice): RMSNorm, SwiGLU, rotary embedding and the lm_head +
-cross-entropy tail of the HF LlamaForCausalLM that the reference drives (/root/reference/src/models/allm.py:99-104),
-as hand-written sm_100a kernels with their backward, wired in through torch.autograd.Function.
+"""LLaMA-side native ops: RMSNorm, SwiGLU, rotary embedding, causal GQA attention (forward and
+backward), the frozen linears and the lm_head + cross-entropy tail of the HF LlamaForCausalLM that the reference drives
+(/root/reference/src/models/allm.py:99-104), as hand-written sm_100a kernels wired in through torch.autograd.Function.
 
-`enable(audio_llm)` patches the LLaMA inside an AudioLLM in place (opt-in; the module API stays the reference's):
+`enable(audio_llm)` patches the LLaMA inside an AudioLLM in place (the module API stays the reference's):
   * every LlamaRMSNorm.forward          -> al_rmsnorm_forward / _backward         (weight frozen: dx only)
   * every LlamaMLP.forward              -> gate / up / down linears unchanged (fused LoRA when enabled), the
                                            `act_fn(gate) * up` between them -> al_swiglu_forward / _backward
   * modeling_llama.apply_rotary_pos_emb -> al_rope (forward and transposed rotation for the gradient)
-  * right-padded attention masks        -> dropped (causal attention already hides the padding from every real token;
-                                           HF then takes SDPA's is_causal path instead of a dense additive bias)
+  * every LlamaAttention.forward        -> q/k/v projections -> al_rope -> al_gqa_attention_forward / _backward -> o_proj
+                                           (head_dim 128, causal + right-padding masks: `attention_plan`; anything else
+                                           keeps HF's forward)
+  * every LlamaDecoderLayer.forward     -> `_layer_forward`: the same pieces with the residual adds inside the o_proj /
+                                           down_proj GEMM epilogues and the gradient sums inside the dgrad GEMMs / the RMSNorm
+                                           backward (no elementwise kernels, no autograd accumulation passes)
   * nn.Linear without LoRA (o_proj, lm_head) -> the tcgen05 GEMM forward and dgrad (frozen weights)
   * the loss (labels given)             -> al_linear_ce: lm_head + cross-entropy per chunk of rows, never forming the
                                            [tokens, vocab] logits (HF upcasts them to fp32: 8 GB at the README batch);
                                            `outputs.logits` is None in that mode.
-Attention itself stays HF's (SDPA / cuDNN flash): library code, like the GEMMs HF calls.
 There is no CPU fallback: inputs that are not bf16 CUDA tensors go to the module's original forward.
 """
 from __future__ import annotations
