@@ -47,7 +47,9 @@ constexpr float GQ_TAU = 8.0f;                 // lazy-rescale threshold of the 
 constexpr int GQ_BAR_EXCH = 1;                 // named barrier of the compute threads
 constexpr float LOG2E_GQ = 1.4426950408889634f;
 
-// -DGQ_CYCLES: per-role cycle accounting (development builds only; tools/bench_gqa_attention.py CYCLES=1 reads it back)
+// -DGQ_CYCLES: cycle accounting by one compute warp per CTA (development builds only: tools/build_gqa_cycles.sh;
+// tools/bench_gqa_attention.py CYCLES=1 reads it back). Slots per kernel (forward 0.., dQ 16.., dK/dV 32..):
+// [0] kv-tile steps, [1] cycles inside the tile loops, [2] cycles between tile loops (epilogue + next item's set-up), [3] items.
 #ifdef GQ_CYCLES
 __device__ unsigned long long gq_cyc[64];
 #define GQC_DECL(...) long long __VA_ARGS__
@@ -325,6 +327,9 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     };
     int g = 0;
     bool first = true;
+#ifdef GQ_CYCLES
+    long long tq_prev = 0;
+#endif
     for (int r = 0; r < rounds; ++r) {
       GqItem it;
       if (!gq_item(r, nq, Hq, B, it)) continue;
@@ -339,6 +344,10 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         first = false;
       }
       float m_ref = -INFINITY, l = 0.f;
+#ifdef GQ_CYCLES
+      const long long tq0 = GQC_NOW();
+      if (lane == 0 && warp == 4 && tq_prev != 0) GQC_ADD(2, tq0 - tq_prev);
+#endif
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int sbuf = g & 1;
         mbar_wait_a(sb + GF_S_FULL + 8 * sbuf, (g >> 1) & 1);
@@ -426,6 +435,14 @@ gqa_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc_fence_before();
         mbar_arrive_a(sb + GF_P_FULL);
       }
+#ifdef GQ_CYCLES
+      tq_prev = GQC_NOW();
+      if (lane == 0 && warp == 4) {
+        GQC_ADD(0, n_tiles);
+        GQC_ADD(1, tq_prev - tq0);
+        GQC_ADD(3, 1);
+      }
+#endif
       // row sum of all parts; then the next item's Q rows into TMEM (every S of this item has been produced, so no product
       // reads the Q columns any more): the issuer starts the next item's first S under this item's epilogue
       GqItem nx;
@@ -743,6 +760,9 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int g = 0, n_item = 0;
     float neg_lse = 0.f, neg_d = 0.f;
     bool first = true;
+#ifdef GQ_CYCLES
+    long long tq_prev = 0;
+#endif
     for (int r = 0; r < rounds; ++r) {
       GqItem it;
       if (!gq_item(r, nq, Hq, B, it)) continue;
@@ -757,6 +777,10 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         first = false;
       }
       const unsigned long long c2 = pk2(scale_log2, scale_log2), nl2 = pk2(neg_lse, neg_lse), nd2 = pk2(neg_d, neg_d);
+#ifdef GQ_CYCLES
+      const long long tq0 = GQC_NOW();
+      if (lane == 0 && warp == 4 && tq_prev != 0) GQC_ADD(18, tq0 - tq_prev);
+#endif
       for (int j = 0; j < n_tiles; ++j, ++g) {
         mbar_wait_a(sb + GD_S_FULL, g & 1);
         tc_fence_after();
@@ -807,6 +831,14 @@ gqa_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tc_fence_before();
         mbar_arrive_a(sb + GD_DS_FULL);
       }
+#ifdef GQ_CYCLES
+      tq_prev = GQC_NOW();
+      if (lane == 0 && warp == 4) {
+        GQC_ADD(16, n_tiles);
+        GQC_ADD(17, tq_prev - tq0);
+        GQC_ADD(19, 1);
+      }
+#endif
       // Next item's rows: every S and dP of this item has been produced (this thread has seen the last DP_FULL), so the Q
       // and dO columns of TMEM are free; the issuer starts the next item's first products under this item's epilogue.
       GqItem nx;
@@ -1036,6 +1068,9 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int tid_c = threadIdx.x - 128;
     const unsigned long long c2 = pk2(scale_log2, scale_log2);
     int g = 0, nl = 0;
+#ifdef GQ_CYCLES
+    long long tq_prev = 0;
+#endif
     for (int r = 0; r < rounds; ++r) {
       GkItem item;
       if (!gk_item(r, nq, Hkv, B, item)) continue;
@@ -1066,6 +1101,10 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         return v;
       };
       float stat_next = (tid_c < 256) ? load_stat(0) : 0.f;
+#ifdef GQ_CYCLES
+      const long long tq0 = GQC_NOW();
+      if (lane == 0 && warp == 4 && tq_prev != 0) GQC_ADD(34, tq0 - tq_prev);
+#endif
       for (int t = 0; t < n_it; ++t, ++g) {
         const int s = g & 1;
         const int i = kt + t % n_q_local;
@@ -1139,6 +1178,14 @@ gqa_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();
         mbar_arrive_a(sb + GK_DST_FULL);
       }
+#ifdef GQ_CYCLES
+      tq_prev = GQC_NOW();
+      if (lane == 0 && warp == 4) {
+        GQC_ADD(32, n_it);
+        GQC_ADD(33, tq_prev - tq0);
+        GQC_ADD(35, 1);
+      }
+#endif
       mbar_wait_a(sb + GK_ACC_DONE, nl & 1);
       ++nl;
       tc_fence_after();

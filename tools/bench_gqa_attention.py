@@ -74,7 +74,7 @@ if os.environ.get("KERNELS"):                      # per-kernel device times of 
         if "gqa_" in ev.key:
             print(f"  {ev.key[:48]:48s} {ev.device_time_total / ev.count:9.1f} us x {ev.count}")
 
-if os.environ.get("CYCLES"):                       # a -DGQ_CYCLES build (AUDIOLLM_B200_LIB=...): per-role cycle accounts
+if os.environ.get("CYCLES"):                       # a -DGQ_CYCLES build (tools/build_gqa_cycles.sh): cycle accounts of one compute warp
     import ctypes
     lib = ctypes.CDLL(os.environ["AUDIOLLM_B200_LIB"])
     buf = (ctypes.c_ulonglong * 64)()
@@ -82,10 +82,8 @@ if os.environ.get("CYCLES"):                       # a -DGQ_CYCLES build (AUDIOL
     ours_fb()
     lib.al_debug_gqa_cycles(buf, 0)
     v = list(buf)
-    names = {0: "fwd issuer [total wait_P]", 8: "fwd compute [total wait_S max bar exp wait_O store]", 16: "dq issuer [total issue_SdP wait_dS]",
-             24: "dq compute [total wait_SdP math wait_dQ store]", 32: "dkv issuer [total wait_PT wait_dST]",
-             40: "dkv compute [total bar wait_ST P wait_dPT dS]",
-             48: "fwd per CTA [entry->loop, loop, entry->stores done, entry->exit]"}
-    for base, nm in names.items():
-        if v[base]:
-            print(f"  {nm}: n={v[base]}  per-unit cycles: " + " ".join(f"{x / v[base]:.0f}" for x in v[base + 1:base + 8]))
+    for base, nm in ((0, "forward"), (16, "dQ"), (32, "dK/dV")):
+        steps, in_loop, between, items = v[base:base + 4]
+        if steps:
+            print(f"  {nm:8s} {items} items, {steps} kv-tile steps: {in_loop / steps:7.0f} cycles per step inside the tile loops, "
+                  f"{between / max(items, 1):7.0f} cycles per item between them")
