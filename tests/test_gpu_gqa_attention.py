@@ -44,7 +44,10 @@ def test_gqa_forward(B, S, Hq, Hkv, kv_len):
 
 
 @pytest.mark.parametrize("B,S,Hq,Hkv,kv_len", [(1, 128, 1, 1, None), (2, 300, 4, 2, None), (1, 1000, 6, 2, [700]),
-                                               (2, 515, 3, 1, [515, 130]), (1, 2014, 6, 2, None)])
+                                               (2, 515, 3, 1, [515, 130]), (1, 2014, 6, 2, None),
+                                               # more work items than SMs in all three persistent kernels (288 / 288 / 192),
+                                               # with fully padded kv tiles in the middle of a CTA's item list
+                                               (4, 700, 16, 8, [700, 130, 5, 384])])
 def test_gqa_backward(B, S, Hq, Hkv, kv_len):
     q, k, v = make(B, S, Hq, Hkv, seed=7 * S + Hq, spread=1.2)
     scale = 128 ** -0.5
@@ -65,6 +68,27 @@ def test_gqa_backward(B, S, Hq, Hkv, kv_len):
         for b, n in enumerate(kv_len):
             assert float(kc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
             assert float(vc.grad[b, n:].abs().max() if n < S else 0.0) == 0.0
+
+
+def test_gqa_persistent_kernels_are_deterministic_across_item_schedules():
+    """The persistent kernels walk their item lists in a serpentine order over the SMs; a tile's result must not depend
+    on which CTA took it or on what that CTA did before: the same rows computed alone (few items) and inside a large
+    batch (many items per CTA) are bit-identical, forward and backward."""
+    B, S, Hq, Hkv = 6, 900, 12, 4
+    q, k, v = make(B, S, Hq, Hkv, seed=5)
+    d_out = torch.randn(B, S, Hq, 128, generator=torch.Generator().manual_seed(2)).bfloat16()
+    scale = 128 ** -0.5
+
+    def run(sl):
+        qc, kc, vc = (t[sl].contiguous().cuda().requires_grad_(True) for t in (q, k, v))
+        out = LN.gqa_attention(qc, kc, vc, None, scale)
+        out.backward(d_out[sl].contiguous().cuda())
+        return out.detach().cpu(), qc.grad.cpu(), kc.grad.cpu(), vc.grad.cpu()
+
+    big = run(slice(0, B))
+    one = run(slice(3, 4))
+    for a, b_ in zip(big, one):
+        assert torch.equal(a[3:4], b_)
 
 
 def test_native_attention_inside_audio_llm_matches_hf_with_padding():
