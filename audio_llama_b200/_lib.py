@@ -59,6 +59,7 @@ SIGNATURES = {
     "al_lora_linear_forward": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
     "al_lora_linear_backward_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "al_lora_linear_backward": (i32, [vp, vp, i32, i32, i32, i32] + [vp] * 9),
+    "al_lora_pack": (i32, [vp, vp, i32, i32, i32, f32, vp, vp, vp]),
     "al_lora_linear_forward_ex": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     "al_lora_linear_backward_ex": (i32, [vp, vp, i32, i32, i32, i32] + [vp] * 10),
     "al_linear_add_bf16": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),

@@ -1021,6 +1021,16 @@ int al_projector_backward(const void* x, int rows, int d_in, int hidden, int d_o
 }
 
 // ----------------------------------------------------------------------------- LoRA linear
+int al_lora_pack(const float* lora_A, const float* lora_B, int rank, int in_dim, int out_dim, float scaling, void* a_pad,
+                 void* b_scaled_pad, al_stream_t stream) {
+  AL_REQUIRE(lora_A && lora_B && a_pad && b_scaled_pad, "al_lora_pack: NULL argument");
+  AL_REQUIRE(rank > 0 && in_dim > 0 && out_dim > 0, "al_lora_pack: bad shape rank=%d in=%d out=%d", rank, in_dim, out_dim);
+  int rc = launch_lora_pack(lora_A, lora_B, rank, (rank + 7) / 8 * 8, in_dim, out_dim, scaling, a_pad, b_scaled_pad,
+                            (cudaStream_t)stream);
+  if (rc == 0) g_launches += 1;
+  return rc;
+}
+
 int al_linear_add_bf16(const void* x, int rows, int in_dim, int out_dim, const void* W, const float* bias, const void* addend,
                        void* out, al_stream_t stream) {
   AL_REQUIRE(x && W && out && addend, "al_linear_add_bf16: NULL argument");
@@ -1104,8 +1114,12 @@ int al_lora_linear_backward_ex(const void* x, const void* dy, int rows, int in_d
   void* AT = take((size_t)in_dim * rank * 2);
   void* U = take((size_t)rows * rank * 2);
 
-  AL_CHECK_CUDA(cudaMemsetAsync(dA, 0, (size_t)rank * in_dim * 4, st));
-  AL_CHECK_CUDA(cudaMemsetAsync(dB_raw, 0, (size_t)out_dim * rank * 4, st));
+  if (dB_raw == dA + (size_t)rank * in_dim) {          // one allocation holding both (audio_llama_b200/ops.py): one memset
+    AL_CHECK_CUDA(cudaMemsetAsync(dA, 0, ((size_t)rank * in_dim + (size_t)out_dim * rank) * 4, st));
+  } else {
+    AL_CHECK_CUDA(cudaMemsetAsync(dA, 0, (size_t)rank * in_dim * 4, st));
+    AL_CHECK_CUDA(cudaMemsetAsync(dB_raw, 0, (size_t)out_dim * rank * 4, st));
+  }
   int rc;
 #define STEP(expr) do { rc = (expr); if (rc) return rc; g_launches += 1; } while (0)
   // 1. U = dy (sB): the weight operand is (sB)^T [rank][out]

@@ -86,6 +86,8 @@ int launch_splice_ragged(const void* table, int elem_bytes, int d, const long lo
                          cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, void* out, long long n, cudaStream_t stream);
 int launch_transpose_bf16(const void* in, void* out, int R, int C, int out_ld, cudaStream_t stream);
+int launch_lora_pack(const float* A, const float* Bm, int rank, int r_pad, int in_dim, int out_dim, float scaling, void* a_pad,
+                     void* b_pad, cudaStream_t stream);
 int launch_layernorm_bwd(const float* y, const float* dout, const float* gamma, void* dy_bf16, float* dgamma,
                          float* dbeta, float* dbias, int rows, int d, float eps, cudaStream_t stream);
 int launch_colsum_bf16(const void* x, float* out, int rows, int n, cudaStream_t stream);

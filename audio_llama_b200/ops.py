@@ -251,6 +251,13 @@ def pack_lora(lora_a: torch.Tensor, lora_b: torch.Tensor, scaling: float):
     r, in_dim = lora_a.shape
     out_dim = lora_b.shape[0]
     r_pad = (r + 7) // 8 * 8
+    if lora_a.is_cuda and lora_a.dtype == torch.float32 and lora_b.dtype == torch.float32 and lora_a.is_contiguous() \
+            and lora_b.is_contiguous():
+        a = torch.empty(r_pad, in_dim, dtype=torch.bfloat16, device=lora_a.device)
+        b = torch.empty(out_dim, r_pad, dtype=torch.bfloat16, device=lora_b.device)
+        check(lib().al_lora_pack(ptr(lora_a.detach()), ptr(lora_b.detach()), r, in_dim, out_dim, float(scaling), ptr(a), ptr(b),
+                                 stream_ptr()), "al_lora_pack")
+        return a, b
     a = torch.zeros(r_pad, in_dim, dtype=torch.bfloat16, device=lora_a.device)
     a[:r] = lora_a.detach().to(torch.bfloat16)
     b = torch.zeros(out_dim, r_pad, dtype=torch.bfloat16, device=lora_b.device)
@@ -317,8 +324,9 @@ def lora_linear_backward(x: torch.Tensor, dy: torch.Tensor, w_t: Optional[torch.
             dx = _req(dx_accumulate, torch.bfloat16, "dx_accumulate").view(rows, in_dim)
         else:
             dx = torch.empty_like(x2)
-    dA = torch.empty(r_pad, in_dim, dtype=torch.float32, device=x.device)
-    dB = torch.empty(out_dim, r_pad, dtype=torch.float32, device=x.device)
+    dAB = torch.empty(r_pad * in_dim + out_dim * r_pad, dtype=torch.float32, device=x.device)   # (one memset for both)
+    dA = dAB[:r_pad * in_dim].view(r_pad, in_dim)
+    dB = dAB[r_pad * in_dim:].view(out_dim, r_pad)
     check(lib().al_lora_linear_backward_ex(ptr(x2), ptr(dy2), rows, in_dim, out_dim, r_pad, ptr(w_t) if need_dx else None,
                                            ptr(a_pad), ptr(b_scaled_pad), ptr(t_saved), ptr(ws),
                                            ptr(dx) if (need_dx and dx_accumulate is not None) else None, ptr(dx), ptr(dA),

@@ -199,6 +199,10 @@ int al_lora_linear_forward(const void* x, int rows, int in_dim, int out_dim, int
  * dA = U^T x [rank][in] f32; dB_raw = dy^T T [out][rank] f32 with T = x A^T saved by the forward (t_ws) — the
  * gradient of the UNSCALED lora_B is scaling * dB_raw, and dA already carries the scaling through U.
  * W_T is the frozen weight transposed, [in][out] bf16 (transposed once by the caller, it never changes). */
+/* The fused GEMM's LoRA operands from the fp32 parameters of lora.py's LoRALayer in one launch: a_pad [round8(rank)][in]
+ * bf16 = A (padding rows zero), b_scaled_pad [out][round8(rank)] bf16 = scaling * B (padding columns zero). */
+int al_lora_pack(const float* lora_A, const float* lora_B, int rank, int in_dim, int out_dim, float scaling, void* a_pad,
+                 void* b_scaled_pad, al_stream_t stream);
 size_t al_lora_linear_backward_workspace_bytes(int rows, int in_dim, int out_dim, int rank);
 /* The _ex forms fold an elementwise add into the GEMM epilogue (what HF's LlamaDecoderLayer.forward writes as
  * `residual + hidden_states`, and what autograd does when several projections share one input):

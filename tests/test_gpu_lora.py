@@ -143,6 +143,25 @@ def test_lora_linear_epilogue_adds(in_dim, out_dim, rank, rows):
     assert O.rel_l2(dA_c.cpu(), 0.5 * dA_a.cpu()) <= 1e-2
 
 
+def test_lora_pack_kernel_is_bit_identical_to_the_torch_formula():
+    """al_lora_pack (one launch) == zero-padded bf16(A), bf16(scaling * B) built with torch ops; non-fp32 parameters keep
+    the torch path."""
+    g = torch.Generator().manual_seed(9)
+    for rank, in_dim, out_dim in ((64, 3072, 1024), (12, 256, 520)):
+        A = (torch.randn(rank, in_dim, generator=g) * 0.05).cuda()
+        B = (torch.randn(out_dim, rank, generator=g) * 0.05).cuda()
+        scaling = 16 / rank
+        a, b = ops.pack_lora(A, B, scaling)
+        r_pad = (rank + 7) // 8 * 8
+        a_ref = torch.zeros(r_pad, in_dim, dtype=torch.bfloat16, device="cuda")
+        a_ref[:rank] = A.to(torch.bfloat16)
+        b_ref = torch.zeros(out_dim, r_pad, dtype=torch.bfloat16, device="cuda")
+        b_ref[:, :rank] = (B.float() * scaling).to(torch.bfloat16)
+        assert torch.equal(a, a_ref) and torch.equal(b, b_ref)
+        a16, b16 = ops.pack_lora(A.half(), B.half(), scaling)
+        assert a16.shape == a_ref.shape and b16.shape == b_ref.shape
+
+
 def test_fused_and_native_paths_are_the_default_for_bf16_cuda():
     """AudioLLM.to("cuda") with bf16 LLaMA weights switches to the fused frozen+LoRA GEMMs and the native row kernels
     by itself; fp32 weights keep the reference-style hooks. Loss of the default path == loss of the hook path."""
