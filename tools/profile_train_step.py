@@ -24,6 +24,10 @@ print(f"# GPU time of the profiled step: {tot / 1e3:.1f} ms")
 for e in rows[:32]:
     print(f"# {e.device_time_total / 1e3:9.2f} ms {100 * e.device_time_total / tot:5.1f}% x{e.count:<5d} {e.key[:120]}")
 
+print('# most-launched device activities:')
+for e in sorted(prof.key_averages(), key=lambda e: -e.count)[:14]:
+    print(f"#   x{e.count:<5d} {e.device_time_total / 1e3:7.2f} ms  {e.key[:110]}")
+
 # --- where the GPU idles inside the step: gaps between consecutive device activities (kernels / memcpys / memsets)
 evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
 evs.sort(key=lambda e: e.time_range.start)
