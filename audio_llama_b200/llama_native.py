@@ -374,6 +374,22 @@ def gqa_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_len=None
 _ATTN_STATE = {"active": False, "kv_len": None}
 
 
+_STATIC_PLAN = {"on": False}
+
+
+class static_attention_plan:
+    """Context: attention_plan() takes every 2-D mask as right padding WITHOUT reading it on the host (kv_len = count of
+    non-zeros, computed on the device). For callers that have checked their masks once (a fixed synthetic batch, a
+    collate_fn that only pads on the right) and replay the step as a CUDA graph."""
+
+    def __enter__(self):
+        self.prev = _STATIC_PLAN["on"]
+        _STATIC_PLAN["on"] = True
+
+    def __exit__(self, *a):
+        _STATIC_PLAN["on"] = self.prev
+
+
 def attention_plan(attention_mask):
     """(usable, kv_len): the native attention covers causal + right-padding masks. `attention_mask` is the 2-D [B, S]
     mask the reference passes (float after _extend_attention_mask). None -> no padding. A mask that is ones-then-zeros
@@ -382,6 +398,8 @@ def attention_plan(attention_mask):
     mask. One tiny device->host read."""
     if attention_mask is None:
         return True, None
+    if _STATIC_PLAN["on"]:                              # the caller vouches for right padding (no host read: CUDA-graph capture)
+        return True, (attention_mask != 0).sum(dim=1).to(torch.int32).contiguous()
     m = attention_mask
     if m.dim() != 2:
         return False, None

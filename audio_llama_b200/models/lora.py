@@ -64,6 +64,8 @@ def _packed_operands(lora_A, lora_B, scaling):
     """pack_lora(A, B, scaling), repacked after optimizer steps (the parameters' version counters move)."""
     from .. import ops
     global _PACKS
+    if REPACK_ALWAYS:
+        return ops.pack_lora(lora_A, lora_B, scaling)
     if _PACKS is None:
         _PACKS = ops.TensorDerivedCache()
     return _PACKS.get((lora_A, lora_B), lambda: ops.pack_lora(lora_A, lora_B, scaling), extra=scaling)
@@ -71,6 +73,10 @@ def _packed_operands(lora_A, lora_B, scaling):
 
 _PACKS = None
 _WTS = None
+# True: the bf16 operands are rebuilt from the parameters on every forward instead of once per optimizer step. A step that
+# is captured as a CUDA graph needs the pack launches INSIDE the graph (a cache hit at capture time would freeze the
+# LoRA weights of every replay at their captured values).
+REPACK_ALWAYS = False
 
 
 class _FusedLoRALinearFn(torch.autograd.Function):

@@ -218,7 +218,7 @@ def splice(table: torch.Tensor, input_ids: torch.Tensor, attention_mask: Optiona
     check(lib().al_splice(ptr(table), table.element_size(), d, ptr(input_ids), ptr(attention_mask), ptr(labels), B, T,
                           n_audio, start_id, end_id, ptr(audio_rows), ptr(out), ptr(mask_out), ptr(labels_out),
                           vocab, ptr(flag), stream_ptr()), "al_splice")
-    if check_ids:
+    if check_ids and not DEFER_ID_CHECKS:
         raise_if_bad_ids(table.device, vocab)
     return out, mask_out, labels_out
 
@@ -234,6 +234,11 @@ def bad_id_flag(device) -> torch.Tensor:
         f = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
         _bad_id_flags[key] = f
     return f
+
+
+# True: splice() never synchronises to check its ids, whatever check_ids says; the caller reads the flag later through
+# raise_if_bad_ids() (a training step replayed as a CUDA graph cannot read the host inside the step)
+DEFER_ID_CHECKS = False
 
 
 def raise_if_bad_ids(device, vocab=None):

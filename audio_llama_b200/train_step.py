@@ -65,7 +65,7 @@ class TrainStep:
     the backward pass did not hide (the wait inside finish_overlap)."""
 
     def __init__(self, model, ecfg: EncoderConfig, batch: int, dev, rank: int = 0, world: int = 1, t_txt: int = 512,
-                 overlap: bool = True, n_chunks: int = 4, lr: float = 1e-4):
+                 overlap: bool = True, n_chunks: int = 4, lr: float = 1e-4, graph: bool = False):
         from .features import LogMelExtractor
         self.model, self.dev, self.rank, self.world, self.batch = model, dev, rank, world, batch
         vocab = model.llama.model.model.embed_tokens.weight.shape[0]
@@ -81,14 +81,62 @@ class TrainStep:
         self.fe = LogMelExtractor(ecfg.n_mels, device=dev)
         self.clips = [synth.synth_clip(rank * batch + i) for i in range(batch)]
         self.loss = None
+        # graph=True (single GPU): zero + forward + backward are captured ONCE as a CUDA graph and replayed (the ~3000
+        # launches of the step then follow each other without the ~2 us launch gaps); the feature extraction, the gradient
+        # clipping and AdamW stay eager. The two host reads of the forward (attention_plan, the splice id check) are
+        # deferred: the mask is right padding by construction here and the id flag is read after the step.
+        self.graph = None
+        self.want_graph = bool(graph) and world == 1
+        self.graph_error = None
+        self.eager_steps = 0
+
+    def _fwd_bwd(self, feats):
+        self.bucket.zero()
+        out = self.model(input_ids=self.ids, attention_mask=self.mask, audio_features=feats, labels=self.labels)
+        out.loss.backward()
+        return out.loss.detach()
+
+    def _capture(self, feats):
+        """Capture zero + forward + backward on the static inputs. Any failure leaves the eager path in place."""
+        from . import llama_native, ops
+        from .models import lora as lora_mod
+        self.static_feats = feats.clone()
+        g = torch.cuda.CUDAGraph()
+        try:
+            ops.DEFER_ID_CHECKS = True
+            lora_mod.REPACK_ALWAYS = True                # the pack launches must be part of the graph
+            with llama_native.static_attention_plan():
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):               # one more warm-up on the side stream the capture will use
+                    self._fwd_bwd(self.static_feats)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g, stream=s):
+                    self.static_loss = self._fwd_bwd(self.static_feats)
+            self.graph = g
+        except Exception as e:                           # noqa: BLE001
+            self.graph_error = f"{type(e).__name__}: {e}"[:300]
+            self.graph = None
+            self.want_graph = False
+            torch.cuda.synchronize()
+        finally:
+            ops.DEFER_ID_CHECKS = False
+            lora_mod.REPACK_ALWAYS = False
 
     def step(self) -> Dict[str, float]:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
         feats = self.fe(self.clips, sampling_rate=16000).input_features.unsqueeze(1)
-        self.bucket.zero()
-        out = self.model(input_ids=self.ids, attention_mask=self.mask, audio_features=feats, labels=self.labels)
-        out.loss.backward()
+        if self.want_graph and self.graph is None and self.eager_steps >= 2:
+            self._capture(feats)
+        if self.graph is not None:
+            self.static_feats.copy_(feats)
+            self.graph.replay()
+            loss = self.static_loss
+        else:
+            loss = self._fwd_bwd(feats)
+            self.eager_steps += 1
         ev[1].record()
         if self.overlap:
             self.bucket.finish_overlap()
@@ -100,7 +148,10 @@ class TrainStep:
         self.opt.step()
         ev[3].record()
         torch.cuda.synchronize()
-        self.loss = float(out.loss.detach())
+        self.loss = float(loss)
+        if self.graph is not None:
+            from . import ops
+            ops.raise_if_bad_ids(self.dev)               # the id check the captured forward could not do on the host
         return {"step_ms": ev[0].elapsed_time(ev[3]), "fwd_bwd_ms": ev[0].elapsed_time(ev[1]),
                 "exchange_exposed_ms": ev[1].elapsed_time(ev[2]), "optimizer_ms": ev[2].elapsed_time(ev[3])}
 
@@ -124,12 +175,13 @@ class TrainStep:
 
 
 def run_config3(dev, rank: int, world: int, llama: str = "3b", batch: int = 8, steps: int = 3, warmup: int = 1,
-                overlap: bool = True, encoder_weights=None, ecfg: EncoderConfig = WHISPER_LARGE_V3_TURBO) -> Optional[dict]:
+                overlap: bool = True, encoder_weights=None, ecfg: EncoderConfig = WHISPER_LARGE_V3_TURBO,
+                graph: bool = False) -> Optional[dict]:
     """The config-3 record: max-over-ranks step time of `steps` training steps, the exposed and stand-alone exchange
     times and the bus bandwidth. Every rank calls it; rank 0 gets the dict."""
     model = build_model(llama, ecfg, batch, dev, encoder_weights=encoder_weights)
-    ts = TrainStep(model, ecfg, batch, dev, rank, world, overlap=overlap)
-    for _ in range(warmup):
+    ts = TrainStep(model, ecfg, batch, dev, rank, world, overlap=overlap, graph=graph)
+    for _ in range(warmup + (2 if ts.want_graph else 0)):     # (graph mode: two eager steps, then the capture step)
         ts.step()
     recs = []
     for _ in range(steps):
@@ -156,6 +208,7 @@ def run_config3(dev, rank: int, world: int, llama: str = "3b", batch: int = 8, s
         "steps": steps, "warmup": warmup, "step_ms": mean["step_ms"], "step_ms_each": all_steps, "fwd_bwd_ms": mean["fwd_bwd_ms"],
         "optimizer_ms": mean["optimizer_ms"], "audio_s_per_s": world * batch * 30.0 / (mean["step_ms"] / 1e3),
         "trainable_params": ts.bucket.numel, "loss": ts.loss,
+        "cuda_graph": {"requested": bool(graph), "replayed": ts.graph is not None, "error": ts.graph_error},
         "allreduce": {"bytes": nbytes, "overlapped_with_backward": bool(ts.overlap),
                       "chunks": ts.n_chunks,
                       "chunks_launched_during_backward": getattr(ts, "chunks_in_backward", None),

@@ -430,7 +430,8 @@ def run_product(args):
             from audio_llama_b200 import train_step
             del emb_d
             torch.cuda.empty_cache()
-            config3 = train_step.run_config3(dev, rank, world, llama="3b", batch=8, steps=3, warmup=2, encoder_weights=ew)
+            config3 = train_step.run_config3(dev, rank, world, llama="3b", batch=8, steps=3, warmup=2, encoder_weights=ew,
+                                             graph=(world == 1))
         except Exception as e:                                    # noqa: BLE001
             config3 = {"error": f"{type(e).__name__}: {e}"[:300]}
     del ew

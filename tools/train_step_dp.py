@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--no-overlap", action="store_true", help="one all-reduce after backward instead of the overlapped chunks")
+    ap.add_argument("--graph", action="store_true", help="single GPU: replay zero + forward + backward as one CUDA graph")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -38,7 +39,7 @@ def main():
         parallel.init_nccl(dev)
     ecfg = WHISPER_LARGE_V3_TURBO if args.encoder == "turbo" else WHISPER_TINY_128
     rec = train_step.run_config3(dev, rank, world, llama=args.llama, batch=args.batch, steps=args.steps,
-                                 overlap=not args.no_overlap, ecfg=ecfg)
+                                 overlap=not args.no_overlap, ecfg=ecfg, graph=args.graph)
     if rank == 0:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
