@@ -418,3 +418,22 @@ def test_place_audio_rows_autograd():
     with torch.no_grad():
         e2 = emb.clone()
         assert AudioLLM._place(e2, proj, A) is e2 and torch.equal(e2, ref.detach())
+
+
+def test_static_attention_plan_reads_nothing_on_the_host():
+    """attention_plan under static_attention_plan(): kv_len straight from the mask (the caller vouches for right padding),
+    no validity read; outside the context a left-padded mask is refused as before."""
+    import torch
+    from audio_llama_b200 import llama_native as LN
+    right = torch.tensor([[1, 1, 1, 0], [1, 1, 1, 1]], dtype=torch.float32)
+    left = torch.tensor([[0, 1, 1, 1], [1, 1, 1, 1]], dtype=torch.float32)
+    ok, kv = LN.attention_plan(right)
+    assert ok and kv.tolist() == [3, 4]
+    ok, kv = LN.attention_plan(left)
+    assert not ok and kv is None
+    with LN.static_attention_plan():
+        ok, kv = LN.attention_plan(right)
+        assert ok and kv.dtype == torch.int32 and kv.tolist() == [3, 4]
+        assert LN.attention_plan(None) == (True, None)
+    assert not LN._STATIC_PLAN["on"]
+
