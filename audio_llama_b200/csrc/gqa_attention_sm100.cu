@@ -33,9 +33,8 @@ namespace al {
 constexpr int GQ_T = 128;                      // tile rows (queries or keys) and head_dim
 constexpr int GQ_TILE_BYTES = GQ_T * GQ_T * 2; // 32 KB: one 128 x 128 bf16 tile = two [128][64] SW128 boxes
 constexpr int GQ_BOX_BYTES = GQ_T * 64 * 2;    // 16 KB
-#ifndef GQ_SPLIT
-#define GQ_SPLIT 4                             // compute threads per tile row (2 or 4)
-#endif
+#define GQ_SPLIT 4                             // compute threads per query row of the forward (16 softmax warps: with 8 the
+                                               // exponent phase is latency-bound, tools/ncu_hot.py: 'wait' + 'branch' stalls)
 constexpr int GQ_CW = GQ_T / GQ_SPLIT;         // columns of a 128-wide tile row that one compute thread owns
 constexpr int GQ_COMPUTE = GQ_T * GQ_SPLIT;    // compute threads
 constexpr int GQ_THREADS = 128 + GQ_COMPUTE;   // warps 0-3 control (TMA, MMA, TMEM allocator, idle), then the compute warps
