@@ -170,12 +170,15 @@ class AudioConditioner:
     # ------------------------------------------------------------------ config 5: ragged clips, several spans per sample
     @torch.no_grad()
     def forward_ragged(self, wave: torch.Tensor, n_samples: torch.Tensor, spans_per_sample, input_ids: torch.Tensor,
-                       attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
+                       attention_mask: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None,
+                       n_samples_host=None):
         """EXTENSION (not in the reference, SURVEY.md §8 extension row). wave [n_clips, <=480000] fp32 with n_samples
         [n_clips] int32 valid samples (all clips of all samples, in sample order); spans_per_sample[b] = number of
         clips of sample b. Every clip is zero-padded to 30 s and encoded exactly as the reference would encode it
         (the encoder is never masked, HF modeling_whisper.py:607-610); only its first
         ((n // 160) - 1) // 2 + 1 encoder rows are kept and spliced as <audio> rows </audio> spans before the text.
+        n_samples_host: the same lengths as a host sequence (a dataloader has them); without it they are read back from
+        the device, which synchronises (the span layout and S_max are host decisions).
         Returns (inputs_embeds [B, S_max, d_l], mask fp32, labels | None, span_start int32 [B, max_spans])."""
         from .splice import encoder_rows_for_samples, splice_ragged
         n_clips = wave.shape[0]
@@ -186,7 +189,9 @@ class AudioConditioner:
         proj = torch.empty(n_clips, N_CTX, self.d_out, dtype=self.table.dtype, device=self.device)
         projector_forward_raw(self.pw, enc.view(n_clips * N_CTX, self.cfg.d_model), out=proj.view(n_clips * N_CTX, self.d_out),
                               rows_per_group=n_clips * N_CTX, out_group_stride=0, out_row_offset=0, cache=self._pcache)
-        lens = n_samples.tolist()
+        lens = list(n_samples_host) if n_samples_host is not None else n_samples.tolist()
+        if len(lens) != n_clips:
+            raise ValueError("n_samples_host must hold one length per clip")
         rows, i = [], 0
         for k in spans_per_sample:
             rows.append([encoder_rows_for_samples(n) for n in lens[i:i + k]])

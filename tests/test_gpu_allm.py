@@ -227,3 +227,7 @@ def test_pipeline_ragged_config5():
     _, _, total, S = O.ragged_layout([[p.shape[0] for p in ps] for ps in per_sample], T)
     for b in range(3):
         assert (out[b, total[b]:].cpu() == 0).all() and (m[b, total[b]:].cpu() == 0).all()   # right padding rows
+    # host-side lengths given: no device read-back, same result
+    out2, m2, lab2, starts2 = cond.forward_ragged(torch.from_numpy(buf).cuda(), torch.tensor(lens, dtype=torch.int32).cuda(),
+                                                  spans, ids.cuda(), mask.cuda(), labels.cuda(), n_samples_host=lens)
+    assert torch.equal(out2, out) and torch.equal(m2, m) and torch.equal(lab2, lab) and torch.equal(starts2, starts)
