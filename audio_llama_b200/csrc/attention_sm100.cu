@@ -172,8 +172,8 @@ static_assert(ATT_OFF_EXACT + 4 + 1024 <= ATT_SMEM, "shared-memory carve-up exce
 // straight from the accumulator values: the scale-and-subtract FFMA2 of every element pair disappears.
 template <bool QLOG2>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloat16* __restrict__ qkv,
-                     __nv_bfloat16* __restrict__ out, int T, int H) {
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmOut,
+                     const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int H) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = opaque_u32((smem_u32(smem_raw) + 1023u) & ~1023u);   // the one base register
 
@@ -190,6 +190,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
   if (warp == 0 && elect_one()) {
     const int d = H * ATT_HD, h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * ATT_BQ;
     tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmOut);
     for (uint32_t a = ATT_BAR_Q_FULL; a <= ATT_BAR_O_FULL; a += 8) mbar_init_a(sb + a, 1);
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(sb + ATT_OFF_EXACT), "r"(0u) : "memory");
     fence_barrier_init();
@@ -489,21 +490,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __nv_bfloa
     TR(27, nkv);
     const int d = H * ATT_HD, h = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * ATT_BQ;
     {
-      const int q = q0 + row;
-      uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * T + q) * d + h * ATT_HD + half * 32);
+      // The normalised tile leaves through ONE TMA store: each thread writes its 64 bytes into the Q buffer (dead since
+      // the last Q K^T ran) in the 128-byte-swizzled layout of the output map; rows >= T are clipped by the map. (Stored
+      // straight from the threads, each lane's 64 bytes go to a different 2.5 KB-strided row: 32 cache lines per
+      // instruction, ~1000 L1 tag cycles per tile.)
       uint32_t r[32];
       tmem_ld_32x32(tOP + 128, r);
       tmem_ld_wait();
-      if (q < T) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint4 v;
-          v.x = pack_bf16(__uint_as_float(r[8 * u]) * inv_l, __uint_as_float(r[8 * u + 1]) * inv_l);
-          v.y = pack_bf16(__uint_as_float(r[8 * u + 2]) * inv_l, __uint_as_float(r[8 * u + 3]) * inv_l);
-          v.z = pack_bf16(__uint_as_float(r[8 * u + 4]) * inv_l, __uint_as_float(r[8 * u + 5]) * inv_l);
-          v.w = pack_bf16(__uint_as_float(r[8 * u + 6]) * inv_l, __uint_as_float(r[8 * u + 7]) * inv_l);
-          dst[u] = v;
-        }
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v0 = pack_bf16(__uint_as_float(r[8 * u]) * inv_l, __uint_as_float(r[8 * u + 1]) * inv_l);
+        const uint32_t v1 = pack_bf16(__uint_as_float(r[8 * u + 2]) * inv_l, __uint_as_float(r[8 * u + 3]) * inv_l);
+        const uint32_t v2 = pack_bf16(__uint_as_float(r[8 * u + 4]) * inv_l, __uint_as_float(r[8 * u + 5]) * inv_l);
+        const uint32_t v3 = pack_bf16(__uint_as_float(r[8 * u + 6]) * inv_l, __uint_as_float(r[8 * u + 7]) * inv_l);
+        const uint32_t chunk = static_cast<uint32_t>(half * 4 + u);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(sb + ATT_OFF_Q + row * 128 + ((chunk ^ (row & 7)) << 4)), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(ATT_BAR_SOFTMAX, 256);
+      if (warp == 4 && elect_one()) {
+        tma_store_3d_a(&tmOut, sb + ATT_OFF_Q, h * ATT_HD, q0, b);
+        tma_commit_group();
+        if (exact) tma_wait_group<0>();            // the exact path below overwrites rows of this tile with plain stores
+        else tma_wait_group_read<0>();             // shared memory must outlive the read
       }
     }
     TR(28, nkv);
@@ -557,6 +568,17 @@ void att_trace_dump() {
 #endif
 
 int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int B, int T, int H, int q_log2, cudaStream_t stream) {
+  // output map [B][T][H * 64] bf16, box = one (128-row tile, head); rebuilt only when the buffer or the shape changes (the
+  // encoder plan calls this 32 times per step on the same buffer)
+  static thread_local struct { const void* out; int B, T, H; CUtensorMap tm; } oc = {nullptr, 0, 0, 0, {}};
+  if (oc.out != out || oc.B != B || oc.T != T || oc.H != H) {
+    const uint64_t dd = static_cast<uint64_t>(H) * ATT_HD;
+    const uint64_t dims[3] = {dd, static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    const uint64_t str[3] = {2, dd * 2, dd * 2 * static_cast<uint64_t>(T)};
+    const uint32_t box[3] = {ATT_HD, ATT_BQ, 1};
+    if (make_tmap(&oc.tm, out, 2, 3, dims, str, box, true) != 0) return -1;
+    oc.out = out; oc.B = B; oc.T = T; oc.H = H;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     AL_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -565,10 +587,10 @@ int launch_attention(const CUtensorMap& tm_qkv, const void* qkv, void* out, int 
   }
   dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
   if (q_log2)
-    attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
+    attention_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, oc.tm, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                                         reinterpret_cast<__nv_bfloat16*>(out), T, H);
   else
-    attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, reinterpret_cast<const __nv_bfloat16*>(qkv),
+    attention_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, oc.tm, reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                                          reinterpret_cast<__nv_bfloat16*>(out), T, H);
   AL_CHECK_CUDA(cudaGetLastError());
   return 0;
