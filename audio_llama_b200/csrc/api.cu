@@ -915,7 +915,15 @@ static int gemm_plain(const void* A, long long lda, int M, const void* W, long l
     const int per = (num_kb + ks - 1) / ks;
     p.k_splits = (num_kb + per - 1) / per;          // every slice non-empty
   }
-  rc = launch_gemm(ta, tb, to, p, flags, num_sms(), st);
+  if (flags & EPI_ADD_BF16) {                        // grad_in = the bf16 addend [M][grad_ld]: brought in by TMA (output map's box)
+    CUtensorMap tadd = to;
+    if (grad_in != out && (rc = tmap_rows3d(&tadd, grad_in, 2, N, M, 1, grad_ld, (uint64_t)M * grad_ld, gemm_out_box_cols(flags), 128)))
+      return rc;
+    p.K2 = 0;
+    rc = launch_gemm2_add(ta, tb, to, ta, tb, tadd, p, flags, num_sms(), st);
+  } else {
+    rc = launch_gemm(ta, tb, to, p, flags, num_sms(), st);
+  }
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -1069,9 +1077,11 @@ int al_lora_linear_forward_ex(const void* x, int rows, int in_dim, int out_dim, 
     return rc;
   GemmParams p{};
   p.m_per_batch = rows; p.batch = 1; p.N = out_dim; p.K = in_dim; p.K2 = rank; p.bias = bias;
-  p.grad_in = reinterpret_cast<const __nv_bfloat16*>(addend);
-  p.grad_ld = out_dim;
-  rc = launch_gemm2(ta, tb, to, ta2, tb2, p, flags, num_sms(), (cudaStream_t)stream);
+  CUtensorMap tadd = to;                             // the addend chunk arrives through TMA with the output map's box
+  if (addend != nullptr && addend != out &&
+      (rc = tmap_rows3d(&tadd, addend, 2, out_dim, rows, 1, out_dim, (uint64_t)rows * out_dim, gemm_out_box_cols(flags), 128)))
+    return rc;
+  rc = launch_gemm2_add(ta, tb, to, ta2, tb2, tadd, p, flags, num_sms(), (cudaStream_t)stream);
   if (rc == 0) g_launches += 1;
   return rc;
 }
@@ -1136,9 +1146,11 @@ int al_lora_linear_backward_ex(const void* x, const void* dy, int rows, int in_d
     if ((rc = tmap_rows3d(&to, dx, 2, in_dim, rows, 1, in_dim, (uint64_t)rows * in_dim, gemm_out_box_cols(0), 128))) return rc;
     GemmParams p{};
     p.m_per_batch = rows; p.batch = 1; p.N = in_dim; p.K = out_dim; p.K2 = rank;
-    p.grad_in = reinterpret_cast<const __nv_bfloat16*>(dx_addend);   // dx = ... + dx_addend (may be dx itself)
-    p.grad_ld = in_dim;
-    rc = launch_gemm2(ta, tb, to, ta2, tb2, p, dx_addend ? EPI_ADD_BF16 : 0, num_sms(), st);
+    CUtensorMap tadd = to;                           // dx = ... + dx_addend (may be dx itself: then the output map serves)
+    if (dx_addend != nullptr && dx_addend != dx &&
+        (rc = tmap_rows3d(&tadd, dx_addend, 2, in_dim, rows, 1, in_dim, (uint64_t)rows * in_dim, gemm_out_box_cols(0), 128)))
+      return rc;
+    rc = launch_gemm2_add(ta, tb, to, ta2, tb2, tadd, p, dx_addend ? EPI_ADD_BF16 : 0, num_sms(), st);
     if (rc) return rc;
     g_launches += 1;
   }

@@ -47,7 +47,7 @@ template <int FLAGS, bool CTA2>
 __global__ void __launch_bounds__(384, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmAdd, const GemmParams p) {
   constexpr int BN = 256;
   constexpr int STAGES = gemm_stages<CTA2>();
   constexpr bool OUT_F32 = (FLAGS & EPI_OUT_F32) != 0;
@@ -75,7 +75,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* addfull = tempty + 2;                // EPI_ADD_BF16: "addend chunk has landed", one per epilogue warpgroup
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(addfull + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,6 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
+      mbar_init(&addfull[a], 1);
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], CTA2 ? 512 : 256);   // (pair: the leader's collects both CTAs' epilogue threads)
     }
@@ -217,6 +219,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* rowp = stg + row * 128;
     int as = 0;
     uint32_t aph = 0;
+    uint32_t addph = 0;                           // phase of this warpgroup's addend barrier
+    if constexpr (ADD16) {
+      if (etid == 0) tma_prefetch_desc(&tmAdd);
+    }
     for (int t = worker; t < num_tiles; t += n_workers) {
       const int ot = t % out_tiles, split = t / out_tiles;
       const int nt = ot % p.tiles_n;
@@ -263,27 +269,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (DO_GELU) {
 #pragma unroll
           for (int j = 0; j < CH; j += 2) gelu_erf_fast2(v[j], v[j + 1]);
-        }
-        if constexpr (ADD16) {
-          // + a bf16 addend with the output's shape (possibly the output buffer itself: this CTA is the only reader and
-          // writer of the tile and reads it before its own TMA store -> plain coherent loads)
-          const __nv_bfloat16* ap = p.grad_in + (static_cast<size_t>(b) * p.m_per_batch + grow) * p.grad_ld + col0;
-#pragma unroll
-          for (int j = 0; j < CH; j += 8) {
-            if (fullc) {
-              const uint4 g = *reinterpret_cast<const uint4*>(ap + j);
-              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                v[j + 2 * q] += __uint_as_float(gw[q] << 16);
-                v[j + 2 * q + 1] += __uint_as_float(gw[q] & 0xffff0000u);
-              }
-            } else {
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                if (col0 + j + q < p.N) v[j + q] += __bfloat162float(ap[j + q]);
-            }
-          }
         }
         if constexpr (GELU_GRAD) {
           // backward of h = gelu(a): v holds the recomputed pre-activation a = x W1^T + b1; out = dh * gelu'(a),
@@ -341,8 +326,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         // stage into 128B-swizzled smem (row = 128 B; 16 B unit u of row r lives at u ^ (r & 7))
         // (bulk async-groups belong to the issuing thread: elect.sync with the full mask always elects the same lane)
-        if (etid < 32 && elect_one()) tma_wait_group_read<0>();   // this warpgroup's previous store has drained the buffer
-        named_bar_sync(1 + 2 * wg, 128);
+        if constexpr (ADD16) {
+          // + a bf16 addend with the output's shape (possibly the output buffer itself): its [128 rows][64 columns] chunk
+          // is brought by TMA into this warpgroup's staging buffer (coalesced, asynchronous -- read straight from the
+          // threads, each lane's 128 bytes of a different row cost 5 - 17 % of the GEMM), added in place row by row (a
+          // thread reads and writes only its own row), and the same buffer then leaves through the TMA store below.
+          const bool rows_live = m0 < p.m_per_batch;                // (pair: the peer's rows may lie wholly past the end)
+          if (rows_live) {
+            if (etid < 32 && elect_one()) {
+              tma_wait_group_read<0>();                             // this warpgroup's previous store has drained the buffer
+              mbar_arrive_expect_tx(&addfull[wg], STG_BYTES);
+              tma_load_3d(stg, &tmAdd, &addfull[wg], col0, m0, b);
+            }
+            mbar_wait(&addfull[wg], addph);
+            addph ^= 1;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const uint4 g = *reinterpret_cast<const uint4*>(rowp + ((u ^ (row & 7)) << 4));
+              const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[8 * u + 2 * q] += __uint_as_float(gw[q] << 16);
+                v[8 * u + 2 * q + 1] += __uint_as_float(gw[q] & 0xffff0000u);
+              }
+            }
+          } else {
+            if (etid < 32 && elect_one()) tma_wait_group_read<0>();
+            named_bar_sync(1 + 2 * wg, 128);
+          }
+        } else {
+          if (etid < 32 && elect_one()) tma_wait_group_read<0>();   // this warpgroup's previous store has drained the buffer
+          named_bar_sync(1 + 2 * wg, 128);
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           uint4 q;
@@ -393,7 +408,7 @@ void gemm_set_mode(int pair) { g_use_pair = pair ? 1 : 0; }
 
 template <int FLAGS, bool CTA2>
 static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
-                      const CUtensorMap& tmB2, const GemmParams& p, int num_sms, cudaStream_t stream) {
+                      const CUtensorMap& tmB2, const CUtensorMap& tmAdd, const GemmParams& p, int num_sms, cudaStream_t stream) {
   constexpr int smem = gemm_smem_bytes<CTA2>();
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<FLAGS, CTA2>;
@@ -420,7 +435,7 @@ static int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  AL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmA2, tmB2, p));
+  AL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, tmA2, tmB2, tmAdd, p));
   return 0;
 }
 
@@ -434,31 +449,37 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 
 template <int FLAGS>
 static int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
-                       const CUtensorMap& tmB2, const GemmParams& p, int num_sms, cudaStream_t stream) {
-  if (use_pair()) return launch_one<FLAGS, true>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
-  return launch_one<FLAGS, false>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+                       const CUtensorMap& tmB2, const CUtensorMap& tmAdd, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (use_pair()) return launch_one<FLAGS, true>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
+  return launch_one<FLAGS, false>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
 }
 
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                  const CUtensorMap& tmB2, GemmParams p, int flags, int num_sms, cudaStream_t stream) {
+  return launch_gemm2_add(tmA, tmB, tmO, tmA2, tmB2, tmO, p, flags, num_sms, stream);
+}
+
+// tmAdd: the EPI_ADD_BF16 addend, a bf16 matrix with the output's shape and the output map's box (it may BE the output)
+int launch_gemm2_add(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                     const CUtensorMap& tmB2, const CUtensorMap& tmAdd, GemmParams p, int flags, int num_sms, cudaStream_t stream) {
   p.tiles_m_per_batch = 0;   // (derived in the kernel from the tile height of the chosen form)
   p.tiles_n = (p.N + 255) / 256;
   switch (flags) {
-    case 0: return launch_mode<0>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
-    case EPI_GELU: return launch_mode<EPI_GELU>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
-    case EPI_OUT_F32: return launch_mode<EPI_OUT_F32>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+    case 0: return launch_mode<0>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
+    case EPI_GELU: return launch_mode<EPI_GELU>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
+    case EPI_OUT_F32: return launch_mode<EPI_OUT_F32>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_REDUCE_ADD:
-      return launch_mode<EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_RESIDUAL:
-      return launch_mode<EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_RESIDUAL>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX:
-      return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_OUT_F32 | EPI_GELU | EPI_ROWAUX>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_GELU_GRAD:
-      return launch_mode<EPI_GELU_GRAD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_GELU_GRAD>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_ADD_BF16:
-      return launch_mode<EPI_ADD_BF16>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_ADD_BF16>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     case EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD:
-      return launch_mode<EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, p, num_sms, stream);
+      return launch_mode<EPI_TN | EPI_OUT_F32 | EPI_REDUCE_ADD>(tmA, tmB, tmO, tmA2, tmB2, tmAdd, p, num_sms, stream);
     default:
       set_error("launch_gemm: unsupported epilogue flags %d", flags);
       return -1;

@@ -17,7 +17,8 @@ enum GemmEpilogue : int {
   EPI_GELU_GRAD = 32,   // out = grad_in[row][col] * gelu'(acc + bias)  (backward of a Linear+GELU, recomputed)
   EPI_TN = 64,          // operand layout, not an epilogue: out = A_src^T W_src with A_src [K][M], W_src [K][N] row-major
   EPI_ADD_BF16 = 128,   // + addend[row][col] (bf16 rows of grad_ld elements through grad_in; may alias a bf16 out: residual
-                        //   adds and gradient accumulation of the LLaMA layers without a separate elementwise pass)
+                        //   adds and gradient accumulation of the LLaMA layers without a separate elementwise pass); the addend's tensor map is
+                        //   passed to launch_gemm2_add, its chunks arrive through TMA
                         // (contraction over the ROWS: weight gradients); both operands are staged MN-major
 };
 
@@ -47,6 +48,8 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 // out = epilogue(A W^T + A2 W2^T + bias): second operand pair over p.K2, same accumulator (fused LoRA update).
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                  const CUtensorMap& tmB2, GemmParams p, int flags, int num_sms, cudaStream_t stream);
+int launch_gemm2_add(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                     const CUtensorMap& tmB2, const CUtensorMap& tmAdd, GemmParams p, int flags, int num_sms, cudaStream_t stream);
 
 // ------------------------------------------------------------------ attention (attention_sm100.cu)
 // qkv: [B][T][3*H*64] bf16 (q pre-scaled), out: [B][T][H*64] bf16. tm_qkv: 3-D map, box {64,128,1}, SW128.
